@@ -1,0 +1,196 @@
+/*
+ * spurfies_b200.h -- C ABI of libspurfies_b200.so (hand-written sm_100a kernels).
+ *
+ * This is the drop-in boundary for the reference's per-ray hot path.  Every entry point takes
+ * raw DEVICE pointers, sizes, scalars and a cudaStream_t (passed as void*), returns 0 on success
+ * or a negative spf_status, never allocates, never synchronises, and is re-entrant per stream.
+ * The caller (the Python mirrors of torch_knnquery.VoxelGrid / PointVolSDF) owns all memory.
+ *
+ * Reference interfaces replaced (paths relative to kevinYitshak/spurfies @ 858a95f):
+ *   torch_knnquery/src/knnquery.cu:570-577   pybind module `knnquery_cuda` (6 functions)
+ *   torch_knnquery/torch_knnquery/knnquery.py:52-164, 168-285   VoxelGrid.set_pointset / query
+ *   spurfies/model/utils.py:90-183, 221-281  query / get_keypoint_data / tv_regul glue
+ *   spurfies/model/pointneus_disent.py:207-247, 300-346, 894-908  filter_points, compute_weights,
+ *                                            get_sdf, get_gradients, get_color, volume_rendering
+ *   spurfies/model/density.py:21-30          LaplaceDensity
+ *   spurfies/model/ray_sampler.py:34-59, 377-588  UniformSampler / ErrorBoundSampler_pn
+ * The ctypes binding a maintainer would add on the reference side is shown in INTEGRATION.md.
+ */
+#ifndef SPURFIES_B200_H
+#define SPURFIES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SPF_OK = 0,
+  SPF_ERR_INVALID = -1,     /* bad argument (null pointer, K > 20, ...) */
+  SPF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were written for */
+  SPF_ERR_WORKSPACE = -3,   /* workspace too small */
+  SPF_ERR_CUDA = -4         /* a CUDA runtime call / launch failed (see spf_last_cuda_error) */
+} spf_status;
+
+/* Voxel grid over the neural points in the REFERENCE geometry (knnquery.py:66-88): replaces the
+ * five tensors coor_occ / coor_2_occ / occ_2_coor / occ_2_pnts / occ_numpnts (knnquery.py:92-97)
+ * with a CSR of cell-sorted points plus the kernel_size-dilated occupancy.  All pointers device. */
+typedef struct {
+  float shift[3];           /* grid origin  (knnquery.py:88 d_coord_shift) */
+  float vsize[3];           /* scaled voxel edge (knnquery.py:35) */
+  int32_t dim[3];           /* scaled_vdim (knnquery.py:81) */
+  int32_t ks[3];            /* kernel_size */
+  int32_t n_points;
+  int32_t n_cells;          /* dim[0]*dim[1]*dim[2] */
+  const int32_t* cell_start;   /* [n_cells+1] */
+  const float* sorted;         /* [n_in_grid][4]  x,y,z,point-id-bits, grouped by cell */
+  const uint8_t* hit;          /* [n_cells] dilated occupancy (knnquery.cu:85-120) */
+} spf_grid;
+
+const char* spf_version(void);
+const char* spf_last_cuda_error(void);
+
+/* ---- a1: VoxelGrid.set_pointset (knnquery.py:52-164; knnquery.cu:22-168) ------------------- */
+size_t spf_grid_workspace_bytes(int32_t n_points, int32_t n_cells);
+/* Fills cell_start / sorted / hit of `g` (whose scalar fields the caller set).
+ * stats[0]=#occupied voxels, [1]=max points in a voxel, [2]=#points inside the grid. */
+int spf_grid_build(const spf_grid* g, const float* points /*[N,3]*/, int32_t* cell_start, float* sorted,
+                   uint8_t* hit, int32_t* stats /*[4]*/, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2: mask + per-ray slots (knnquery.cu:171-221; knnquery.py:208-231) ------------------- */
+int spf_mask_slots(const spf_grid* g, const float* raypos /*[R,D,3]*/, int32_t R, int32_t D, int32_t Smax,
+                   int32_t* slot_sample /*[R,Smax]*/, float* sample_loc /*[R,Smax,3]*/, int32_t* n_slots /*[R]*/,
+                   void* stream);
+/* ---- a3: kNN per slot (knnquery.cu:224-308). pidx sorted by (d2, id), -1 padded.
+ * ray_nvalid[r] = number of slots of ray r with >= 1 neighbour (knnquery.py:272-280). */
+int spf_knn_slots(const spf_grid* g, const float* sample_loc, const int32_t* n_slots, int32_t R, int32_t Smax,
+                  int32_t K, float radius2, int32_t* pidx /*[R,Smax,K]*/, int32_t* ray_nvalid /*[R]*/, void* stream);
+/* a2+a3 fused for point queries (D = 1, Smax = 1: sdf_importance / get_sdf_eval / pseudo_sdf / tv_regul). */
+int spf_knn_points(const spf_grid* g, const float* q /*[Q,3]*/, int64_t Q, int32_t K, float radius2,
+                   int32_t* pidx /*[Q,K]*/, void* stream);
+/* mask only (knnquery.cu:171-196) */
+int spf_mask_points(const spf_grid* g, const float* q, int64_t Q, int32_t* mask, void* stream);
+
+/* ---- a4: compaction of valid slots (utils.py:90-113 masked_select glue), no host sync.
+ * valid(i) := pidx[i*K] >= 0.  list[0..count) = valid i ascending; count stays on the device. */
+size_t spf_compact_workspace_bytes(int64_t n);
+int spf_compact_valid(const int32_t* pidx, int64_t n, int32_t K, int32_t* list /*[n]*/, int32_t* count /*[1]*/,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a11 (first half): filter_points (pointneus_disent.py:207-239): t, delta, recomputed x --- */
+int spf_ray_prep(const float* sample_loc /*[R,Smax,3]*/, const int32_t* pidx, const float* cam_loc /*[3]*/,
+                 const float* ray_dirs /*[R,3]*/, int32_t R, int32_t Smax, int32_t K, float* t /*[R,Smax]*/,
+                 float* delta /*[R,Smax]*/, float* x_new /*[R,Smax,3]*/, void* stream);
+
+/* ---- a5-a8: gather + RBF weights + frozen geometry MLP (+ d sdf / d input) -------------------
+ * Packed weights (see spurfies_b200/packing.py): fp32 mode: per layer Wt [Kin][256] then bias[256].
+ * Rows are (slot, neighbour) pairs; slots come from `list`/`count` (spf_compact_valid).
+ * Outputs are indexed by slot:  sdf[slot] (untouched where invalid), grad[slot][3] = d sdf / d x.
+ * If jw != NULL: jw[(v*K+k)][32] = w_k/norm * d sdf_k / d latent (v = position in `list`), which is
+ * everything the backward needs (frozen weights, detached RBF weights). */
+typedef struct {
+  const float* w1t; const float* b1;   /* [35][256], [256]  F_geometry.0 */
+  const float* w2t; const float* b2;   /* [256][256]        F_geometry.2 */
+  const float* w3t; const float* b3;   /*                   F_geometry.4 */
+  const float* w4t; const float* b4;   /*                   F_geometry.6 */
+  const float* v5;  float c5;          /* folded F_geometry.8 + T: sdf = v5 . h4 + c5 */
+  const float* w1; const float* w2; const float* w3; const float* w4; /* [out][in] originals for the J pass */
+} spf_geo_weights_f32;
+
+int spf_sdf_fwd_f32(const spf_geo_weights_f32* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                    const float* x /*[n,3] by slot*/, const int32_t* pidx /*[n,K]*/, int32_t K,
+                    const float* pts /*[N,3]*/, const float* feat_g /*[N,32]*/, float rbf,
+                    float* sdf /*[n]*/, float* grad /*[n,3] or NULL*/, float* jw /*[n*K,32] or NULL*/, void* stream);
+/* backward: feat_g_grad[p] += d_sdf[slot] * jw[row]  (warp-aggregated vector atomics) */
+int spf_sdf_bwd(const int32_t* list, const int32_t* count, int64_t n_max, const int32_t* pidx, int32_t K,
+                const float* jw, const float* d_sdf /*[n] by slot*/, float* feat_g_grad /*[N,32]*/, void* stream);
+
+/* ---- a9: colour field (per pair) and radiance head (per sample), fp32 mode ------------------ */
+typedef struct {
+  const float* w1t; const float* b1;   /* [103][256] F_color.0 ; input = [PE6(x-p) (39) | feat_c (64)] */
+  const float* w2t; const float* b2;   /* F_color.2 */
+  const float* w3t; const float* b3;   /* F_color.4 */
+  const float* w1; const float* w2; const float* w3; /* [out][in] originals for dgrad */
+} spf_color_weights_f32;
+/* hbar[slot][256] = sum_k w_k/norm * h3_k  (F_color.6 is linear, so it is applied per sample in the head).
+ * Saved for backward (indexed by compact pair row v*K+k): in0 [.,104], h1, h2 [.,256], m3 [.,8] sign bits, wn [.] */
+int spf_color_fwd_f32(const spf_color_weights_f32* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                      const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c,
+                      float rbf, float* hbar, float* in0, float* h1, float* h2, uint32_t* m3, float* wn,
+                      void* stream);
+int spf_color_bwd_f32(const spf_color_weights_f32* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                      const int32_t* pidx, int32_t K, const float* d_hbar /*[n,256] by slot*/,
+                      const float* h1, const float* h2, const uint32_t* m3, const float* wn,
+                      float* dz1, float* dz2, float* dz3 /*[n*K,256] compact rows*/, float* feat_c_grad /*[N,64]*/,
+                      void* stream);
+
+typedef struct {
+  const float* w4t; const float* b4;   /* [256][256] F_color.6 (no activation) */
+  const float* r1t; const float* rb1;  /* [277][256] R.0 ; input = [PE3(dir) (21) | f (256)] */
+  const float* r2t; const float* rb2;  /* R.2 */
+  const float* r3t; const float* rb3;  /* [256][3]   R.4 (then sigmoid) */
+  const float* w4; const float* r1; const float* r2; const float* r3; /* [out][in] originals */
+} spf_head_weights_f32;
+/* rgb[slot][3]; saved (compact sample rows v): f [.,256], a1, a2 [.,256] */
+int spf_head_fwd_f32(const spf_head_weights_f32* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                     const float* hbar, const float* ray_dirs /*[R,3]*/, int32_t Smax, float* rgb,
+                     float* f, float* a1, float* a2, void* stream);
+/* d_hbar[slot][256]; dz rows (compact v): dzf [.,256] (grad wrt F_color.6 output), dz1, dz2 [.,256], dz3 [.,4] */
+int spf_head_bwd_f32(const spf_head_weights_f32* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                     const float* d_rgb /*[n,3] by slot*/, const float* rgb, const float* a1, const float* a2,
+                     float* d_hbar, float* dzf, float* dz1, float* dz2, float* dz3, void* stream);
+
+/* ---- a10 + a11: Laplace density + alpha compositing (density.py:21-30; pointneus_disent.py:894-908, 765-795)
+ * Dense per-ray layout [R,Smax]; a slot is valid iff pidx[slot*K] >= 0.  ray_nvalid[r]==0 -> the ray is
+ * "not hit" and gets the reference's fill values (pointneus_disent.py:817-854). */
+int spf_composite_fwd(const float* sdf, const float* delta, const float* t, const float* rgb_s /*[R,Smax,3]*/,
+                      const float* grad /*[R,Smax,3] or NULL*/, const int32_t* pidx, int32_t K,
+                      const int32_t* ray_nvalid, const float* beta /*[1] device: |beta_p|+beta_min*/,
+                      int32_t R, int32_t Smax, float* weights /*[R,Smax]*/, float* rgb /*[R,3]*/,
+                      float* depth /*[R]*/, float* acc /*[R]*/, float* dist /*[R]*/, float* normal /*[R,3] or NULL*/,
+                      void* stream);
+int spf_composite_bwd(const float* sdf, const float* delta, const float* t, const float* rgb_s,
+                      const int32_t* pidx, int32_t K, const int32_t* ray_nvalid, const float* beta,
+                      int32_t R, int32_t Smax, const float* weights,
+                      const float* d_weights /*[R,Smax] or NULL*/, const float* d_rgb /*[R,3] or NULL*/,
+                      const float* d_depth /*[R] or NULL*/, const float* d_dist /*[R] or NULL*/,
+                      float* d_sdf /*[R,Smax]*/, float* d_rgb_s /*[R,Smax,3]*/, float* d_beta /*[1], accumulated*/,
+                      void* stream);
+
+/* ---- a12: sampler (ray_sampler.py:34-59, 377-588) ------------------------------------------- */
+/* coarse z (+ stratified jitter if t_rand != NULL) and sample positions */
+int spf_sampler_coarse(const float* t_vals /*[M] linspace(0,1,M)*/, const float* t_rand /*[R,M] or NULL*/,
+                       float near, float far, const float* cam_loc /*[3]*/, const float* ray_dirs /*[R,3]*/,
+                       int32_t R, int32_t M, float* z /*[R,M]*/, float* points /*[R,M,3]*/, void* stream);
+/* one iteration of Algorithm 1 given z,sdf [R,M]: d*, beta bisection, weights, inverse-CDF draw.
+ * final != 0: pdf = weights+1e-5, N draws with u (u [R,N] or u_lin [N]); z_out [R, N+2+n_extra] sorted
+ *             (extras: near, far, z[:, extra_idx]).
+ * final == 0: pdf = error-bound opacity, N draws with u_lin; outputs new samples [R,N] + their points.
+ * beta_io [R] in/out; beta0 from *beta_dev; flag_not_converged[0] |= (max beta > beta0). */
+int spf_sampler_iter(const float* z, const float* sdf, int32_t R, int32_t M, const float* beta_dev, float eps,
+                     int32_t beta_iters, float bound_coef, float add_tiny, int32_t first_iter, float* beta_io,
+                     int32_t final, int32_t N, const float* u /*[R,N] or NULL*/, const float* u_lin /*[N]*/,
+                     float near, float far, const int32_t* extra_idx /*[n_extra]*/, int32_t n_extra,
+                     const float* cam_loc, const float* ray_dirs, float* out_z /*final: [R,N+2+n_extra]; else [R,N]*/,
+                     float* out_points /*[R,cols,3]*/, int32_t* flag_not_converged, void* stream);
+/* merge sorted z [R,M] (+sdf) with new sorted samples [R,N] (+sdf) -> [R,M+N] (ray_sampler.py:405-415, 533) */
+int spf_sampler_merge(const float* z, const float* sdf, int32_t M, const float* zs, const float* sdf_s, int32_t N,
+                      int32_t R, float* z_out, float* sdf_out, void* stream);
+
+/* ---- a13: tv_regul (utils.py:221-281) on cached self-kNN lists ------------------------------ */
+/* value[0] = mean_i( sum_j w_ij |f_j - f_i|_1 / sum_j w_ij ); grad (optional) = d value / d feat_g */
+int spf_tv_fwd_bwd(const float* pts, const float* feat_g /*[N,32]*/, const int32_t* self_pidx /*[N,K]*/,
+                   int32_t N, int32_t K, float* value /*[1]*/, float* grad /*[N,32] or NULL (accumulated)*/,
+                   float grad_scale, void* stream);
+
+/* ---- a15: rays (rend_util.py:60-95, 143-156) ------------------------------------------------ */
+int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, const float* intrinsics /*[4,4]*/,
+                    int32_t R, float* ray_dirs /*[R,3]*/, float* cam_loc /*[3]*/, float* depth_scale /*[R]*/,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPURFIES_B200_H */

@@ -1,0 +1,117 @@
+"""ctypes binding of libspurfies_b200.so (include/spurfies_b200.h).  No CPU fallback: if the library is
+missing and cannot be built, importing this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .build import LIB, build_library
+
+_here = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load():
+    path = LIB
+    if not os.path.exists(path):
+        path = build_library()
+    return C.CDLL(path)
+
+
+lib = _load()
+
+
+class SpfGrid(C.Structure):
+    _fields_ = [("shift", C.c_float * 3), ("vsize", C.c_float * 3), ("dim", C.c_int32 * 3), ("ks", C.c_int32 * 3),
+                ("n_points", C.c_int32), ("n_cells", C.c_int32), ("cell_start", C.c_void_p), ("sorted", C.c_void_p),
+                ("hit", C.c_void_p)]
+
+
+class GeoWeightsF32(C.Structure):
+    _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+                ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w4t", C.c_void_p), ("b4", C.c_void_p),
+                ("v5", C.c_void_p), ("c5", C.c_float),
+                ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p), ("w4", C.c_void_p)]
+
+
+class ColorWeightsF32(C.Structure):
+    _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+                ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p)]
+
+
+class HeadWeightsF32(C.Structure):
+    _fields_ = [("w4t", C.c_void_p), ("b4", C.c_void_p), ("r1t", C.c_void_p), ("rb1", C.c_void_p),
+                ("r2t", C.c_void_p), ("rb2", C.c_void_p), ("r3t", C.c_void_p), ("rb3", C.c_void_p),
+                ("w4", C.c_void_p), ("r1", C.c_void_p), ("r2", C.c_void_p), ("r3", C.c_void_p)]
+
+
+lib.spf_version.restype = C.c_char_p
+lib.spf_last_cuda_error.restype = C.c_char_p
+lib.spf_grid_workspace_bytes.restype = C.c_size_t
+lib.spf_grid_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+lib.spf_compact_workspace_bytes.restype = C.c_size_t
+lib.spf_compact_workspace_bytes.argtypes = [C.c_int64]
+
+_P, _I, _L, _F, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+_SIGS = {
+    "spf_grid_build": [_P, _P, _P, _P, _P, _P, _P, _Z, _P],
+    "spf_mask_slots": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "spf_knn_slots": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "spf_knn_points": [_P, _P, _L, _I, _F, _P, _P],
+    "spf_mask_points": [_P, _P, _L, _P, _P],
+    "spf_compact_valid": [_P, _L, _I, _P, _P, _P, _Z, _P],
+    "spf_ray_prep": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "spf_sdf_fwd_f32": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
+    "spf_sdf_bwd": [_P, _P, _L, _P, _I, _P, _P, _P, _P],
+    "spf_color_fwd_f32": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "spf_color_bwd_f32": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spf_head_fwd_f32": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _P, _P, _P],
+    "spf_head_bwd_f32": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spf_composite_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "spf_composite_bwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spf_sampler_coarse": [_P, _P, _F, _F, _P, _P, _I, _I, _P, _P, _P],
+    "spf_sampler_iter": [_P, _P, _I, _I, _P, _F, _I, _F, _F, _I, _P, _I, _I, _P, _P, _F, _F, _P, _I, _P, _P, _P, _P,
+                         _P, _P],
+    "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
+    "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
+    "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
+}
+for _n, _a in _SIGS.items():
+    _f = getattr(lib, _n)
+    _f.restype = C.c_int
+    _f.argtypes = _a
+
+EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes", *_SIGS]
+
+
+class SpfError(RuntimeError):
+    pass
+
+
+_CODES = {-1: "SPF_ERR_INVALID", -2: "SPF_ERR_UNSUPPORTED", -3: "SPF_ERR_WORKSPACE", -4: "SPF_ERR_CUDA"}
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL). Tensors must be CUDA + contiguous, like the reference
+    extension requires (torch_knnquery/src/knnquery.cu:13-15)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SpfError("tensor must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise SpfError("tensor is not contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = _CODES.get(rc, str(rc))
+        if rc == -4:
+            msg += ": " + lib.spf_last_cuda_error().decode()
+        raise SpfError(f"{name} failed: {msg}")

@@ -1,0 +1,633 @@
+// render.cu -- per-ray kernels: camera rays, filter_points (t / delta), Laplace density + alpha
+// compositing (fwd + bwd), VolSDF error-bounded sampler, TV regulariser.
+//
+// All of these are memory / latency bound segmented scans: ONE WARP PER RAY, lanes strided over the
+// ray's samples, prefix sums by warp shuffles, no intermediate tensors (the reference issues ~150
+// tiny torch kernels per sampler iteration and a dozen per compositing call).
+// Compiled with -fmad=false so that every fp32 operation rounds exactly like the reference's
+// separate torch ops (mul, add, div as individual kernels).
+#include <math.h>
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// a15: camera rays (spurfies/utils/rend_util.py:60-95, 143-156), pose-matrix branch, B = 1
+// ------------------------------------------------------------------------------------------------
+__global__ void k_camera_rays(const float* __restrict__ uv, const float* __restrict__ pose,
+                              const float* __restrict__ K, int R, float* __restrict__ dirs,
+                              float* __restrict__ cam_loc, float* __restrict__ depth_scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { cam_loc[0] = pose[3]; cam_loc[1] = pose[7]; cam_loc[2] = pose[11]; }
+  if (i >= R) return;
+  float fx = K[0], fy = K[5], cx = K[2], cy = K[6], sk = K[1];
+  float x = uv[2 * i], y = uv[2 * i + 1];
+  // lift (rend_util.py:143-156), z = 1
+  float xl = (x - cx + cy * sk / fy - sk * y / fy) / fx * 1.0f;
+  float yl = (y - cy) / fy * 1.0f;
+  float zl = 1.0f;
+  float o[3] = {pose[3], pose[7], pose[11]};
+  float w[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) w[a] = pose[4 * a] * xl + pose[4 * a + 1] * yl + pose[4 * a + 2] * zl + o[a];
+  float d[3] = {w[0] - o[0], w[1] - o[1], w[2] - o[2]};
+  float n = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);  // F.normalize
+  dirs[3 * i] = d[0] / n; dirs[3 * i + 1] = d[1] / n; dirs[3 * i + 2] = d[2] / n;
+  // depth_scale = z of the normalised camera-frame direction (pointneus_disent.py:642-645)
+  float nc = fmaxf(sqrtf(xl * xl + yl * yl + zl * zl), 1e-12f);
+  depth_scale[i] = zl / nc;
+}
+
+extern "C" int spf_camera_rays(const float* uv, const float* pose, const float* intrinsics, int32_t R,
+                               float* ray_dirs, float* cam_loc, float* depth_scale, void* stream_) {
+  if (!uv || !pose || !intrinsics || !ray_dirs || !cam_loc || !depth_scale) return SPF_ERR_INVALID;
+  int n = R > 0 ? R : 1;
+  k_camera_rays<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(uv, pose, intrinsics, R, ray_dirs, cam_loc,
+                                                                     depth_scale);
+  SPF_CHECK_LAUNCH("k_camera_rays");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a11a: filter_points (pointneus_disent.py:207-239)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float slot_t(const float* __restrict__ loc, bool valid, const float o[3], const float d[3]) {
+  if (!valid) return 0.0f;
+  float s = 0.0f;
+  int c = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float q = (loc[a] - o[a]) / d[a];  // IEEE division; 0/0 -> NaN dropped by nanmean, x/0 -> inf kept
+    if (!isnan(q)) { s += q; c++; }
+  }
+  return s / (float)c;
+}
+
+__global__ void k_ray_prep(const float* __restrict__ sample_loc, const int* __restrict__ pidx,
+                           const float* __restrict__ cam_loc, const float* __restrict__ ray_dirs, int R, int Smax,
+                           int K, float* __restrict__ t_out, float* __restrict__ delta, float* __restrict__ x_new) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float o[3] = {cam_loc[0], cam_loc[1], cam_loc[2]};
+  float d[3] = {ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2]};
+  for (int s = lane; s < Smax; s += 32) {
+    size_t i = (size_t)r * Smax + s;
+    bool v = pidx[i * K] >= 0;
+    float t = slot_t(sample_loc + 3 * i, v, o, d);
+    float tn = 0.0f;
+    if (s + 1 < Smax) tn = slot_t(sample_loc + 3 * (i + 1), pidx[(i + 1) * K] >= 0, o, d);
+    t_out[i] = t;
+    delta[i] = v ? fmaxf(tn - t, 0.0f) : 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) x_new[3 * i + a] = v ? o[a] + t * d[a] : 0.0f;
+  }
+}
+
+extern "C" int spf_ray_prep(const float* sample_loc, const int32_t* pidx, const float* cam_loc,
+                            const float* ray_dirs, int32_t R, int32_t Smax, int32_t K, float* t, float* delta,
+                            float* x_new, void* stream_) {
+  if (!sample_loc || !pidx || !cam_loc || !ray_dirs || !t || !delta || !x_new) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  k_ray_prep<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(sample_loc, pidx, cam_loc, ray_dirs, R, Smax, K, t,
+                                                             delta, x_new);
+  SPF_CHECK_LAUNCH("k_ray_prep");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10: Laplace density (density.py:21-26) and its partials
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgnf(float s) { return (s > 0.0f) ? 1.0f : ((s < 0.0f) ? -1.0f : 0.0f); }
+__device__ __forceinline__ float laplace_density(float s, float beta) {
+  float alpha = 1.0f / beta;
+  return alpha * (0.5f + 0.5f * sgnf(s) * expm1f(-fabsf(s) / beta));
+}
+
+#define MAX_CHUNKS 4  // Smax <= 128
+
+// ------------------------------------------------------------------------------------------------
+// a11b: compositing forward (pointneus_disent.py:894-908, 765-807)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_composite_fwd(const float* __restrict__ sdf, const float* __restrict__ delta,
+                                const float* __restrict__ t, const float* __restrict__ rgb_s,
+                                const float* __restrict__ grad, const int* __restrict__ pidx, int K,
+                                const int* __restrict__ ray_nvalid, const float* __restrict__ beta_p, int R, int Smax,
+                                float* __restrict__ weights, float* __restrict__ rgb, float* __restrict__ depth,
+                                float* __restrict__ acc, float* __restrict__ dist, float* __restrict__ normal) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  if (ray_nvalid[r] <= 0) {  // pointneus_disent.py:817-835 fill values
+    for (int s = lane; s < Smax; s += 32) weights[(size_t)r * Smax + s] = 0.0f;
+    if (lane < 3) { rgb[3 * r + lane] = 0.0f; if (normal) normal[3 * r + lane] = 0.0f; }
+    if (lane == 0) { depth[r] = 1.0f; acc[r] = 0.0f; dist[r] = 0.0f; }
+    return;
+  }
+  const float beta = beta_p[0];
+  float carry = 0.0f;
+  float sw = 0.f, swt = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sn0 = 0.f, sn1 = 0.f, sn2 = 0.f;
+  float wloc[MAX_CHUNKS], tloc[MAX_CHUNKS];
+  int nch = (Smax + 31) >> 5;
+  for (int c = 0; c < nch; ++c) {
+    int s = c * 32 + lane;
+    size_t i = (size_t)r * Smax + s;
+    bool v = s < Smax && pidx[i * K] >= 0;
+    float E = 0.0f, ti = 0.0f;
+    if (v) { E = delta[i] * laplace_density(sdf[i], beta); ti = t[i]; }
+    float inc = warp_scan_incl(E, lane);
+    float excl = carry + (inc - E);
+    float T = expf(-excl);
+    float alpha = 1.0f - expf(-E);
+    float w = alpha * T;
+    carry += __shfl_sync(SPF_FULL, inc, 31);
+    wloc[c] = w; tloc[c] = ti;
+    if (s < Smax) weights[i] = w;
+    if (v) {
+      sw += w; swt += w * ti;
+      sc0 += w * rgb_s[3 * i]; sc1 += w * rgb_s[3 * i + 1]; sc2 += w * rgb_s[3 * i + 2];
+      if (normal && grad) {
+        float gx = grad[3 * i], gy = grad[3 * i + 1], gz = grad[3 * i + 2];
+        float gn = sqrtf(gx * gx + gy * gy + gz * gz);  // pointneus_disent.py:805 (no eps)
+        sn0 += w * (gx / gn); sn1 += w * (gy / gn); sn2 += w * (gz / gn);
+      }
+    }
+  }
+  sw = warp_sum(sw); swt = warp_sum(swt);
+  sc0 = warp_sum(sc0); sc1 = warp_sum(sc1); sc2 = warp_sum(sc2);
+  // dist_map = sum( w/(sum w + 1e-10) * t )  (pointneus_disent.py:765-770)
+  float dm = 0.0f;
+  float den = sw + 1e-10f;
+  for (int c = 0; c < nch; ++c) dm += wloc[c] / den * tloc[c];
+  dm = warp_sum(dm);
+  if (normal) { sn0 = warp_sum(sn0); sn1 = warp_sum(sn1); sn2 = warp_sum(sn2); }
+  if (lane == 0) {
+    rgb[3 * r] = sc0; rgb[3 * r + 1] = sc1; rgb[3 * r + 2] = sc2;
+    depth[r] = swt / (sw + 1e-8f);
+    acc[r] = sw;
+    dist[r] = dm;
+    if (normal) { normal[3 * r] = sn0; normal[3 * r + 1] = sn1; normal[3 * r + 2] = sn2; }
+  }
+}
+
+extern "C" int spf_composite_fwd(const float* sdf, const float* delta, const float* t, const float* rgb_s,
+                                 const float* grad, const int32_t* pidx, int32_t K, const int32_t* ray_nvalid,
+                                 const float* beta, int32_t R, int32_t Smax, float* weights, float* rgb, float* depth,
+                                 float* acc, float* dist, float* normal, void* stream_) {
+  if (!sdf || !delta || !t || !rgb_s || !pidx || !ray_nvalid || !beta || !weights || !rgb || !depth || !acc || !dist)
+    return SPF_ERR_INVALID;
+  if (Smax > 32 * MAX_CHUNKS) return SPF_ERR_UNSUPPORTED;
+  if (R <= 0) return SPF_OK;
+  k_composite_fwd<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(sdf, delta, t, rgb_s, grad, pidx, K, ray_nvalid,
+                                                                  beta, R, Smax, weights, rgb, depth, acc, dist,
+                                                                  normal);
+  SPF_CHECK_LAUNCH("k_composite_fwd");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a11c: compositing + density backward
+//   E_i = delta_i sigma_i, T_i = exp(-sum_{j<i} E_j), w_i = (1-e^{-E_i}) T_i
+//   dL/dE_k = g_k (T_k - w_k) - sum_{i>k} g_i w_i ,  g_i = total dL/dw_i
+// ------------------------------------------------------------------------------------------------
+__global__ void k_composite_bwd(const float* __restrict__ sdf, const float* __restrict__ delta,
+                                const float* __restrict__ t, const float* __restrict__ rgb_s,
+                                const int* __restrict__ pidx, int K, const int* __restrict__ ray_nvalid,
+                                const float* __restrict__ beta_p, int R, int Smax, const float* __restrict__ weights,
+                                const float* __restrict__ d_weights, const float* __restrict__ d_rgb,
+                                const float* __restrict__ d_depth, const float* __restrict__ d_dist,
+                                float* __restrict__ d_sdf, float* __restrict__ d_rgb_s, float* __restrict__ d_beta) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  float dbeta_acc = 0.0f;
+  if (r < R) {
+    int nch = (Smax + 31) >> 5;
+    if (ray_nvalid[r] <= 0) {
+      for (int s = lane; s < Smax; s += 32) {
+        size_t i = (size_t)r * Smax + s;
+        d_sdf[i] = 0.0f;
+        d_rgb_s[3 * i] = 0.f; d_rgb_s[3 * i + 1] = 0.f; d_rgb_s[3 * i + 2] = 0.f;
+      }
+    } else {
+      const float beta = beta_p[0];
+      float dr0 = d_rgb ? d_rgb[3 * r] : 0.f, dr1 = d_rgb ? d_rgb[3 * r + 1] : 0.f, dr2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
+      float dd = d_depth ? d_depth[r] : 0.f, dm = d_dist ? d_dist[r] : 0.f;
+      float Tl[MAX_CHUNKS], wl[MAX_CHUNKS], gl[MAX_CHUNKS];
+      float carry = 0.0f, A = 0.0f, B = 0.0f;
+      for (int c = 0; c < nch; ++c) {
+        int s = c * 32 + lane;
+        size_t i = (size_t)r * Smax + s;
+        bool v = s < Smax && pidx[i * K] >= 0;
+        float E = v ? delta[i] * laplace_density(sdf[i], beta) : 0.0f;
+        float inc = warp_scan_incl(E, lane);
+        Tl[c] = expf(-(carry + (inc - E)));
+        carry += __shfl_sync(SPF_FULL, inc, 31);
+        float w = s < Smax ? weights[i] : 0.0f;
+        wl[c] = w;
+        if (v) { A += w * t[i]; B += w; }
+      }
+      A = warp_sum(A); B = warp_sum(B);
+      float b8 = B + 1e-8f, b10 = B + 1e-10f;
+      float suffix = 0.0f;  // sum of g_i w_i over later chunks
+      for (int c = 0; c < nch; ++c) {
+        int s = c * 32 + lane;
+        size_t i = (size_t)r * Smax + s;
+        bool v = s < Smax && pidx[i * K] >= 0;
+        float g = 0.0f;
+        if (v) {
+          float ti = t[i];
+          g = (d_weights ? d_weights[i] : 0.0f) + dr0 * rgb_s[3 * i] + dr1 * rgb_s[3 * i + 1] + dr2 * rgb_s[3 * i + 2] +
+              dd * (ti / b8 - A / (b8 * b8)) + dm * (ti / b10 - A / (b10 * b10));
+        } else if (s < Smax && d_weights) {
+          g = d_weights[i];  // invalid slots still carry w = 0, so g never matters; kept for clarity
+          g = 0.0f;
+        }
+        gl[c] = g;
+      }
+      for (int c = nch - 1; c >= 0; --c) {
+        int s = c * 32 + lane;
+        size_t i = (size_t)r * Smax + s;
+        bool v = s < Smax && pidx[i * K] >= 0;
+        float G = gl[c] * wl[c];
+        // inclusive suffix scan inside the chunk
+        float suf = G;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float n = __shfl_down_sync(SPF_FULL, suf, o);
+          if (lane + o < 32) suf += n;
+        }
+        float later = suffix + (suf - G);
+        suffix += __shfl_sync(SPF_FULL, suf, 0);
+        if (s < Smax) {
+          float ds = 0.0f;
+          if (v) {
+            float dE = gl[c] * (Tl[c] - wl[c]) - later;
+            float dsig = delta[i] * dE;
+            float sv = sdf[i];
+            float e = expf(-fabsf(sv) / beta);
+            float b2 = beta * beta;
+            float dsds, dsdb;
+            if (sv > 0.0f) { dsds = -e / (2.0f * b2); dsdb = e * (sv / beta - 1.0f) / (2.0f * b2); }
+            else if (sv < 0.0f) { dsds = -e / (2.0f * b2); dsdb = -1.0f / b2 + e * (1.0f + sv / beta) / (2.0f * b2); }
+            else { dsds = 0.0f; dsdb = -0.5f / b2; }
+            ds = dsig * dsds;
+            dbeta_acc += dsig * dsdb;
+          }
+          d_sdf[i] = ds;
+          float w = wl[c];
+          d_rgb_s[3 * i] = v ? w * dr0 : 0.f; d_rgb_s[3 * i + 1] = v ? w * dr1 : 0.f; d_rgb_s[3 * i + 2] = v ? w * dr2 : 0.f;
+        }
+      }
+    }
+  }
+  dbeta_acc = warp_sum(dbeta_acc);
+  __shared__ float s_b[8];
+  if (lane == 0) s_b[threadIdx.x >> 5] = dbeta_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += s_b[w];
+    if (tsum != 0.0f) atomicAdd(d_beta, tsum);
+  }
+}
+
+extern "C" int spf_composite_bwd(const float* sdf, const float* delta, const float* t, const float* rgb_s,
+                                 const int32_t* pidx, int32_t K, const int32_t* ray_nvalid, const float* beta,
+                                 int32_t R, int32_t Smax, const float* weights, const float* d_weights,
+                                 const float* d_rgb, const float* d_depth, const float* d_dist, float* d_sdf,
+                                 float* d_rgb_s, float* d_beta, void* stream_) {
+  if (!sdf || !delta || !t || !rgb_s || !pidx || !ray_nvalid || !beta || !weights || !d_sdf || !d_rgb_s || !d_beta)
+    return SPF_ERR_INVALID;
+  if (Smax > 32 * MAX_CHUNKS) return SPF_ERR_UNSUPPORTED;
+  if (R <= 0) return SPF_OK;
+  k_composite_bwd<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(sdf, delta, t, rgb_s, pidx, K, ray_nvalid, beta, R,
+                                                                  Smax, weights, d_weights, d_rgb, d_depth, d_dist,
+                                                                  d_sdf, d_rgb_s, d_beta);
+  SPF_CHECK_LAUNCH("k_composite_bwd");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a12: sampler
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sampler_coarse(const float* __restrict__ t_vals, const float* __restrict__ t_rand, float near_,
+                                 float far_, const float* __restrict__ cam_loc, const float* __restrict__ dirs, int R,
+                                 int M, float* __restrict__ z, float* __restrict__ pts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * M) return;
+  int r = (int)(i / M), m = (int)(i - (long long)r * M);
+  // ray_sampler.py:46-47
+  float tv = t_vals[m];
+  float zc = near_ * (1.0f - tv) + far_ * tv;
+  float zv = zc;
+  if (t_rand) {  // ray_sampler.py:49-57 stratified
+    float lower = zc, upper = zc;
+    if (m > 0) { float tp = t_vals[m - 1]; float zp = near_ * (1.0f - tp) + far_ * tp; lower = 0.5f * (zc + zp); }
+    if (m < M - 1) { float tn = t_vals[m + 1]; float zn = near_ * (1.0f - tn) + far_ * tn; upper = 0.5f * (zn + zc); }
+    zv = lower + (upper - lower) * t_rand[i];
+  }
+  z[i] = zv;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pts[3 * i + a] = cam_loc[a] + zv * dirs[3 * r + a];  // ray_sampler.py:398
+}
+
+extern "C" int spf_sampler_coarse(const float* t_vals, const float* t_rand, float near_, float far_,
+                                  const float* cam_loc, const float* ray_dirs, int32_t R, int32_t M, float* z,
+                                  float* points, void* stream_) {
+  if (!t_vals || !cam_loc || !ray_dirs || !z || !points || M < 2) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  long long n = (long long)R * M;
+  k_sampler_coarse<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(t_vals, t_rand, near_, far_,
+                                                                                  cam_loc, ray_dirs, R, M, z, points);
+  SPF_CHECK_LAUNCH("k_sampler_coarse");
+  return SPF_OK;
+}
+
+// error bound for one beta (ray_sampler.py:576-588); lanes own contiguous chunks of the M-1 sections
+__device__ float error_bound_warp(const float* __restrict__ sz, const float* __restrict__ sd,
+                                  const float* __restrict__ sds, int M, float beta, int lane) {
+  const int n = M - 1;
+  const int ch = (n + 31) >> 5;
+  const int i0 = lane * ch, i1 = min(n, i0 + ch);
+  const float fb2 = 4.0f * (beta * beta);
+  float se = 0.0f, sf = 0.0f;
+  for (int i = i0; i < i1; ++i) {
+    float a = sz[i + 1] - sz[i];
+    se += expf(-sds[i] / beta) * (a * a) / fb2;
+    sf += a * laplace_density(sd[i], beta);
+  }
+  float ie = warp_scan_incl(se, lane) - se;  // exclusive offsets
+  float jf = warp_scan_incl(sf, lane) - sf;
+  float mx = -INFINITY;
+  bool anynan = false;
+  for (int i = i0; i < i1; ++i) {
+    float a = sz[i + 1] - sz[i];
+    ie += expf(-sds[i] / beta) * (a * a) / fb2;                   // inclusive error integral
+    float b = (fminf(expf(ie), 1.0e6f) - 1.0f) * expf(-jf);       // uses the exclusive density integral
+    jf += a * laplace_density(sd[i], beta);
+    anynan |= isnan(b);
+    mx = fmaxf(mx, b);
+  }
+  mx = warp_max(mx);
+  if (__any_sync(SPF_FULL, anynan)) mx = NAN;  // torch.max propagates NaN
+  return mx;
+}
+
+__global__ void k_sampler_iter(const float* __restrict__ z, const float* __restrict__ sdf, int R, int M,
+                               const float* __restrict__ beta_dev, float eps, int beta_iters, float bound_coef,
+                               float add_tiny, int first_iter, float* __restrict__ beta_io, int final_, int N,
+                               const float* __restrict__ u, const float* __restrict__ u_lin, float near_, float far_,
+                               const int* __restrict__ extra_idx, int n_extra, const float* __restrict__ cam_loc,
+                               const float* __restrict__ dirs, float* __restrict__ out_z, float* __restrict__ out_pts,
+                               int* __restrict__ flag) {
+  extern __shared__ float smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
+  const int stride = M + 1;
+  float* sz = smem + (size_t)wid * 4 * stride;   // z
+  float* sd = sz + stride;                        // sdf
+  float* sds = sd + stride;                       // d_star, later scratch for the final sort
+  float* scdf = sds + stride;                     // cdf
+  if (r >= R) return;
+  for (int i = lane; i < M; i += 32) { sz[i] = z[(size_t)r * M + i]; sd[i] = sdf[(size_t)r * M + i]; }
+  __syncwarp();
+  const int n = M - 1;
+  // d* (ray_sampler.py:417-432) and sum of squared dists
+  float ss = 0.0f;
+  for (int i = lane; i < n; i += 32) {
+    float a = sz[i + 1] - sz[i];
+    float d0 = sd[i], d1 = sd[i + 1];
+    float b = fabsf(d0), c = fabsf(d1);
+    bool first = a * a + b * b <= c * c;
+    bool second = a * a + c * c <= b * b;
+    float ds = 0.0f;
+    if (first) ds = b;
+    if (second) ds = c;
+    float s = (a + b + c) / 2.0f;
+    float area = s * (s - a) * (s - b) * (s - c);
+    if (!first && !second && (b + c - a > 0.0f)) ds = (2.0f * sqrtf(area)) / a;
+    if (!(sgnf(d1) * sgnf(d0) == 1.0f)) ds = 0.0f;
+    sds[i] = ds;
+    ss += a * a;
+  }
+  ss = warp_sum(ss);
+  __syncwarp();
+  const float beta0 = beta_dev[0];
+  float beta = first_iter ? sqrtf(bound_coef * ss) : beta_io[r];  // ray_sampler.py:388-392
+  // line search (ray_sampler.py:435-445)
+  float e0 = error_bound_warp(sz, sd, sds, M, beta0, lane);
+  if (e0 <= eps) beta = beta0;
+  float bmin = beta0, bmax = beta;
+  for (int j = 0; j < beta_iters; ++j) {
+    float mid = (bmin + bmax) / 2.0f;
+    float e = error_bound_warp(sz, sd, sds, M, mid, lane);
+    if (e <= eps) bmax = mid;
+    else if (e > eps) bmin = mid;
+  }
+  beta = bmax;
+  if (lane == 0) {
+    beta_io[r] = beta;
+    if (beta > beta0) atomicOr(flag, 1);  // ray_sampler.py:468
+  }
+  // weights / transmittance with the chosen beta (ray_sampler.py:448-464), lanes own contiguous chunks of M
+  const int chM = (M + 31) >> 5;
+  const int j0 = lane * chM, j1 = min(M, j0 + chM);
+  float sf = 0.0f, se = 0.0f;
+  const float fb2 = 4.0f * (beta * beta);
+  for (int i = j0; i < j1; ++i) {
+    float a = i < n ? sz[i + 1] - sz[i] : 1e10f;
+    sf += a * laplace_density(sd[i], beta);
+    if (i < n) se += expf(-sds[i] / beta) * (a * a) / fb2;
+  }
+  float jf = warp_scan_incl(sf, lane) - sf;
+  float ie = warp_scan_incl(se, lane) - se;
+  // unnormalised pdf into scdf[0..n)
+  float tot = 0.0f;
+  for (int i = j0; i < j1; ++i) {
+    float a = i < n ? sz[i + 1] - sz[i] : 1e10f;
+    float fe = a * laplace_density(sd[i], beta);
+    float T = expf(-jf);
+    float p;
+    if (final_) {
+      float w = (1.0f - expf(-fe)) * T;
+      p = w + 1e-5f;                                               // ray_sampler.py:495-497
+    } else {
+      if (i < n) ie += expf(-sds[i] / beta) * (a * a) / fb2;
+      p = (fminf(expf(ie), 1.0e6f) - 1.0f) * T + add_tiny;         // ray_sampler.py:476-486
+    }
+    jf += fe;
+    if (i < n) { scdf[i + 1] = p; tot += p; }
+  }
+  tot = warp_sum(tot);
+  __syncwarp();
+  // normalise + inclusive scan -> cdf[0..M)  (cdf[0] = 0)
+  {
+    const int ch = (n + 31) >> 5;
+    const int i0 = lane * ch, i1 = min(n, i0 + ch);
+    float s = 0.0f;
+    for (int i = i0; i < i1; ++i) { float p = scdf[i + 1] / tot; scdf[i + 1] = p; s += p; }
+    float off = warp_scan_incl(s, lane) - s;
+    for (int i = i0; i < i1; ++i) { off += scdf[i + 1]; scdf[i + 1] = off; }
+    if (lane == 0) scdf[0] = 0.0f;
+  }
+  __syncwarp();
+  // inverse CDF (ray_sampler.py:517-529)
+  float* ssort = sds;  // reuse
+  const int cols = final_ ? N + 2 + n_extra : N;
+  for (int j = lane; j < N; j += 32) {
+    float uu = u ? u[(size_t)r * N + j] : u_lin[j];
+    int lo = 0, hi = M;  // first index with cdf > uu  (searchsorted right=True)
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (scdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    int below = max(lo - 1, 0), above = min(M - 1, lo);
+    float cb = scdf[below], ca = scdf[above];
+    float den = ca - cb;
+    if (den < 1e-5f) den = 1.0f;
+    float tt = (uu - cb) / den;
+    float smp = sz[below] + tt * (sz[above] - sz[below]);
+    if (final_) ssort[j] = smp;
+    else {
+      out_z[(size_t)r * N + j] = smp;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) out_pts[((size_t)r * N + j) * 3 + a] = cam_loc[a] + smp * dirs[3 * r + a];
+    }
+  }
+  if (!final_) return;
+  // extras + sort (ray_sampler.py:548-559)
+  if (lane == 0) { ssort[N] = near_; ssort[N + 1] = far_; }
+  for (int e = lane; e < n_extra; e += 32) ssort[N + 2 + e] = sz[extra_idx[e]];
+  __syncwarp();
+  for (int i = lane; i < cols; i += 32) {
+    float v = ssort[i];
+    int rank = 0;
+    for (int j = 0; j < cols; ++j) {
+      float o = ssort[j];
+      rank += (o < v) || (o == v && j < i);
+    }
+    out_z[(size_t)r * cols + rank] = v;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) out_pts[((size_t)r * cols + rank) * 3 + a] = cam_loc[a] + v * dirs[3 * r + a];
+  }
+}
+
+extern "C" int spf_sampler_iter(const float* z, const float* sdf, int32_t R, int32_t M, const float* beta_dev,
+                                float eps, int32_t beta_iters, float bound_coef, float add_tiny, int32_t first_iter,
+                                float* beta_io, int32_t final_, int32_t N, const float* u, const float* u_lin,
+                                float near_, float far_, const int32_t* extra_idx, int32_t n_extra,
+                                const float* cam_loc, const float* ray_dirs, float* out_z, float* out_points,
+                                int32_t* flag_not_converged, void* stream_) {
+  if (!z || !sdf || !beta_dev || !beta_io || !cam_loc || !ray_dirs || !out_z || !out_points || !flag_not_converged)
+    return SPF_ERR_INVALID;
+  if (!u && !u_lin) return SPF_ERR_INVALID;
+  if (M < 2 || N < 1) return SPF_ERR_INVALID;
+  if (final_ && (N + 2 + n_extra > M)) return SPF_ERR_UNSUPPORTED;
+  if (n_extra > 0 && !extra_idx) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  const int wpb = 4;
+  size_t smem = (size_t)wpb * 4 * (M + 1) * sizeof(float);
+  if (smem > 200 * 1024) return SPF_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    SPF_CUDA(cudaFuncSetAttribute(k_sampler_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "sampler_iter smem attr");
+  k_sampler_iter<<<(R + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream_>>>(
+      z, sdf, R, M, beta_dev, eps, beta_iters, bound_coef, add_tiny, first_iter, beta_io, final_, N, u, u_lin, near_,
+      far_, extra_idx, n_extra, cam_loc, ray_dirs, out_z, out_points, flag_not_converged);
+  SPF_CHECK_LAUNCH("k_sampler_iter");
+  return SPF_OK;
+}
+
+// merge two sorted rows (ray_sampler.py:533 sort of cat, :405-415 gather of the merged sdf)
+__global__ void k_sampler_merge(const float* __restrict__ z, const float* __restrict__ sdf, int M,
+                                const float* __restrict__ zs, const float* __restrict__ sdf_s, int N, int R,
+                                float* __restrict__ z_out, float* __restrict__ sdf_out) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* a = z + (size_t)r * M;
+  const float* b = zs + (size_t)r * N;
+  float* zo = z_out + (size_t)r * (M + N);
+  float* so = sdf_out + (size_t)r * (M + N);
+  for (int i = lane; i < M; i += 32) {
+    float v = a[i];
+    int lo = 0, hi = N;  // count of b < v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (b[mid] < v) lo = mid + 1; else hi = mid; }
+    zo[i + lo] = v; so[i + lo] = sdf[(size_t)r * M + i];
+  }
+  for (int j = lane; j < N; j += 32) {
+    float v = b[j];
+    int lo = 0, hi = M;  // count of a <= v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    zo[j + lo] = v; so[j + lo] = sdf_s[(size_t)r * N + j];
+  }
+}
+
+extern "C" int spf_sampler_merge(const float* z, const float* sdf, int32_t M, const float* zs, const float* sdf_s,
+                                 int32_t N, int32_t R, float* z_out, float* sdf_out, void* stream_) {
+  if (!z || !sdf || !zs || !sdf_s || !z_out || !sdf_out) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  k_sampler_merge<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(z, sdf, M, zs, sdf_s, N, R, z_out, sdf_out);
+  SPF_CHECK_LAUNCH("k_sampler_merge");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13: tv_regul (spurfies/model/utils.py:221-281) over cached self-kNN lists; one warp per point,
+// one lane per latent channel (C_g = 32).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tv(const float* __restrict__ pts, const float* __restrict__ feat, const int* __restrict__ nbr, int N,
+                     int K, float* __restrict__ value, float* __restrict__ grad, float grad_scale) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  float tv_i = 0.0f;
+  if (i < N) {
+    // utils.py:236-253: pad with self, drop self when other neighbours exist
+    int my = lane < K ? nbr[(size_t)i * K + lane] : -1;
+    bool has = __any_sync(SPF_FULL, my >= 0);
+    if (!has && lane == 0) my = i;
+    int cnt = __popc(__ballot_sync(SPF_FULL, my >= 0));
+    if (cnt > 1 && my == i) my = -1;
+    float w = 0.0f;
+    if (my >= 0) {
+      float dx = pts[3 * my] - pts[3 * i], dy = pts[3 * my + 1] - pts[3 * i + 1], dz = pts[3 * my + 2] - pts[3 * i + 2];
+      w = 1.0f / (sqrtf(dx * dx + dy * dy + dz * dz) + 1.0e-5f);
+    }
+    float norm = warp_sum(w);
+    float fi = feat[(size_t)i * 32 + lane];
+    float gi = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      int j = __shfl_sync(SPF_FULL, my, k);
+      float wk = __shfl_sync(SPF_FULL, w, k);
+      if (j < 0) continue;
+      float diff = feat[(size_t)j * 32 + lane] - fi;
+      float l1 = warp_sum(fabsf(diff));
+      tv_i += wk * l1;
+      if (grad) {
+        float gsc = grad_scale * wk / norm / (float)N * sgnf(diff);
+        if (gsc != 0.0f) atomicAdd(&grad[(size_t)j * 32 + lane], gsc);
+        gi -= gsc;
+      }
+    }
+    tv_i = tv_i / norm;
+    if (grad && gi != 0.0f) atomicAdd(&grad[(size_t)i * 32 + lane], gi);
+  }
+  __shared__ float s_v[8];
+  if (lane == 0) s_v[threadIdx.x >> 5] = (i < N) ? tv_i : 0.0f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_v[w];
+    atomicAdd(value, t / (float)N);
+  }
+}
+
+extern "C" int spf_tv_fwd_bwd(const float* pts, const float* feat_g, const int32_t* self_pidx, int32_t N, int32_t K,
+                              float* value, float* grad, float grad_scale, void* stream_) {
+  if (!pts || !feat_g || !self_pidx || !value) return SPF_ERR_INVALID;
+  if (K > 32) return SPF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPF_CUDA(cudaMemsetAsync(value, 0, sizeof(float), st), "tv memset");
+  if (N <= 0) return SPF_OK;
+  k_tv<<<(N + 7) / 8, 256, 0, st>>>(pts, feat_g, self_pidx, N, K, value, grad, grad_scale);
+  SPF_CHECK_LAUNCH("k_tv");
+  return SPF_OK;
+}

@@ -1,0 +1,317 @@
+"""Host-side wrappers (torch.autograd.Function) around the field / compositing kernels of libspurfies_b200.so.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every tensor op on the hot path is a
+hand-written kernel reached through the C ABI (include/spurfies_b200.h).  The only library GEMMs are the plain
+weight-gradient products dW = dZ^T @ A of the trainable colour MLP / radiance head (cuBLAS through torch.matmul).
+
+Layout: a *slot* is one query position (ray sample or point).  ``pidx`` [n, K] holds its neighbours sorted by
+(d^2, id), -1 padded.  Valid slots (>= 1 neighbour) are compacted on the device into ``list`` / ``count``; per-slot
+outputs (sdf, grad, hbar, rgb) are indexed by slot, per-pair saved tensors by compact row ``v*K + k``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ColorWeightsF32, GeoWeightsF32, HeadWeightsF32, call, ptr, stream
+
+K_NEIGH = 8
+ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
+
+
+class SlotSet:
+    """Compacted list of the valid slots of one query (utils.py:90-113 glue, without the host sync)."""
+
+    def __init__(self, pidx: torch.Tensor):
+        assert pidx.dtype == torch.int32 and pidx.is_contiguous()
+        self.K = pidx.shape[-1]
+        self.pidx = pidx.view(-1, self.K)
+        self.n = self.pidx.shape[0]
+        dev = pidx.device
+        self.list = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(_lib.lib.spf_compact_workspace_bytes(self.n), dtype=torch.uint8, device=dev)
+        call("spf_compact_valid", ptr(self.pidx), self.n, self.K, ptr(self.list), ptr(self.count), ptr(ws), ws.numel(),
+             stream())
+        # deferred host copy of the count: waited on only when somebody needs V on the host (wgrad GEMM sizes,
+        # ragged outputs); by then the GPU is long past this point of the stream.
+        self._count_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        self._count_host.copy_(self.count, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._V: Optional[int] = None
+
+    @property
+    def V(self) -> int:
+        if self._V is None:
+            self._event.synchronize()
+            self._V = int(self._count_host[0])
+        return self._V
+
+    def valid_mask(self) -> torch.Tensor:
+        return self.pidx[:, 0] >= 0
+
+    def rows_alloc(self, per_slot: int) -> int:
+        return self.n * per_slot + ROW_PAD
+
+
+# ------------------------------------------------------------------------------------------------ weight packs
+class GeoPack:
+    """Frozen geometry MLP (F_geometry + T, pointneus_disent.py:86-98) packed for the kernels; rebuilt only when
+    a parameter's version counter changes."""
+
+    def __init__(self):
+        self._key = None
+
+    def get(self, F_geometry, T):
+        lin = [m for m in F_geometry if isinstance(m, torch.nn.Linear)]
+        prm = [p for m in lin for p in (m.weight, m.bias)] + [T[0].weight, T[0].bias]
+        key = tuple((p.data_ptr(), p._version) for p in prm)
+        if key != self._key:
+            with torch.no_grad():
+                W = [m.weight.detach().float().contiguous() for m in lin]
+                b = [m.bias.detach().float().contiguous() for m in lin]
+                tw, tb = T[0].weight.detach().double(), T[0].bias.detach().double()
+                # fold F_geometry.8 and T (both linear, no activation in between)
+                v5 = (tw @ W[4].double()).reshape(-1).float().contiguous()
+                c5 = float((tw @ b[4].double() + tb).reshape(()))
+                self.W, self.b = W, b
+                self.Wt = [w.t().contiguous() for w in W[:4]]
+                self.v5, self.c5 = v5, c5
+                s = GeoWeightsF32()
+                s.w1t, s.b1 = self.Wt[0].data_ptr(), b[0].data_ptr()
+                s.w2t, s.b2 = self.Wt[1].data_ptr(), b[1].data_ptr()
+                s.w3t, s.b3 = self.Wt[2].data_ptr(), b[2].data_ptr()
+                s.w4t, s.b4 = self.Wt[3].data_ptr(), b[3].data_ptr()
+                s.v5, s.c5 = v5.data_ptr(), c5
+                s.w1, s.w2, s.w3, s.w4 = (W[i].data_ptr() for i in range(4))
+                self.f32 = s
+            self._key = key
+        return self
+
+
+def geo_sdf_raw(pack: GeoPack, slots: SlotSet, x, pts, feat_g, rbf, want_grad, want_jw, fill=1000.0):
+    n = slots.n
+    dev = x.device
+    sdf = torch.full((n,), fill, dtype=torch.float32, device=dev)
+    grad = torch.zeros(n, 3, dtype=torch.float32, device=dev) if want_grad else None
+    jw = torch.empty(slots.rows_alloc(slots.K), 32, dtype=torch.float32, device=dev) if want_jw else None
+    call("spf_sdf_fwd_f32", C.byref(pack.f32), ptr(slots.list), ptr(slots.count), n, ptr(x), ptr(slots.pidx), slots.K,
+         ptr(pts), ptr(feat_g), float(rbf), ptr(sdf), ptr(grad), ptr(jw), stream())
+    return sdf, grad, jw
+
+
+class GeoSDF(torch.autograd.Function):
+    """sdf[slot] = sum_k w_k T(F_geometry([g_k | x - p_k])) / sum_k w_k and d sdf / d x  (pointneus_disent.py:241-247,
+    300-323).  Gradients: latents (scatter-add of the saved Jacobian rows) and, when x requires grad (pseudo-point
+    path, pointneus_disent.py:771-780), x."""
+
+    @staticmethod
+    def forward(ctx, feat_g, x, slots: SlotSet, pack: GeoPack, pts, rbf, want_grad):
+        feat_needs, x_needs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        x = x.detach().contiguous()
+        sdf, grad, jw = geo_sdf_raw(pack, slots, x, pts, feat_g.detach(), rbf, want_grad or x_needs, feat_needs)
+        ctx.slots, ctx.jw, ctx.grad = slots, jw, grad
+        ctx.feat_shape = feat_g.shape
+        ctx.x_needs = x_needs
+        if grad is None:
+            grad = torch.zeros(0, 3, device=x.device)
+        ctx.mark_non_differentiable(grad)
+        return sdf, grad
+
+    @staticmethod
+    def backward(ctx, d_sdf, _):
+        slots = ctx.slots
+        gfeat = None
+        d_sdf = d_sdf.contiguous()
+        if ctx.jw is not None:
+            gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=d_sdf.device)
+            call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
+                 ptr(d_sdf), ptr(gfeat), stream())
+        dx = None
+        if ctx.x_needs:
+            dx = torch.where(slots.valid_mask()[:, None], d_sdf[:, None] * ctx.grad, torch.zeros_like(ctx.grad))
+        return gfeat, dx, None, None, None, None, None
+
+
+def _color_struct(W, b):
+    s = ColorWeightsF32()
+    Wt = [w.t().contiguous() for w in W]
+    s.w1t, s.b1, s.w2t, s.b2, s.w3t, s.b3 = (Wt[0].data_ptr(), b[0].data_ptr(), Wt[1].data_ptr(), b[1].data_ptr(),
+                                             Wt[2].data_ptr(), b[2].data_ptr())
+    s.w1, s.w2, s.w3 = W[0].data_ptr(), W[1].data_ptr(), W[2].data_ptr()
+    return s, Wt
+
+
+class ColorField(torch.autograd.Function):
+    """hbar[slot] = sum_k w_k/norm * h3_k with h3 = first three layers of F_color on [PE6(x-p_k) | c_k]
+    (pointneus_disent.py:325-336; F_color.6 is applied per sample in RadianceHead)."""
+
+    @staticmethod
+    def forward(ctx, feat_c, W1, b1, W2, b2, W3, b3, x, slots: SlotSet, pts, rbf):
+        dev = x.device
+        W = [w.detach().float().contiguous() for w in (W1, W2, W3)]
+        b = [v.detach().float().contiguous() for v in (b1, b2, b3)]
+        s, Wt = _color_struct(W, b)
+        n, K = slots.n, slots.K
+        hbar = torch.zeros(n, 256, dtype=torch.float32, device=dev)
+        need = any(ctx.needs_input_grad[:7])
+        rows = slots.rows_alloc(K)
+        in0 = h1 = h2 = m3 = wn = None
+        if need:
+            in0 = torch.empty(rows, 104, dtype=torch.float32, device=dev)
+            h1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+            h2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+            m3 = torch.empty(rows, 8, dtype=torch.int32, device=dev)
+            wn = torch.empty(rows, dtype=torch.float32, device=dev)
+        call("spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(x.contiguous()), ptr(slots.pidx), K,
+             ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0), ptr(h1), ptr(h2), ptr(m3), ptr(wn),
+             stream())
+        ctx.slots, ctx.saved_t = slots, (W, b, Wt, in0, h1, h2, m3, wn)
+        ctx.feat_shape = feat_c.shape
+        return hbar
+
+    @staticmethod
+    def backward(ctx, d_hbar):
+        slots = ctx.slots
+        W, b, Wt, in0, h1, h2, m3, wn = ctx.saved_t
+        dev = d_hbar.device
+        s, _keep = _color_struct(W, b)
+        rows = slots.rows_alloc(slots.K)
+        dz1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        dz2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        dz3 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
+        call("spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
+             ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2), ptr(dz3), ptr(gfeat),
+             stream())
+        r = slots.V * slots.K
+        # plain weight-gradient GEMMs (library): dW = dZ^T @ A over the compact pair rows
+        dW3, db3 = dz3[:r].t() @ h2[:r], dz3[:r].sum(0)
+        dW2, db2 = dz2[:r].t() @ h1[:r], dz2[:r].sum(0)
+        dW1, db1 = dz1[:r].t() @ in0[:r, :103], dz1[:r].sum(0)
+        return gfeat, dW1, db1, dW2, db2, dW3, db3, None, None, None, None
+
+
+def positional_encoding(x: torch.Tensor, multires: int) -> torch.Tensor:
+    """embedder.py:10-36 (host-side copy, only used to assemble the wgrad operand of R.0)."""
+    out = [x]
+    for l in range(multires):
+        out += [torch.sin(x * float(2 ** l)), torch.cos(x * float(2 ** l))]
+    return torch.cat(out, -1)
+
+
+class RadianceHead(torch.autograd.Function):
+    """rgb[slot] = sigmoid(R([PE3(dir) | F_color.6(hbar)]))  (pointneus_disent.py:83, 100-107, 338-346)."""
+
+    @staticmethod
+    def forward(ctx, hbar, W4, b4, R1, rb1, R2, rb2, R3, rb3, dirs, slots: SlotSet, Smax):
+        dev = hbar.device
+        W = [w.detach().float().contiguous() for w in (W4, R1, R2, R3)]
+        b = [v.detach().float().contiguous() for v in (b4, rb1, rb2, rb3)]
+        Wt = [w.t().contiguous() for w in W]
+        s = HeadWeightsF32()
+        s.w4t, s.b4, s.r1t, s.rb1, s.r2t, s.rb2, s.r3t, s.rb3 = (Wt[0].data_ptr(), b[0].data_ptr(), Wt[1].data_ptr(),
+                                                                  b[1].data_ptr(), Wt[2].data_ptr(), b[2].data_ptr(),
+                                                                  Wt[3].data_ptr(), b[3].data_ptr())
+        s.w4, s.r1, s.r2, s.r3 = (w.data_ptr() for w in W)
+        n = slots.n
+        rgb = torch.zeros(n, 3, dtype=torch.float32, device=dev)
+        rows = slots.rows_alloc(1)
+        need = any(ctx.needs_input_grad[:9])
+        f = a1 = a2 = None
+        if need:
+            f = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+            a1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+            a2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        hbar_c = hbar.detach().contiguous()
+        call("spf_head_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(dirs), int(Smax),
+             ptr(rgb), ptr(f), ptr(a1), ptr(a2), stream())
+        ctx.slots, ctx.saved_t, ctx.Smax = slots, (s, W, b, Wt, hbar_c, rgb, f, a1, a2, dirs), Smax
+        return rgb
+
+    @staticmethod
+    def backward(ctx, d_rgb):
+        slots = ctx.slots
+        s, W, b, Wt, hbar, rgb, f, a1, a2, dirs = ctx.saved_t
+        dev = d_rgb.device
+        n = slots.n
+        rows = slots.rows_alloc(1)
+        d_hbar = torch.zeros(n, 256, dtype=torch.float32, device=dev)
+        dzf = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        dz1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        dz2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        dz3 = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+        call("spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
+             ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), stream())
+        V = slots.V
+        lst = slots.list[:V].long()
+        dW4, db4 = dzf[:V].t() @ hbar[lst], dzf[:V].sum(0)
+        cat = torch.cat([positional_encoding(dirs[lst // ctx.Smax], 3), f[:V]], -1)
+        dR1, drb1 = dz1[:V].t() @ cat, dz1[:V].sum(0)
+        dR2, drb2 = dz2[:V].t() @ a1[:V], dz2[:V].sum(0)
+        dR3, drb3 = dz3[:V, :3].t() @ a2[:V], dz3[:V, :3].sum(0)
+        return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
+
+
+class Composite(torch.autograd.Function):
+    """Laplace density + alpha compositing + per-ray reductions (density.py:21-30; pointneus_disent.py:701-723,
+    765-807, 894-908)."""
+
+    @staticmethod
+    def forward(ctx, sdf, rgb_s, beta, delta, t, grad, pidx, nvalid, R, Smax, K, want_normal):
+        dev = sdf.device
+        weights = torch.empty(R, Smax, dtype=torch.float32, device=dev)
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(R, dtype=torch.float32, device=dev)
+        acc = torch.empty(R, dtype=torch.float32, device=dev)
+        dist = torch.empty(R, dtype=torch.float32, device=dev)
+        normal = torch.empty(R, 3, dtype=torch.float32, device=dev) if want_normal else None
+        sdf_c, rgb_c, beta_c = sdf.detach().contiguous(), rgb_s.detach().contiguous(), beta.detach().reshape(1).contiguous()
+        call("spf_composite_fwd", ptr(sdf_c), ptr(delta), ptr(t), ptr(rgb_c), ptr(grad) if want_normal else None,
+             ptr(pidx), K, ptr(nvalid), ptr(beta_c), R, Smax, ptr(weights), ptr(rgb), ptr(depth), ptr(acc), ptr(dist),
+             ptr(normal), stream())
+        ctx.saved_t = (sdf_c, rgb_c, beta_c, delta, t, pidx, nvalid, weights)
+        ctx.dims = (R, Smax, K)
+        if normal is None:
+            normal = torch.zeros(0, 3, device=dev)
+        ctx.mark_non_differentiable(normal)
+        return weights, rgb, depth, acc, dist, normal
+
+    @staticmethod
+    def backward(ctx, d_w, d_rgb, d_depth, d_acc, d_dist, _):
+        sdf, rgb_s, beta, delta, t, pidx, nvalid, weights = ctx.saved_t
+        R, Smax, K = ctx.dims
+        dev = sdf.device
+        if d_acc is not None:  # acc = sum_i w_i
+            d_w = d_acc[:, None].expand(R, Smax) if d_w is None else d_w + d_acc[:, None]
+        c = lambda v: v.contiguous() if v is not None else None
+        d_sdf = torch.empty(R * Smax, dtype=torch.float32, device=dev)
+        d_rgb_s = torch.empty(R * Smax, 3, dtype=torch.float32, device=dev)
+        d_beta = torch.zeros(1, dtype=torch.float32, device=dev)
+        call("spf_composite_bwd", ptr(sdf), ptr(delta), ptr(t), ptr(rgb_s), ptr(pidx), K, ptr(nvalid), ptr(beta), R,
+             Smax, ptr(weights), ptr(c(d_w)), ptr(c(d_rgb)), ptr(c(d_depth)), ptr(c(d_dist)), ptr(d_sdf), ptr(d_rgb_s),
+             ptr(d_beta), stream())
+        return d_sdf, d_rgb_s, d_beta.reshape(()), None, None, None, None, None, None, None, None, None
+
+
+class TVRegul(torch.autograd.Function):
+    """tv_regul (utils.py:221-281) on the cached self-kNN lists of the (static) neural points."""
+
+    @staticmethod
+    def forward(ctx, feat_g, pts, self_pidx):
+        N, K = self_pidx.shape
+        dev = feat_g.device
+        value = torch.zeros(1, dtype=torch.float32, device=dev)
+        grad = torch.zeros_like(feat_g, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        call("spf_tv_fwd_bwd", ptr(pts), ptr(feat_g.detach().contiguous()), ptr(self_pidx), N, K, ptr(value), ptr(grad),
+             1.0, stream())
+        ctx.grad = grad
+        return value.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None
