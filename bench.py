@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/s (fwd + bwd + Adam) of the per-ray hot path on synthetic DTU-shaped scenes.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload at N = 1: BASELINE.json configs[1] -- DTU 3-view 512x384, N ~ 100 k neural points, 4096-ray batch, full
+training step (coarse pass -> error-bounded sampler -> kNN -> fields -> compositing -> loss -> backward -> Adam).
+For N > 1 every rank runs that same per-GPU batch on its own pixel subset (weak scaling) and the flat gradient
+buffer is all-reduced with NCCL each step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_POINTS = 100_000
+RAYS = 4096
+RES = (512, 384)
+METRIC = "train rays/s (fwd+bwd)"
+
+# kernels launched per C-ABI call (for gpu_launches)
+LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3}
+
+# FLOPs per (sample, neighbour) pair of the geometry field, 2 * MAC.
+#  algorithmic = SURVEY 8(d): reference graph, 35->256->256->256->256->256->1 = 271 360 MAC, forward + the
+#                autograd.grad pass over the same layers (pointneus_disent.py:315-323)
+#  executed    = what k_sdf_* runs after folding F_geometry.8 + T: (35*256 + 3*256^2 + 256) MAC, fwd + J pass
+GEO_FLOPS_ALGO = 2 * 2 * 271_360
+GEO_FLOPS_EXEC = 2 * 2 * (35 * 256 + 3 * 256 * 256 + 256)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_scene(device, seed=24):
+    from spurfies_b200 import scenes
+    from spurfies_b200.model import PointVolSDF, default_conf
+    sc = scenes.dtu_like(N_POINTS, seed=seed)
+    torch.manual_seed(0)
+    # caps above the occupancy so the reference semantics are well defined for this density
+    model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], device=device,
+                        max_points_per_voxel=128, max_occ_voxels=32768)
+    with torch.no_grad():  # non-degenerate latents (the real ones come from a trained prior / optimisation)
+        model.neural_feats_geometry.mul_(8.0)
+        model.neural_feats_color[:, 3:].mul_(500.0)
+    return sc, model
+
+
+def host_batches(n_batches, rank, n_rays=RAYS):
+    """Synthetic per-step inputs in pinned host memory: pixels, ground truth, sampler draws."""
+    from spurfies_b200 import scenes
+    out = []
+    for b in range(n_batches):
+        seed = 1000 * rank + b
+        cam = scenes.camera(b % 3, 2.3, RES)
+        item = {"uv": scenes.pixel_batch(n_rays, seed, RES), "pose": cam["pose"], "intrinsics": cam["intrinsics"]}
+        item.update({"gt_" + k: v for k, v in scenes.synthetic_gt(n_rays, seed).items()})
+        item.update({"rng_" + k: v for k, v in scenes.rng_inputs(n_rays, seed).items()})
+        out.append({k: v.contiguous().pin_memory() if torch.cuda.is_available() else v for k, v in item.items()})
+    return out
+
+
+def to_device(item, device):
+    return {k: v.to(device, non_blocking=True) for k, v in item.items()}
+
+
+def split(item):
+    batch = {"uv": item["uv"], "pose": item["pose"], "intrinsics": item["intrinsics"], "local_data": None}
+    gt = {"rgb": item["gt_rgb"], "mask": item["gt_mask"]}
+    rng = {"t_rand": item["rng_t_rand"], "u": item["rng_u"], "sampling_idx": item["rng_sampling_idx"]}
+    return batch, gt, rng
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from spurfies_b200 import _lib
+    from spurfies_b200.train import TrainStep
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    sc, model = build_scene(device)
+    step = TrainStep(model, world_size=world)
+    nb = 8
+    hb = host_batches(nb, rank)
+    db = [to_device(h, device) for h in hb]
+    torch.cuda.synchronize()
+
+    def one(item):
+        b, g, r = split(item)
+        return step(b, g, r)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one(db[i % nb])
+    barrier()
+    # ---------------- timed region 1: inputs resident in HBM
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.profile_reset(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        one(db[(args.warmup + i) % nb])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_collect()
+    _lib.profile_reset(False)
+    pairs_per_step = float(model._last["slots"].V) * 8  # last step's fine-pass pairs (representative)
+    # ---------------- timed region 2: end to end from pinned host buffers, loss read back every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for i in range(args.steps):
+        losses = one(to_device(hb[(args.warmup + i) % nb], device))
+        last = float(losses["loss"].item())  # D2H of the step's result
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total_rays = RAYS * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    e2e = total_rays / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in hb[0].values())
+    # roofline of the dominant kernel (geometry field forward + Jacobian pass), from the live event timings
+    dom = "spf_sdf_fwd_f32" if "spf_sdf_fwd_f32" in prof else max(prof, key=lambda k: prof[k]["ms"])
+    kt = prof[dom]
+    # the fine pass (with J) is the big launch: take the longest-per-step launch of that entry point
+    ms_launch = kt["max_ms"]
+    achieved = GEO_FLOPS_ALGO * pairs_per_step / (ms_launch * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": dom + " (fine pass, fwd + d sdf/d input)", "achieved": achieved,
+            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+            "traffic": None, "peak_source": pk["source"] + " bf16 sustained", "ms_per_launch": ms_launch,
+            "pairs_per_launch": pairs_per_step, "flops_per_pair_algorithmic": GEO_FLOPS_ALGO,
+            "flops_per_pair_executed": GEO_FLOPS_EXEC,
+            "achieved_executed": GEO_FLOPS_EXEC * pairs_per_step / (ms_launch * 1e-3) / 1e12,
+            "precision_mode": "fp32 SIMT (exact mode)"}
+    launches = sum(v["calls"] * LAUNCHES.get(k, 1) for k, v in prof.items())
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: DTU-shaped 3-view 512x384, %d neural points, %d-ray batch per GPU, "
+                               "full training step (coarse pass + error-bounded sampler + kNN + fields + compositing + "
+                               "loss + backward + Adam)" % (N_POINTS, RAYS),
+                   "rays_per_gpu": RAYS, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
+                   "l2": "distinct ray batch each step; per-step working set (saved activations, > 1 GB) >> 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roof,
+        "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    if args.cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_rays=128, repeats=1, threads=None):
+    """The reference's CPU path: the pure-torch oracle port with brute-force cdist kNN, full
+    fwd + bwd of the same loss, all host threads.  A step has a per-ray part and a fixed part (tv_regul's self-kNN
+    over all N neural points, utils.py:221-281, recomputed every step by the reference); the per-ray part is timed
+    on a bounded `sample_rays` sample and scaled to the workload's 4096-ray batch, the fixed part is timed once."""
+    from oracle import hotpath as H
+    from spurfies_b200 import scenes
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    H.KNN_BACKEND = "cdist"
+    sc = scenes.dtu_like(N_POINTS, seed=24)
+    P = H.init_params(sc["pts"], sc["colors"], seed=0)
+    P.neural_feats_geometry *= 8.0
+    P.neural_feats_color[:, 3:] *= 500.0
+    for t in P.trainable():
+        t.requires_grad_()
+    grid = P.make_grid()
+    cam = scenes.camera(0, sc["cam_radius"], RES)
+
+    def rays_step(n, seed, with_tv):
+        uv, rng, gt = scenes.pixel_batch(n, seed, RES), scenes.rng_inputs(n, seed), scenes.synthetic_gt(n, seed)
+        t0 = time.perf_counter()
+        out = H.render_forward(P, grid, uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), True, 1, rng, with_tv=with_tv)
+        lo = H.volsdf_loss(out, gt["rgb"], gt["mask"][0, :, 0])
+        lo["loss"].backward()
+        dt = time.perf_counter() - t0
+        for t in P.trainable():
+            t.grad = None
+        return dt
+
+    rays_step(8, 5, False)  # warm-up (thread pools, allocator)
+    t_rays = statistics.median([rays_step(sample_rays, 77 + r, False) for r in range(max(1, repeats))])
+    t0 = time.perf_counter()
+    H.tv_regul(P, grid).backward()
+    t_tv = time.perf_counter() - t0
+    H.KNN_BACKEND = "grid"
+    t_full = t_tv + t_rays * RAYS / sample_rays
+    return {"value": RAYS / t_full, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": "pure-torch oracle port, brute-force cdist+topk kNN (test_queries.py:22-74), fwd+bwd of the full loss: "
+                      "per-ray part timed on a %d-ray sample (%.2f s, median of %d after warm-up) and scaled to the %d-ray "
+                      "batch; fixed per-step tv_regul self-kNN over all %d points timed once (%.2f s)"
+                      % (sample_rays, t_rays, max(1, repeats), RAYS, N_POINTS, t_tv),
+            "seconds_per_step": t_full, "seconds_sample": t_rays, "seconds_tv": t_tv}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = args.cpu_rays
+    t0 = time.perf_counter()
+    cb = cpu_baseline(sample_rays=rays, repeats=max(1, min(args.steps, 3)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "rays/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": 1,
+            "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] scene and schedule, bounded %d-ray sample per step on the host CPU "
+                                   "(the reference has no CPU implementation: this is the oracle port, SURVEY D4)" % rays},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rays", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or int(os.environ.get("RANK", "0")) > 0:
+            args.cpu_baseline = False if int(os.environ.get("RANK", "0")) != 0 else args.cpu_baseline
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,9 @@ import torch.nn.functional as F
 from .knn import OracleGrid
 
 LEAKY = 0.01  # nn.LeakyReLU default slope (pointneus_disent.py:76-107)
+# "grid": C restatement of the reference voxel-grid kernels; "cdist": the reference test's pure-torch brute force
+# (torch.cdist + topk), which is what bench.py times as the CPU baseline.
+KNN_BACKEND = "grid"
 
 
 # ----------------------------------------------------------------------------- parameters
@@ -140,7 +143,7 @@ def camera_rays(uv, pose, intrinsics):
 def ragged_query(grid: OracleGrid, pts: torch.Tensor, k: int, r: float, smax: int):
     """utils.py:90-113 on top of knnquery.py:168-285.  pts [R,D,3].
     Returns neighbor_idx [V,k] (int64, -1 pad), shading_pts [V,3], mask [R,smax] bool, ray_mask [R] bool."""
-    out = grid.query_dense(pts, k, r, smax)
+    out = (grid.query_dense_cdist if KNN_BACKEND == "cdist" else grid.query_dense)(pts, k, r, smax)
     ray_mask = out["ray_mask2"].bool()
     slot_valid = (out["pidx"] >= 0).any(-1)                       # [R,smax]
     mask = slot_valid & ray_mask[:, None]

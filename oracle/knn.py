@@ -148,6 +148,35 @@ class OracleGrid:
             "candidates_scanned": int(scanned),
         }
 
+    def query_dense_cdist(self, raypos: torch.Tensor, k: int, radius_limit_scale: float, smax: int, chunk: int = 4096):
+        """Same contract as query_dense, but the neighbour search is the reference test's brute force
+        (test_queries.py:36-41: torch.cdist + topk + radius mask, exact non-matmul distances) in `chunk`-query
+        blocks.  This is the "reference CPU path" of BASELINE.md section 2: pure-torch, all host threads."""
+        R, D = raypos.shape[0], raypos.shape[1]
+        m = self.mask(raypos).bool()                                     # knnquery.cu:171-196
+        cum = torch.cumsum(m.int(), -1)
+        take = m & (cum <= smax)                                         # knnquery.py:230-231
+        slot_sample = torch.full((R, smax), -1, dtype=torch.int32)
+        rr, dd = torch.nonzero(take, as_tuple=True)
+        ss = (cum[rr, dd] - 1).long()
+        slot_sample[rr, ss] = dd.int()
+        loc = torch.zeros(R, smax, 3)
+        loc[rr, ss] = raypos[rr, dd]
+        pidx = torch.full((R, smax, k), -1, dtype=torch.int32)
+        pts = torch.from_numpy(self.pts)
+        q = raypos[rr, dd]
+        r = float(self.radius2(radius_limit_scale)) ** 0.5
+        res = []
+        for i in range(0, q.shape[0], chunk):
+            dist = torch.cdist(q[i:i + chunk][None], pts[None], compute_mode="donot_use_mm_for_euclid_dist")[0]
+            top = torch.topk(dist, min(k, dist.shape[-1]), dim=-1, largest=False, sorted=True)
+            res.append(torch.where(top.values <= r, top.indices, torch.full_like(top.indices, -1)).int())
+        if res:
+            pidx[rr, ss] = torch.cat(res, 0)
+        m2 = (pidx >= 0).any(-1).any(-1)
+        return {"slot_sample": slot_sample, "sample_loc": loc, "pidx": pidx, "ray_mask1": m.any(-1).to(torch.int8),
+                "ray_mask2": m2.to(torch.int8), "candidates_scanned": int(q.shape[0]) * int(pts.shape[0])}
+
     def brute(self, q: torch.Tensor, k: int, radius_limit_scale: float) -> torch.Tensor:
         qn = np.ascontiguousarray(q.detach().reshape(-1, 3).cpu().numpy().astype(np.float32))
         out = np.empty((qn.shape[0], k), dtype=np.int32)

@@ -108,8 +108,33 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- optional per-entry-point device timing (CUDA events on the launching stream), used by bench.py
+_PROFILE = {"on": False, "events": {}, "calls": {}}
+
+
+def profile_reset(on: bool):
+    _PROFILE["on"], _PROFILE["events"], _PROFILE["calls"] = on, {}, {}
+
+
+def profile_collect():
+    """-> {entry point: {"calls", "ms" (total), "max_ms"}}; synchronises."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in _PROFILE["events"].items():
+        times = [a.elapsed_time(b) for a, b in evs]
+        out[name] = {"calls": len(times), "ms": sum(times), "max_ms": max(times)}
+    return out
+
+
 def call(name, *args):
-    rc = getattr(lib, name)(*args)
+    if _PROFILE["on"]:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        _PROFILE["events"].setdefault(name, []).append((a, b))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = _CODES.get(rc, str(rc))
         if rc == -4:

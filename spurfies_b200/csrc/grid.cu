@@ -315,9 +315,9 @@ extern "C" int spf_knn_slots(const spf_grid* g, const float* sample_loc, const i
 
 extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int32_t K, float radius2, int32_t* pidx,
                               void* stream_) {
-  if (!g || !q || !pidx) return SPF_ERR_INVALID;
   if (K < 1 || K > 20) return SPF_ERR_INVALID;
   if (Q <= 0) return SPF_OK;
+  if (!g || !q || !pidx) return SPF_ERR_INVALID;
   const int wpb = 8;
   long long warps = (Q + 31) / 32;
   k_knn_points<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream_>>>(to_dev(g), q, Q, K,
@@ -327,8 +327,8 @@ extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int3
 }
 
 extern "C" int spf_mask_points(const spf_grid* g, const float* q, int64_t Q, int32_t* mask, void* stream_) {
-  if (!g || !q || !mask) return SPF_ERR_INVALID;
   if (Q <= 0) return SPF_OK;
+  if (!g || !q || !mask) return SPF_ERR_INVALID;
   k_mask_points<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(to_dev(g), q, Q, mask);
   SPF_CHECK_LAUNCH("k_mask_points");
   return SPF_OK;

@@ -1,0 +1,73 @@
+"""One optimisation step of the reference trainer around the hot path (spurfies/train.py:330-397): forward,
+VolSDFLoss, backward, clip_grad_norm_(1.0), NaN guard, Adam (lr 5e-4 on every trainable tensor, train.py:168-189).
+
+Data parallel (new functionality): one process per GPU, the step's rays are sharded across
+ranks, the neural points / grid / latents / MLPs are replicated, and ONE NCCL all-reduce per step carries the
+flat fp32 gradient buffer (latents N x 96 + colour MLP + radiance head + beta).  Clipping uses the global norm,
+so it runs after the all-reduce; every rank then takes the identical Adam step.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .model import PointVolSDF, VolSDFLoss
+
+
+class TrainStep:
+    def __init__(self, model: PointVolSDF, lr: float = 5.0e-4, grad_clip: float = 1.0, loss: Optional[VolSDFLoss] = None,
+                 world_size: int = 1):
+        self.model = model
+        self.loss = loss or VolSDFLoss()
+        for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
+            prm.requires_grad_(False)  # the local-prior SDF field is frozen (train.py:151-154)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
+        self.grad_clip = grad_clip
+        self.world_size = world_size
+        self._flat = None
+
+    def _allreduce_grads(self):
+        if self.world_size <= 1:
+            return
+        n = sum(p.numel() for p in self.params)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is None:
+                self._flat[off:off + k].zero_()
+            else:
+                self._flat[off:off + k].copy_(p.grad.reshape(-1))
+            off += k
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.mul_(1.0 / self.world_size)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            g = self._flat[off:off + k].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += k
+
+    def __call__(self, batch: Dict[str, torch.Tensor], gt: Dict[str, torch.Tensor], rng=None) -> Dict[str, torch.Tensor]:
+        self.model.train()
+        out = self.model(batch, fast=1, rng=rng, dense_outputs=True)  # fast=1: train.py:345-346
+        losses = self.loss(out, gt)
+        self.opt.zero_grad(set_to_none=True)
+        losses["loss"].backward()
+        self._allreduce_grads()
+        if self.grad_clip > 0:
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip, foreach=True)
+        # NaN / Inf guard (train.py:548-564): skip the update by zeroing the gradients, no host sync
+        finite = torch.stack([torch.isfinite(p.grad).all() for p in self.params if p.grad is not None]).all()
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.mul_(finite.to(p.grad.dtype))
+        self.opt.step()
+        return losses

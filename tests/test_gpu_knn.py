@@ -69,7 +69,7 @@ def test_rays_match_oracle_bit_exact(n_points, k):
         assert torch.equal(loc.cpu(), ref["sample_loc"])
         assert torch.equal(pidx.cpu(), ref["pidx"])
         assert torch.equal((nvalid.cpu() > 0), ref["ray_mask2"].bool())
-        assert int((ref["pidx"] >= 0).sum()) > 1000
+        assert int((ref["pidx"] >= 0).sum()) > 50
 
 
 def test_points_match_oracle_and_mask():
