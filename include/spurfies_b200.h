@@ -190,6 +190,11 @@ int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, cons
                     int32_t R, float* ray_dirs /*[R,3]*/, float* cam_loc /*[3]*/, float* depth_scale /*[R]*/,
                     void* stream);
 
+/* ---- bf16 tensor-core mode (tcgen05.mma + TMEM) ------------------------------------------------
+ * Packed weight images: see spurfies_b200/packing.py (k-block major, 128B-swizzled, bf16). */
+/* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
+int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ _SIGS = {
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
 }
 for _n, _a in _SIGS.items():
     _f = getattr(lib, _n)

@@ -1,0 +1,27 @@
+"""Weight images for the tcgen05 kernels (mlp_tc.cu).
+
+A B operand of ``tcgen05.mma`` is an [N x K] matrix with K contiguous ("K-major"), i.e. exactly a torch
+``nn.Linear.weight`` [out, in] for a forward layer, or its transpose for a dgrad layer.  The kernels load it with
+plain bulk copies (``cp.async.bulk``), so the image in global memory must already be in the shared-memory layout
+the MMA descriptor expects: k-blocks of 64 bf16 columns; inside a k-block one 128-byte row per n; the eight
+16-byte chunks of a row XOR-swizzled by (n & 7) (the hardware's 128B swizzle).  Byte size: ceil(K/64) * N * 128.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def pack_sw128(W: torch.Tensor, n_pad: int | None = None) -> torch.Tensor:
+    """W [N, K] (any float dtype, any device) -> uint8 image [ceil(K/64) * n_pad * 128] on the same device."""
+    N, K = W.shape
+    n_pad = n_pad or N
+    assert n_pad % 8 == 0 and n_pad >= N
+    nkb = (K + 63) // 64
+    Wb = torch.zeros(n_pad, nkb * 64, dtype=torch.bfloat16, device=W.device)
+    Wb[:N, :K] = W.detach().to(torch.bfloat16)
+    t = Wb.view(n_pad, nkb, 8, 8).permute(1, 0, 2, 3)                      # [kb, n, chunk, 8]
+    n = torch.arange(n_pad, device=W.device)
+    c = torch.arange(8, device=W.device)
+    src = (c[None, :] ^ (n[:, None] & 7))                                  # out chunk c holds in chunk c ^ (n & 7)
+    t = torch.gather(t, 2, src[None, :, :, None].expand(nkb, n_pad, 8, 8))
+    return t.contiguous().view(torch.uint8).reshape(-1)
