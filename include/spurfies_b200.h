@@ -192,6 +192,33 @@ int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, cons
 
 /* ---- bf16 tensor-core mode (tcgen05.mma + TMEM) ------------------------------------------------
  * Packed weight images: see spurfies_b200/packing.py (k-block major, 128B-swizzled, bf16). */
+typedef struct {
+  const uint8_t* w1p;   /* pack([W1[:, :32] | W1[:, 32:35] | W1[:, 32:35]] -> K = 38 padded to 64): x - p enters as bf16 hi + lo */
+  const uint8_t* w2p; const uint8_t* w3p; const uint8_t* w4p;     /* pack(F_geometry.{2,4,6}.weight) */
+  const uint8_t* w4tp; const uint8_t* w3tp; const uint8_t* w2tp;  /* pack(weight^T) for the d sdf / d input chain */
+  const uint8_t* w1tp;  /* pack(W1^T padded to [48][256]) */
+  const float* b1; const float* b2; const float* b3; const float* b4; const float* v5; float c5;
+} spf_geo_weights_tc;
+/* same contract as spf_sdf_fwd_f32 (bf16 inputs / weights, fp32 accumulation, 2e-2 tolerance) */
+int spf_sdf_fwd_tc(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                   const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_g, float rbf,
+                   float* sdf, float* grad, float* jw, void* stream);
+typedef struct {
+  const uint8_t* w1p;   /* pack(F_color.0.weight with input columns permuted to [c (64) | PE6 (39)], K = 103 -> 128) */
+  const uint8_t* w2p; const uint8_t* w3p;                     /* pack(F_color.{2,4}.weight) */
+  const uint8_t* w3tp; const uint8_t* w2tp;                   /* pack(weight^T) for dgrad */
+  const uint8_t* w1ftp;                                       /* pack(F_color.0.weight[:, 39:103]^T) -> [64][256] */
+  const float* b1; const float* b2; const float* b3;
+} spf_color_weights_tc;
+/* as spf_color_fwd_f32; saved tensors are bf16: in0 [rows,112] (permuted columns), h1, h2 [rows,256] */
+int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                     const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c, float rbf,
+                     float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn, void* stream);
+/* as spf_color_bwd_f32; dz1..3 are bf16 [rows,256] */
+int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                     const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
+                     const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
+                     void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

@@ -35,6 +35,18 @@ class GeoWeightsF32(C.Structure):
                 ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p), ("w4", C.c_void_p)]
 
 
+class GeoWeightsTC(C.Structure):
+    _fields_ = [("w1p", C.c_void_p), ("w2p", C.c_void_p), ("w3p", C.c_void_p), ("w4p", C.c_void_p),
+                ("w4tp", C.c_void_p), ("w3tp", C.c_void_p), ("w2tp", C.c_void_p), ("w1tp", C.c_void_p),
+                ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p), ("b4", C.c_void_p), ("v5", C.c_void_p),
+                ("c5", C.c_float)]
+
+
+class ColorWeightsTC(C.Structure):
+    _fields_ = [("w1p", C.c_void_p), ("w2p", C.c_void_p), ("w3p", C.c_void_p), ("w3tp", C.c_void_p),
+                ("w2tp", C.c_void_p), ("w1ftp", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p)]
+
+
 class ColorWeightsF32(C.Structure):
     _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
                 ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p)]
@@ -77,6 +89,9 @@ _SIGS = {
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
+    "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
+    "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 for _n, _a in _SIGS.items():
     _f = getattr(lib, _n)

@@ -16,7 +16,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ColorWeightsF32, GeoWeightsF32, HeadWeightsF32, call, ptr, stream
+from ._lib import ColorWeightsF32, ColorWeightsTC, GeoWeightsF32, GeoWeightsTC, HeadWeightsF32, call, ptr, stream
+from .packing import pack_sw128
 
 K_NEIGH = 8
 ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
@@ -89,8 +90,26 @@ class GeoPack:
                 s.v5, s.c5 = v5.data_ptr(), c5
                 s.w1, s.w2, s.w3, s.w4 = (W[i].data_ptr() for i in range(4))
                 self.f32 = s
+                # bf16 tensor-core images (mlp_tc.cu): x - p enters twice (bf16 hi + lo) against the same weights
+                W1ext = torch.cat([W[0][:, :32], W[0][:, 32:35], W[0][:, 32:35]], dim=1)
+                self.tc_imgs = [pack_sw128(W1ext), pack_sw128(W[1]), pack_sw128(W[2]), pack_sw128(W[3]),
+                                pack_sw128(W[3].t()), pack_sw128(W[2].t()), pack_sw128(W[1].t()),
+                                pack_sw128(W[0].t(), n_pad=48)]
+                t = GeoWeightsTC()
+                (t.w1p, t.w2p, t.w3p, t.w4p, t.w4tp, t.w3tp, t.w2tp, t.w1tp) = (i.data_ptr() for i in self.tc_imgs)
+                t.b1, t.b2, t.b3, t.b4 = (b[i].data_ptr() for i in range(4))
+                t.v5, t.c5 = v5.data_ptr(), c5
+                self.tc = t
             self._key = key
         return self
+
+
+PRECISION = {"mode": "fp32"}  # "fp32": exact SIMT kernels (1e-4); "bf16": tcgen05 tensor-core kernels (2e-2)
+
+
+def set_precision(mode: str):
+    assert mode in ("fp32", "bf16")
+    PRECISION["mode"] = mode
 
 
 def geo_sdf_raw(pack: GeoPack, slots: SlotSet, x, pts, feat_g, rbf, want_grad, want_jw, fill=1000.0):
@@ -99,8 +118,12 @@ def geo_sdf_raw(pack: GeoPack, slots: SlotSet, x, pts, feat_g, rbf, want_grad, w
     sdf = torch.full((n,), fill, dtype=torch.float32, device=dev)
     grad = torch.zeros(n, 3, dtype=torch.float32, device=dev) if want_grad else None
     jw = torch.empty(slots.rows_alloc(slots.K), 32, dtype=torch.float32, device=dev) if want_jw else None
-    call("spf_sdf_fwd_f32", C.byref(pack.f32), ptr(slots.list), ptr(slots.count), n, ptr(x), ptr(slots.pidx), slots.K,
-         ptr(pts), ptr(feat_g), float(rbf), ptr(sdf), ptr(grad), ptr(jw), stream())
+    if PRECISION["mode"] == "bf16":
+        call("spf_sdf_fwd_tc", C.byref(pack.tc), ptr(slots.list), ptr(slots.count), n, ptr(x), ptr(slots.pidx), slots.K,
+             ptr(pts), ptr(feat_g), float(rbf), ptr(sdf), ptr(grad), ptr(jw), stream())
+    else:
+        call("spf_sdf_fwd_f32", C.byref(pack.f32), ptr(slots.list), ptr(slots.count), n, ptr(x), ptr(slots.pidx), slots.K,
+             ptr(pts), ptr(feat_g), float(rbf), ptr(sdf), ptr(grad), ptr(jw), stream())
     return sdf, grad, jw
 
 
@@ -146,6 +169,27 @@ def _color_struct(W, b):
     return s, Wt
 
 
+def _color_struct_tc(W, b):
+    """bf16 weight images for k_color_fwd_tc / k_color_bwd_tc (input columns permuted to [c (64) | PE6 (39)])."""
+    W1perm = torch.cat([W[0][:, 39:103], W[0][:, :39]], dim=1)
+    imgs = [pack_sw128(W1perm), pack_sw128(W[1]), pack_sw128(W[2]), pack_sw128(W[2].t()), pack_sw128(W[1].t()),
+            pack_sw128(W[0][:, 39:103].t())]
+    s = ColorWeightsTC()
+    s.w1p, s.w2p, s.w3p, s.w3tp, s.w2tp, s.w1ftp = (i.data_ptr() for i in imgs)
+    s.b1, s.b2, s.b3 = (v.data_ptr() for v in b)
+    return s, imgs
+
+
+def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a_t^T @ b with fp32 output for bf16 operands (plain library GEMM: the weight-gradient product)."""
+    if a_t.dtype == torch.float32:
+        return a_t.t() @ b
+    try:
+        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return (a_t.t() @ b).float()
+
+
 class ColorField(torch.autograd.Function):
     """hbar[slot] = sum_k w_k/norm * h3_k with h3 = first three layers of F_color on [PE6(x-p_k) | c_k]
     (pointneus_disent.py:325-336; F_color.6 is applied per sample in RadianceHead)."""
@@ -153,46 +197,49 @@ class ColorField(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_c, W1, b1, W2, b2, W3, b3, x, slots: SlotSet, pts, rbf):
         dev = x.device
+        tcm = PRECISION["mode"] == "bf16"
         W = [w.detach().float().contiguous() for w in (W1, W2, W3)]
         b = [v.detach().float().contiguous() for v in (b1, b2, b3)]
-        s, Wt = _color_struct(W, b)
+        s, keep = (_color_struct_tc if tcm else _color_struct)(W, b)
         n, K = slots.n, slots.K
         hbar = torch.zeros(n, 256, dtype=torch.float32, device=dev)
         need = any(ctx.needs_input_grad[:7])
         rows = slots.rows_alloc(K)
         in0 = h1 = h2 = m3 = wn = None
         if need:
-            in0 = torch.empty(rows, 104, dtype=torch.float32, device=dev)
-            h1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-            h2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+            adt = torch.bfloat16 if tcm else torch.float32
+            in0 = torch.empty(rows, 112 if tcm else 104, dtype=adt, device=dev)
+            h1 = torch.empty(rows, 256, dtype=adt, device=dev)
+            h2 = torch.empty(rows, 256, dtype=adt, device=dev)
             m3 = torch.empty(rows, 8, dtype=torch.int32, device=dev)
             wn = torch.empty(rows, dtype=torch.float32, device=dev)
-        call("spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(x.contiguous()), ptr(slots.pidx), K,
-             ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0), ptr(h1), ptr(h2), ptr(m3), ptr(wn),
-             stream())
-        ctx.slots, ctx.saved_t = slots, (W, b, Wt, in0, h1, h2, m3, wn)
+        call("spf_color_fwd_tc" if tcm else "spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
+             ptr(x.contiguous()), ptr(slots.pidx), K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0),
+             ptr(h1), ptr(h2), ptr(m3), ptr(wn), stream())
+        ctx.slots, ctx.saved_t, ctx.tcm = slots, (s, keep, W, b, in0, h1, h2, m3, wn), tcm
         ctx.feat_shape = feat_c.shape
         return hbar
 
     @staticmethod
     def backward(ctx, d_hbar):
-        slots = ctx.slots
-        W, b, Wt, in0, h1, h2, m3, wn = ctx.saved_t
+        slots, tcm = ctx.slots, ctx.tcm
+        s, keep, W, b, in0, h1, h2, m3, wn = ctx.saved_t
         dev = d_hbar.device
-        s, _keep = _color_struct(W, b)
         rows = slots.rows_alloc(slots.K)
-        dz1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-        dz2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-        dz3 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
+        adt = torch.bfloat16 if tcm else torch.float32
+        dz1 = torch.empty(rows, 256, dtype=adt, device=dev)
+        dz2 = torch.empty(rows, 256, dtype=adt, device=dev)
+        dz3 = torch.empty(rows, 256, dtype=adt, device=dev)
         gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
-        call("spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
-             ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2), ptr(dz3), ptr(gfeat),
-             stream())
+        call("spf_color_bwd_tc" if tcm else "spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n,
+             ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
+             ptr(dz3), ptr(gfeat), stream())
         r = slots.V * slots.K
         # plain weight-gradient GEMMs (library): dW = dZ^T @ A over the compact pair rows
-        dW3, db3 = dz3[:r].t() @ h2[:r], dz3[:r].sum(0)
-        dW2, db2 = dz2[:r].t() @ h1[:r], dz2[:r].sum(0)
-        dW1, db1 = dz1[:r].t() @ in0[:r, :103], dz1[:r].sum(0)
+        dW3, db3 = _mm_f32(dz3[:r], h2[:r]), dz3[:r].float().sum(0) if not tcm else dz3[:r].sum(0, dtype=torch.float32)
+        dW2, db2 = _mm_f32(dz2[:r], h1[:r]), dz2[:r].sum(0, dtype=torch.float32)
+        dW1p, db1 = _mm_f32(dz1[:r], in0[:r]), dz1[:r].sum(0, dtype=torch.float32)
+        dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1) if tcm else dW1p[:, :103]
         return gfeat, dW1, db1, dW2, db2, dW3, db3, None, None, None, None
 
 

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import call, ptr, stream
-from .fields import ColorField, Composite, GeoPack, GeoSDF, RadianceHead, SlotSet, TVRegul, geo_sdf_raw
+from .fields import ColorField, Composite, GeoPack, GeoSDF, RadianceHead, SlotSet, TVRegul, geo_sdf_raw, set_precision
 from .knnquery import VoxelGrid
 
 
@@ -198,8 +198,11 @@ class ErrorBoundSampler_pn:
 class PointVolSDF(nn.Module):
     def __init__(self, conf, scan_id=None, dataset=None, neural_points: Optional[torch.Tensor] = None,
                  neural_colors: Optional[torch.Tensor] = None, device="cuda", ranges=None,
-                 max_points_per_voxel: int = 26, max_occ_voxels: int = 20000):
+                 max_points_per_voxel: int = 26, max_occ_voxels: int = 20000, precision: str = "fp32"):
         super().__init__()
+        # "fp32": exact SIMT kernels (1e-4 vs the reference); "bf16": tcgen05 tensor-core kernels (2e-2)
+        assert precision in ("fp32", "bf16")
+        self.precision = precision
         if not isinstance(conf, _Conf) and isinstance(conf, dict):
             conf = _Conf(conf)
         self.conf = conf
@@ -268,6 +271,7 @@ class PointVolSDF(nn.Module):
     # ------------------------------------------------------------------ point SDF queries
     def sdf_importance(self, inputs: torch.Tensor) -> torch.Tensor:
         """pointneus_disent.py:348-421: SDF at points [N,3] -> [N], 1000 where no neighbour."""
+        set_precision(self.precision)
         x = inputs.detach().contiguous().float()
         slots = self._point_slots(x)
         sdf, _, _ = geo_sdf_raw(self._pack(), slots, x, self.neural_pts, self.neural_feats_geometry.detach(),
@@ -281,6 +285,7 @@ class PointVolSDF(nn.Module):
     def pseudo_sdf(self, inputs: torch.Tensor, dense: bool = False):
         """pointneus_disent.py:423-495: SDF at points with autograd; [V,1] over the valid points (reference
         contract, one host sync) or, with dense=True, ([N] with 1000 fill, valid mask) without a sync."""
+        set_precision(self.precision)
         x = inputs.contiguous().float()
         slots = self._point_slots(x.detach())
         sdf, _ = GeoSDF.apply(self.neural_feats_geometry, x, slots, self._pack(), self.neural_pts, self.conf.rbf, False)
@@ -306,6 +311,7 @@ class PointVolSDF(nn.Module):
 
     # ------------------------------------------------------------------ forward (pointneus_disent.py:614-892)
     def forward(self, input, fast=-1, rng=None, dense_outputs: bool = False):
+        set_precision(self.precision)
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
         iter_step = input.get("iter_step", 1)
         dev = self.neural_pts.device
