@@ -219,6 +219,23 @@ int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const i
                      const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                      const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
                      void* stream);
+typedef struct {
+  const uint8_t* w4p;    /* pack(F_color.6.weight) */
+  const uint8_t* r1fp;   /* pack(R.0.weight[:, 21:277])  (the PE3(dir) columns enter through zpe) */
+  const uint8_t* r2p;    /* pack(R.2.weight) */
+  const uint8_t* r3p;    /* pack(R.4.weight padded to [16][256]) */
+  const uint8_t* r3tp;   /* pack(R.4.weight^T padded to [256][16 -> 64]) */
+  const uint8_t* r2tp; const uint8_t* r1ftp; const uint8_t* w4tp;  /* pack(weight^T) for dgrad */
+  const float* b4; const float* rb2; const float* rb3;
+} spf_head_weights_tc;
+/* zpe [R,256] = PE3(dir) @ R.0.weight[:, :21]^T + R.0.bias (fp32, per ray).  Saved bf16 [rows,256] by compact sample
+ * row: hb (= hbar), f, a1, a2. */
+int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                    const float* hbar, const float* zpe, int32_t Smax, float* rgb, void* hb, void* f, void* a1, void* a2,
+                    void* stream);
+int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                    const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
+                    void* dz1, void* dz2, float* dz3, void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

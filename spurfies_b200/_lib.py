@@ -47,6 +47,12 @@ class ColorWeightsTC(C.Structure):
                 ("w2tp", C.c_void_p), ("w1ftp", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p)]
 
 
+class HeadWeightsTC(C.Structure):
+    _fields_ = [("w4p", C.c_void_p), ("r1fp", C.c_void_p), ("r2p", C.c_void_p), ("r3p", C.c_void_p),
+                ("r3tp", C.c_void_p), ("r2tp", C.c_void_p), ("r1ftp", C.c_void_p), ("w4tp", C.c_void_p),
+                ("b4", C.c_void_p), ("rb2", C.c_void_p), ("rb3", C.c_void_p)]
+
+
 class ColorWeightsF32(C.Structure):
     _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
                 ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p)]
@@ -90,6 +96,8 @@ _SIGS = {
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
     "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
+    "spf_head_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
     "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }

@@ -16,25 +16,52 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ColorWeightsF32, ColorWeightsTC, GeoWeightsF32, GeoWeightsTC, HeadWeightsF32, call, ptr, stream
+from ._lib import (ColorWeightsF32, ColorWeightsTC, GeoWeightsF32, GeoWeightsTC, HeadWeightsF32, HeadWeightsTC, call, ptr,
+                   stream)
 from .packing import pack_sw128
 
 K_NEIGH = 8
 ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
 
 
+class Arena:
+    """Persistent device buffers for the big per-step intermediates (saved activations, Jacobian rows, dZ rows).
+    They are sized for the worst case (every slot valid) and would otherwise be cudaMalloc'ed and freed every step
+    (several GB): the caching allocator then dominates the step.  One step is in flight per model and everything is
+    stream-ordered, so reusing the same storage step after step is safe."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, name: str, shape, dtype, device) -> torch.Tensor:
+        key = (name, str(device))
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf[:nbytes].view(dtype).view(*shape)
+
+    @classmethod
+    def clear(cls):
+        cls._bufs.clear()
+
+
 class SlotSet:
     """Compacted list of the valid slots of one query (utils.py:90-113 glue, without the host sync)."""
 
-    def __init__(self, pidx: torch.Tensor):
+    def __init__(self, pidx: torch.Tensor, tag: str = "q"):
         assert pidx.dtype == torch.int32 and pidx.is_contiguous()
+        self.tag = tag  # names this query's arena buffers ("fine", "coarse", "pseudo", ...)
         self.K = pidx.shape[-1]
         self.pidx = pidx.view(-1, self.K)
         self.n = self.pidx.shape[0]
         dev = pidx.device
         self.list = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
-        ws = torch.empty(_lib.lib.spf_compact_workspace_bytes(self.n), dtype=torch.uint8, device=dev)
+        ws = Arena.get("compact_ws", (_lib.lib.spf_compact_workspace_bytes(self.n),), torch.uint8, dev)
         call("spf_compact_valid", ptr(self.pidx), self.n, self.K, ptr(self.list), ptr(self.count), ptr(ws), ws.numel(),
              stream())
         # deferred host copy of the count: waited on only when somebody needs V on the host (wgrad GEMM sizes,
@@ -117,7 +144,7 @@ def geo_sdf_raw(pack: GeoPack, slots: SlotSet, x, pts, feat_g, rbf, want_grad, w
     dev = x.device
     sdf = torch.full((n,), fill, dtype=torch.float32, device=dev)
     grad = torch.zeros(n, 3, dtype=torch.float32, device=dev) if want_grad else None
-    jw = torch.empty(slots.rows_alloc(slots.K), 32, dtype=torch.float32, device=dev) if want_jw else None
+    jw = Arena.get(slots.tag + ".jw", (slots.rows_alloc(slots.K), 32), torch.float32, dev) if want_jw else None
     if PRECISION["mode"] == "bf16":
         call("spf_sdf_fwd_tc", C.byref(pack.tc), ptr(slots.list), ptr(slots.count), n, ptr(x), ptr(slots.pidx), slots.K,
              ptr(pts), ptr(feat_g), float(rbf), ptr(sdf), ptr(grad), ptr(jw), stream())
@@ -202,17 +229,18 @@ class ColorField(torch.autograd.Function):
         b = [v.detach().float().contiguous() for v in (b1, b2, b3)]
         s, keep = (_color_struct_tc if tcm else _color_struct)(W, b)
         n, K = slots.n, slots.K
-        hbar = torch.zeros(n, 256, dtype=torch.float32, device=dev)
+        tg = slots.tag
+        hbar = Arena.get(tg + ".hbar", (n, 256), torch.float32, dev)  # read back only at valid slots
         need = any(ctx.needs_input_grad[:7])
         rows = slots.rows_alloc(K)
         in0 = h1 = h2 = m3 = wn = None
         if need:
             adt = torch.bfloat16 if tcm else torch.float32
-            in0 = torch.empty(rows, 112 if tcm else 104, dtype=adt, device=dev)
-            h1 = torch.empty(rows, 256, dtype=adt, device=dev)
-            h2 = torch.empty(rows, 256, dtype=adt, device=dev)
-            m3 = torch.empty(rows, 8, dtype=torch.int32, device=dev)
-            wn = torch.empty(rows, dtype=torch.float32, device=dev)
+            in0 = Arena.get(tg + ".in0", (rows, 112 if tcm else 104), adt, dev)
+            h1 = Arena.get(tg + ".h1", (rows, 256), adt, dev)
+            h2 = Arena.get(tg + ".h2", (rows, 256), adt, dev)
+            m3 = Arena.get(tg + ".m3", (rows, 8), torch.int32, dev)
+            wn = Arena.get(tg + ".wn", (rows,), torch.float32, dev)
         call("spf_color_fwd_tc" if tcm else "spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
              ptr(x.contiguous()), ptr(slots.pidx), K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0),
              ptr(h1), ptr(h2), ptr(m3), ptr(wn), stream())
@@ -227,9 +255,10 @@ class ColorField(torch.autograd.Function):
         dev = d_hbar.device
         rows = slots.rows_alloc(slots.K)
         adt = torch.bfloat16 if tcm else torch.float32
-        dz1 = torch.empty(rows, 256, dtype=adt, device=dev)
-        dz2 = torch.empty(rows, 256, dtype=adt, device=dev)
-        dz3 = torch.empty(rows, 256, dtype=adt, device=dev)
+        tg = slots.tag
+        dz1 = Arena.get(tg + ".dz1", (rows, 256), adt, dev)
+        dz2 = Arena.get(tg + ".dz2", (rows, 256), adt, dev)
+        dz3 = Arena.get(tg + ".dz3", (rows, 256), adt, dev)
         gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
         call("spf_color_bwd_tc" if tcm else "spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n,
              ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
@@ -257,50 +286,77 @@ class RadianceHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hbar, W4, b4, R1, rb1, R2, rb2, R3, rb3, dirs, slots: SlotSet, Smax):
         dev = hbar.device
+        tcm = PRECISION["mode"] == "bf16"
         W = [w.detach().float().contiguous() for w in (W4, R1, R2, R3)]
         b = [v.detach().float().contiguous() for v in (b4, rb1, rb2, rb3)]
-        Wt = [w.t().contiguous() for w in W]
-        s = HeadWeightsF32()
-        s.w4t, s.b4, s.r1t, s.rb1, s.r2t, s.rb2, s.r3t, s.rb3 = (Wt[0].data_ptr(), b[0].data_ptr(), Wt[1].data_ptr(),
-                                                                  b[1].data_ptr(), Wt[2].data_ptr(), b[2].data_ptr(),
-                                                                  Wt[3].data_ptr(), b[3].data_ptr())
-        s.w4, s.r1, s.r2, s.r3 = (w.data_ptr() for w in W)
         n = slots.n
+        tg = slots.tag
         rgb = torch.zeros(n, 3, dtype=torch.float32, device=dev)
         rows = slots.rows_alloc(1)
         need = any(ctx.needs_input_grad[:9])
-        f = a1 = a2 = None
-        if need:
-            f = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-            a1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-            a2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
         hbar_c = hbar.detach().contiguous()
-        call("spf_head_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(dirs), int(Smax),
-             ptr(rgb), ptr(f), ptr(a1), ptr(a2), stream())
-        ctx.slots, ctx.saved_t, ctx.Smax = slots, (s, W, b, Wt, hbar_c, rgb, f, a1, a2, dirs), Smax
+        if tcm:
+            R1f = W[1][:, 21:].contiguous()
+            imgs = [pack_sw128(W[0]), pack_sw128(R1f), pack_sw128(W[2]), pack_sw128(W[3], n_pad=16),
+                    pack_sw128(W[3].t()), pack_sw128(W[2].t()), pack_sw128(R1f.t()), pack_sw128(W[0].t())]
+            s = HeadWeightsTC()
+            s.w4p, s.r1fp, s.r2p, s.r3p, s.r3tp, s.r2tp, s.r1ftp, s.w4tp = (i.data_ptr() for i in imgs)
+            s.b4, s.rb2, s.rb3 = b[0].data_ptr(), b[2].data_ptr(), b[3].data_ptr()
+            # per-ray constant part of R.0: PE3(dir) columns + bias, kept in fp32
+            zpe = torch.addmm(b[1], positional_encoding(dirs, 3), W[1][:, :21].t()).contiguous()
+            hb = f = a1 = a2 = None
+            if need:
+                hb = Arena.get(tg + ".hhb", (rows, 256), torch.bfloat16, dev)
+                f = Arena.get(tg + ".hf", (rows, 256), torch.bfloat16, dev)
+                a1 = Arena.get(tg + ".ha1", (rows, 256), torch.bfloat16, dev)
+                a2 = Arena.get(tg + ".ha2", (rows, 256), torch.bfloat16, dev)
+            call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(zpe), int(Smax),
+                 ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), stream())
+            ctx.saved_t = (s, imgs, W, b, hb, rgb, f, a1, a2, dirs)
+        else:
+            Wt = [w.t().contiguous() for w in W]
+            s = HeadWeightsF32()
+            s.w4t, s.b4, s.r1t, s.rb1, s.r2t, s.rb2, s.r3t, s.rb3 = (Wt[0].data_ptr(), b[0].data_ptr(), Wt[1].data_ptr(),
+                                                                      b[1].data_ptr(), Wt[2].data_ptr(), b[2].data_ptr(),
+                                                                      Wt[3].data_ptr(), b[3].data_ptr())
+            s.w4, s.r1, s.r2, s.r3 = (w.data_ptr() for w in W)
+            f = a1 = a2 = None
+            if need:
+                f = Arena.get(tg + ".hf", (rows, 256), torch.float32, dev)
+                a1 = Arena.get(tg + ".ha1", (rows, 256), torch.float32, dev)
+                a2 = Arena.get(tg + ".ha2", (rows, 256), torch.float32, dev)
+            call("spf_head_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(dirs), int(Smax),
+                 ptr(rgb), ptr(f), ptr(a1), ptr(a2), stream())
+            ctx.saved_t = (s, Wt, W, b, hbar_c, rgb, f, a1, a2, dirs)
+        ctx.slots, ctx.Smax, ctx.tcm = slots, Smax, tcm
         return rgb
 
     @staticmethod
     def backward(ctx, d_rgb):
-        slots = ctx.slots
-        s, W, b, Wt, hbar, rgb, f, a1, a2, dirs = ctx.saved_t
+        slots, tcm = ctx.slots, ctx.tcm
+        s, keep, W, b, hb, rgb, f, a1, a2, dirs = ctx.saved_t
         dev = d_rgb.device
         n = slots.n
+        tg = slots.tag
         rows = slots.rows_alloc(1)
-        d_hbar = torch.zeros(n, 256, dtype=torch.float32, device=dev)
-        dzf = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-        dz1 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-        dz2 = torch.empty(rows, 256, dtype=torch.float32, device=dev)
-        dz3 = torch.empty(rows, 4, dtype=torch.float32, device=dev)
-        call("spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
-             ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), stream())
+        adt = torch.bfloat16 if tcm else torch.float32
+        d_hbar = Arena.get(tg + ".d_hbar", (n, 256), torch.float32, dev)  # consumed only at valid slots
+        dzf = Arena.get(tg + ".hdzf", (rows, 256), adt, dev)
+        dz1 = Arena.get(tg + ".hdz1", (rows, 256), adt, dev)
+        dz2 = Arena.get(tg + ".hdz2", (rows, 256), adt, dev)
+        dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)
+        call("spf_head_bwd_tc" if tcm else "spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
+             ptr(d_rgb.contiguous()), ptr(rgb), ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3),
+             stream())
         V = slots.V
         lst = slots.list[:V].long()
-        dW4, db4 = dzf[:V].t() @ hbar[lst], dzf[:V].sum(0)
-        cat = torch.cat([positional_encoding(dirs[lst // ctx.Smax], 3), f[:V]], -1)
-        dR1, drb1 = dz1[:V].t() @ cat, dz1[:V].sum(0)
-        dR2, drb2 = dz2[:V].t() @ a1[:V], dz2[:V].sum(0)
-        dR3, drb3 = dz3[:V, :3].t() @ a2[:V], dz3[:V, :3].sum(0)
+        hb_v = hb[:V] if tcm else hb[lst]
+        dW4, db4 = _mm_f32(dzf[:V], hb_v), dzf[:V].sum(0, dtype=torch.float32)
+        pe = positional_encoding(dirs[lst // ctx.Smax], 3).to(adt)
+        dR1 = torch.cat([_mm_f32(dz1[:V], pe), _mm_f32(dz1[:V], f[:V])], dim=1)
+        drb1 = dz1[:V].sum(0, dtype=torch.float32)
+        dR2, drb2 = _mm_f32(dz2[:V], a1[:V]), dz2[:V].sum(0, dtype=torch.float32)
+        dR3, drb3 = dz3[:V, :3].t() @ a2[:V].float(), dz3[:V, :3].sum(0)
         return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
 
 

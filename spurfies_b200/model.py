@@ -264,9 +264,9 @@ class PointVolSDF(nn.Module):
     def _pack(self) -> GeoPack:
         return self._geo_pack.get(self.F_geometry, self.T)
 
-    def _point_slots(self, x: torch.Tensor) -> SlotSet:
+    def _point_slots(self, x: torch.Tensor, tag: str = "points") -> SlotSet:
         pidx = self._grid().query_points(x.contiguous().float(), self.conf.k, self.conf.r)
-        return SlotSet(pidx)
+        return SlotSet(pidx, tag)
 
     # ------------------------------------------------------------------ point SDF queries
     def sdf_importance(self, inputs: torch.Tensor) -> torch.Tensor:
@@ -287,7 +287,7 @@ class PointVolSDF(nn.Module):
         contract, one host sync) or, with dense=True, ([N] with 1000 fill, valid mask) without a sync."""
         set_precision(self.precision)
         x = inputs.contiguous().float()
-        slots = self._point_slots(x.detach())
+        slots = self._point_slots(x.detach(), "pseudo")
         sdf, _ = GeoSDF.apply(self.neural_feats_geometry, x, slots, self._pack(), self.neural_pts, self.conf.rbf, False)
         if dense:
             return sdf, slots.valid_mask()
@@ -330,7 +330,7 @@ class PointVolSDF(nn.Module):
         points = self.ray_sampler.last_points  # cam_loc + z * dir, produced by the sampler kernel
         # kNN (pointneus_disent.py:654-660)
         pidx, loc, _, nvalid = grid.query_dense(points, K, self.conf.r, S)
-        slots = SlotSet(pidx)
+        slots = SlotSet(pidx, "fine")
         n = R * S
         # filter_points (pointneus_disent.py:666-669)
         t = torch.empty(R, S, dtype=torch.float32, device=dev)

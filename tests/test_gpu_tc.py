@@ -161,8 +161,8 @@ def test_color_field_tc_vs_fp32():
         model.zero_grad()
         hbar = ColorField.apply(model.neural_feats_color, fc[0].weight, fc[0].bias, fc[1].weight, fc[1].bias, fc[2].weight,
                                 fc[2].bias, q, slots, model.neural_pts, 45.0)
-        (hbar * up).sum().backward()
-        res[mode] = [hbar.detach().clone(), model.neural_feats_color.grad.clone()] + [p.grad.clone() for m in fc[:3] for p in (m.weight, m.bias)]
+        (hbar * up)[slots.valid_mask()].sum().backward()
+        res[mode] = [torch.where(slots.valid_mask()[:, None], hbar.detach(), torch.zeros(())).clone(), model.neural_feats_color.grad.clone()] + [p.grad.clone() for m in fc[:3] for p in (m.weight, m.bias)]
     fields.set_precision("fp32")
     names = ["hbar", "d latent", "dW1", "db1", "dW2", "db2", "dW3", "db3"]
     errs = {n: float((a - b).abs().max() / b.abs().max()) for n, a, b in zip(names, res["bf16"], res["fp32"])}
