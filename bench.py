@@ -156,11 +156,17 @@ def run_ours(args):
     for i in range(args.warmup):
         one(db[i % nb])
     barrier()
+    graphed = False
+    if args.cuda_graph:
+        graphed = step.capture(*split(db[0]))
+        for i in range(2):
+            one(db[i % nb])
+        barrier()
     # ---------------- timed region 1: inputs resident in HBM
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    _lib.profile_reset(True)
+    _lib.profile_reset(not graphed)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -171,6 +177,18 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     prof = _lib.profile_collect()
     _lib.profile_reset(False)
+    prof_steps = args.steps
+    if graphed:
+        # a replayed CUDA graph cannot be instrumented per kernel: time the SAME kernels on the same batches with CUDA
+        # events around every C-ABI call in eager steps run right after the timed region
+        prof_steps = min(args.steps, 5)
+        _lib.profile_reset(True)
+        for i in range(prof_steps):
+            b, g, r = split(db[(args.warmup + i) % nb])
+            step._eager(b, g, r)
+        prof = _lib.profile_collect()
+        _lib.profile_reset(False)
+        barrier()
     pairs_per_step = float(model._last["slots"].V) * 8  # last step's fine-pass pairs (representative)
     # ---------------- timed region 2: end to end from pinned host buffers, loss read back every step
     barrier()
@@ -212,7 +230,7 @@ def run_ours(args):
             "flops_per_pair_executed": GEO_FLOPS_EXEC,
             "achieved_executed": GEO_FLOPS_EXEC * pairs_per_step / (ms_launch * 1e-3) / 1e12,
             "precision_mode": "bf16 tcgen05 (tensor-core mode)" if args.precision == "bf16" else "fp32 SIMT (exact mode)"}
-    launches = sum(v["calls"] * LAUNCHES.get(k, 1) for k, v in prof.items())
+    launches = int(sum(v["calls"] * LAUNCHES.get(k, 1) for k, v in prof.items()) * args.steps / prof_steps)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -221,13 +239,16 @@ def run_ours(args):
                                "full training step (coarse pass + error-bounded sampler + kNN + fields + compositing + "
                                "loss + backward + Adam)" % (N_POINTS, RAYS),
                    "rays_per_gpu": RAYS, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
+                   "cuda_graph": graphed, "cuda_graph_note": step.graph_error,
                    "l2": "distinct ray batch each step; per-step working set (saved activations, > 1 GB) >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,
-        "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernels_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernel_timing": ("CUDA events around each C-ABI call, eager re-run of %d of the timed steps (graph replay cannot be "
+                          "instrumented)" % prof_steps) if graphed else "CUDA events around each C-ABI call inside the timed region",
     }
     if args.cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=1)
@@ -306,6 +327,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=128)
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="run the step eagerly instead of replaying it as one CUDA graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core field kernels (2e-2 tolerance); fp32: exact SIMT kernels (1e-4)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

@@ -231,11 +231,21 @@ typedef struct {
 /* zpe [R,256] = PE3(dir) @ R.0.weight[:, :21]^T + R.0.bias (fp32, per ray).  Saved bf16 [rows,256] by compact sample
  * row: hb (= hbar), f, a1, a2. */
 int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                    const float* hbar, const float* zpe, int32_t Smax, float* rgb, void* hb, void* f, void* a1, void* a2,
-                    void* stream);
+                    const float* hbar, const float* zpe, const float* ray_dirs, int32_t Smax, float* rgb, void* hb, void* f,
+                    void* a1, void* a2, void* pe /*[rows,32] bf16: PE3(dir) per sample*/, void* stream);
+/* dz3 is bf16 [rows,16] (3 used); drb3 [3] (fp32) is accumulated in-kernel */
 int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
-                    void* dz1, void* dz2, float* dz3, void* stream);
+                    void* dz1, void* dz2, void* dz3, float* drb3, void* stream);
+/* bf16 128B-swizzled k-block-major image of W [N][K] (row stride ld, fp32) or of its transpose (then W is [K][N]);
+ * out holds ceil(K/64) * n_pad * 128 bytes. */
+int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
+                   void* stream);
+/* weight gradient of one linear layer: dW[256][N] += dZ^T @ A, db[256] += colsum(dZ) (both accumulated in fp32), over
+ * the first ceil(count * rows_per_unit / 128) * 128 rows of dZ [.,256] / A [.,lda] (bf16, row-major): exactly the rows
+ * the dgrad kernels write.  N multiple of 16, <= 256.  No host synchronisation. */
+int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count, int32_t rows_per_unit,
+                 int64_t n_max, float* dW, float* db, void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

@@ -621,9 +621,9 @@ extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* li
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_head_fwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
-              const float* __restrict__ hbar, const float* __restrict__ zpe, int Smax, float* __restrict__ rgb,
-              __nv_bfloat16* __restrict__ hb_s, __nv_bfloat16* __restrict__ f_s, __nv_bfloat16* __restrict__ a1_s,
-              __nv_bfloat16* __restrict__ a2_s) {
+              const float* __restrict__ hbar, const float* __restrict__ zpe, const float* __restrict__ dirs, int Smax,
+              float* __restrict__ rgb, __nv_bfloat16* __restrict__ hb_s, __nv_bfloat16* __restrict__ f_s,
+              __nv_bfloat16* __restrict__ a1_s, __nv_bfloat16* __restrict__ a2_s, __nv_bfloat16* __restrict__ pe_s) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + OFF_A;
   uint8_t* sW = smem + OFF_W;
@@ -655,6 +655,28 @@ k_head_fwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __
     const size_t grow = (size_t)tile * TC_ROWS + row;  // compact sample row
     const int slot = (tile * TC_ROWS + row < V) ? list[tile * TC_ROWS + row] : -1;
     const float* zrow = zpe + (size_t)(slot >= 0 ? slot / Smax : 0) * 256;
+    if (pe_s && half == 1) {  // PE3(dir) (21 values, embedder.py:10-36) padded to 32: operand of the R.0 weight gradient
+      float pe[32];
+      float d[3] = {0.f, 0.f, 0.f};
+      if (slot >= 0) { const int ray = slot / Smax; d[0] = dirs[3 * ray]; d[1] = dirs[3 * ray + 1]; d[2] = dirs[3 * ray + 2]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pe[a] = d[a];
+      float fr = 1.0f;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float sv, cv;
+          sincosf(d[a] * fr, &sv, &cv);
+          pe[3 + 6 * l + a] = slot >= 0 ? sv : 0.0f;
+          pe[6 + 6 * l + a] = slot >= 0 ? cv : 0.0f;
+        }
+        fr *= 2.0f;
+      }
+#pragma unroll
+      for (int j = 21; j < 32; ++j) pe[j] = 0.0f;
+      store_g32(pe_s + grow * 32, pe);
+    }
     // A0 = hbar[slot] (bf16)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -720,16 +742,17 @@ k_head_fwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __
 }
 
 extern "C" int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                               const float* hbar, const float* zpe, int32_t Smax, float* rgb, void* hb, void* f, void* a1,
-                               void* a2, void* stream_) {
-  if (!W || !list || !count || !hbar || !zpe || !rgb || Smax < 1) return SPF_ERR_INVALID;
+                               const float* hbar, const float* zpe, const float* dirs, int32_t Smax, float* rgb, void* hb,
+                               void* f, void* a1, void* a2, void* pe, void* stream_) {
+  if (!W || !list || !count || !hbar || !zpe || !dirs || !rgb || Smax < 1) return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
   int64_t tiles = (n_max + TC_ROWS - 1) / TC_ROWS;
   int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
   SPF_CUDA(cudaFuncSetAttribute(k_head_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "head_tc attr");
-  k_head_fwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(*W, list, count, hbar, zpe, Smax, rgb,
+  k_head_fwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(*W, list, count, hbar, zpe, dirs, Smax, rgb,
                                                                      (__nv_bfloat16*)hb, (__nv_bfloat16*)f,
-                                                                     (__nv_bfloat16*)a1, (__nv_bfloat16*)a2);
+                                                                     (__nv_bfloat16*)a1, (__nv_bfloat16*)a2,
+                                                                     (__nv_bfloat16*)pe);
   SPF_CHECK_LAUNCH("k_head_fwd_tc");
   return SPF_OK;
 }
@@ -740,7 +763,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_head_bwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
               const float* __restrict__ d_rgb, const float* __restrict__ rgb, const __nv_bfloat16* __restrict__ a1_s,
               const __nv_bfloat16* __restrict__ a2_s, float* __restrict__ d_hbar, __nv_bfloat16* __restrict__ dzf,
-              __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, float* __restrict__ dz3) {
+              __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
+              float* __restrict__ drb3) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + OFF_A;
   uint8_t* sW = smem + OFF_W;
@@ -774,8 +798,14 @@ k_head_bwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __
 #pragma unroll
         for (int c = 0; c < 3; ++c) { float y = rgb[3 * (size_t)slot + c]; g[c] = d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
       }
-      *reinterpret_cast<float4*>(dz3 + grow * 4) = make_float4(g[0], g[1], g[2], 0.f);
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 0)) = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
+      const uint4 gz = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
+      reinterpret_cast<uint4*>(dz3 + grow * 16)[0] = gz;                     // [rows,16] bf16, operand of the R.4 wgrad
+      reinterpret_cast<uint4*>(dz3 + grow * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (drb3) {                                                             // bias gradient of R.4
+        float s0 = warp_sum(g[0]), s1 = warp_sum(g[1]), s2 = warp_sum(g[2]);
+        if (lane == 0) { atomicAdd(drb3, s0); atomicAdd(drb3 + 1, s1); atomicAdd(drb3 + 2, s2); }
+      }
+      *reinterpret_cast<uint4*>(sA + sw128_off(row, 0)) = gz;
       *reinterpret_cast<uint4*>(sA + sw128_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll 1
@@ -833,7 +863,7 @@ k_head_bwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __
 
 extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar,
-                               void* dzf, void* dz1, void* dz2, float* dz3, void* stream_) {
+                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* stream_) {
   if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || !d_hbar || !dzf || !dz1 || !dz2 || !dz3)
     return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
@@ -842,8 +872,165 @@ extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list
   SPF_CUDA(cudaFuncSetAttribute(k_head_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "headb_tc attr");
   k_head_bwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(
       *W, list, count, d_rgb, rgb, (const __nv_bfloat16*)a1, (const __nv_bfloat16*)a2, d_hbar, (__nv_bfloat16*)dzf,
-      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, dz3);
+      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3);
   SPF_CHECK_LAUNCH("k_head_bwd_tc");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[256][N] += dZ^T @ A, db[256] += column sums of dZ, over the rows written by the dgrad kernels
+// (whole 128-row tiles; rows of invalid slots hold zeros), row count taken from the device-side slot count so the
+// step needs no host synchronisation.  HBM-bound (each operand row is read once): split-K over persistent CTAs,
+// 3-stage cp.async ring of 64-row tiles, both operands MN-major, two M=128 accumulators fill TMEM (512 columns),
+// fp32 vector atomics merge the per-CTA partials.
+// ------------------------------------------------------------------------------------------------
+#define WG_STAGE_BYTES 65536
+#define WG_STAGES 3
+#define WG_SMEM (WG_STAGES * WG_STAGE_BYTES + 256)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ act, int lda, int N,
+           const int* __restrict__ count, int rows_per_unit, float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);  // [WG_STAGES] stage free
+  uint64_t* bar_done = bar_s + WG_STAGES;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long rows = ((long long)(*count) * rows_per_unit + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+  const int ntiles = (int)(rows / 64);
+  if ((int)blockIdx.x >= ntiles) return;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) mbar_init(bar_s + s, 1);
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t sbase = smem_u32(smem);
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nchunk_act = N / 8;  // 16-byte chunks per act row
+  const uint32_t idesc = idesc_bf16_mn(128, N);
+  float bsum = 0.0f;
+
+  auto load_tile = [&](int it) {
+    const int st = it % WG_STAGES;
+    const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * 64;
+    const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    for (int e = tid; e < 64 * 32; e += TC_THREADS) {
+      const int k = e >> 5, mc = e & 31;
+      cp_async16(sdz + (mc >> 3) * 8192 + k * 128 + (((mc & 7) ^ (k & 7)) << 4), dz + (r0 + k) * 256 + mc * 8);
+    }
+    for (int e = tid; e < 64 * nchunk_act; e += TC_THREADS) {
+      const int k = e / nchunk_act, nc = e - k * nchunk_act;
+      cp_async16(sact + (nc >> 3) * 8192 + k * 128 + (((nc & 7) ^ (k & 7)) << 4), act + (r0 + k) * lda + nc * 8);
+    }
+  };
+
+  for (int it = 0; it < WG_STAGES - 1; ++it) {
+    if (it < my_tiles) load_tile(it);
+    cp_async_commit();
+  }
+  for (int it = 0; it < my_tiles; ++it) {
+    const int st = it % WG_STAGES;
+    cp_async_wait<WG_STAGES - 2>();   // tile `it` has landed (only the most recent group may still be in flight)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();                  // ... for every thread; also: everyone is done reading tile it-1
+    const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t bd = smem_desc_mn_sw128(sact + ks * 2048, 8192);
+        mma_bf16(tmem, smem_desc_mn_sw128(sdz + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+        mma_bf16(tmem + 256, smem_desc_mn_sw128(sdz + 16384 + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+      }
+      mma_commit(bar_s + st);
+    }
+    // refill the stage tile it-1 used (tile it+2 maps to it) once its MMAs have retired
+    const int nx = it + WG_STAGES - 1;
+    if (nx < my_tiles) {
+      if (it >= 1) mbar_wait(bar_s + (nx % WG_STAGES), (uint32_t)(((it - 1) / WG_STAGES) & 1));
+      load_tile(nx);
+    }
+    cp_async_commit();
+    // bias gradient: thread = output column, column sum over this tile's 64 rows (read from the swizzled tile)
+    {
+      const uint8_t* pdz = smem + st * WG_STAGE_BYTES + (tid >> 6) * 8192;
+      const int c = (tid & 63) >> 3, e = tid & 7;
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(pdz + k * 128 + ((c ^ (k & 7)) << 4) + e * 2);
+        bsum += __bfloat162float(v);
+      }
+    }
+  }
+  if (tid == 0) mma_commit(bar_done);
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  if (db) atomicAdd(db + tid, bsum);
+  // epilogue: thread = accumulator lane; warps 0-3 drain out rows 0..127, warps 4-7 rows 128..255
+  {
+    const int out_row = 128 * (warp >> 2) + 32 * (warp & 3) + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 256;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(t_lane + c0, v);
+      tmem_ld_wait();
+      float* dst = dW + (size_t)out_row * N + c0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        if (c0 + 4 * j4 < N) atomicAdd(reinterpret_cast<float4*>(dst) + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count,
+                            int32_t rows_per_unit, int64_t n_max, float* dW, float* db, void* stream_) {
+  if (!dz || !act || !count || !dW) return SPF_ERR_INVALID;
+  if (N % 16 || N < 16 || N > 256 || lda < N || lda % 8 || rows_per_unit < 1) return SPF_ERR_UNSUPPORTED;
+  if (n_max <= 0) return SPF_OK;
+  int64_t tiles = (n_max * rows_per_unit + 63) / 64;
+  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
+  SPF_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
+  k_wgrad_tc<<<grid, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)act, lda,
+                                                                  N, count, rows_per_unit, dW, db);
+  SPF_CHECK_LAUNCH("k_wgrad_tc");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight image packing (fp32 [N][K] row-major, or its transpose, -> bf16 k-block-major 128B-swizzled image)
+// thread = one 16-byte chunk of the image
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_sw128(const float* __restrict__ W, int ld, int N, int K, int transpose, int n_pad, int nkb,
+                             uint4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkb * n_pad * 8) return;
+  const int cs = i & 7, n = (i >> 3) % n_pad, kb = i / (8 * n_pad);
+  const int c = cs ^ (n & 7);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kb * 64 + c * 8 + e;
+    v[e] = (n < N && k < K) ? (transpose ? W[(size_t)k * ld + n] : W[(size_t)n * ld + k]) : 0.0f;
+  }
+  out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+extern "C" int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
+                              void* stream_) {
+  if (!W || !out || N < 1 || K < 1 || n_pad < N || n_pad % 8) return SPF_ERR_INVALID;
+  const int nkb = (K + 63) / 64;
+  const int total = nkb * n_pad * 8;
+  k_pack_sw128<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(W, ld, N, K, transpose, n_pad, nkb, (uint4*)out);
+  SPF_CHECK_LAUNCH("k_pack_sw128");
   return SPF_OK;
 }
 

@@ -96,6 +96,24 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// MN-major operand tile (the contraction index k is the SLOW index in memory): 64-element (128 B) rows along M/N,
+// 8 k-rows per 1024-B swizzle atom; panels of 64 M/N elements are `panel_bytes` apart (LBO), 8-row k groups 1024 B
+// apart (SBO).  One K=16 MMA step consumes two k groups: advance the start address by 2048 B per step.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t panel_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((panel_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// as idesc_bf16 but both operands MN-major (transposed in memory)
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // byte offset of (row, 16-byte chunk) inside one [rows x 64 bf16] SW128 k-block
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 

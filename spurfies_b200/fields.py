@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import (ColorWeightsF32, ColorWeightsTC, GeoWeightsF32, GeoWeightsTC, HeadWeightsF32, HeadWeightsTC, call, ptr,
                    stream)
-from .packing import pack_sw128
+from .packing import image_bytes, pack_sw128, pack_sw128_dev
 
 K_NEIGH = 8
 ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
@@ -64,19 +64,14 @@ class SlotSet:
         ws = Arena.get("compact_ws", (_lib.lib.spf_compact_workspace_bytes(self.n),), torch.uint8, dev)
         call("spf_compact_valid", ptr(self.pidx), self.n, self.K, ptr(self.list), ptr(self.count), ptr(ws), ws.numel(),
              stream())
-        # deferred host copy of the count: waited on only when somebody needs V on the host (wgrad GEMM sizes,
-        # ragged outputs); by then the GPU is long past this point of the stream.
-        self._count_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
-        self._count_host.copy_(self.count, non_blocking=True)
-        self._event = torch.cuda.Event()
-        self._event.record()
         self._V: Optional[int] = None
 
     @property
     def V(self) -> int:
+        """Number of valid slots ON THE HOST (one sync).  Only the reference's ragged return contracts and the exact
+        (fp32) mode's library wgrad GEMMs need it; the bf16 training step never does (CUDA-graph capturable)."""
         if self._V is None:
-            self._event.synchronize()
-            self._V = int(self._count_host[0])
+            self._V = int(self.count.item())
         return self._V
 
     def valid_mask(self) -> torch.Tensor:
@@ -196,15 +191,39 @@ def _color_struct(W, b):
     return s, Wt
 
 
+def _img(name, dev, nbytes):
+    return Arena.get("img." + name, (nbytes,), torch.uint8, dev)
+
+
 def _color_struct_tc(W, b):
-    """bf16 weight images for k_color_fwd_tc / k_color_bwd_tc (input columns permuted to [c (64) | PE6 (39)])."""
-    W1perm = torch.cat([W[0][:, 39:103], W[0][:, :39]], dim=1)
-    imgs = [pack_sw128(W1perm), pack_sw128(W[1]), pack_sw128(W[2]), pack_sw128(W[2].t()), pack_sw128(W[1].t()),
-            pack_sw128(W[0][:, 39:103].t())]
+    """bf16 weight images for k_color_fwd_tc / k_color_bwd_tc (input columns permuted to [c (64) | PE6 (39)]),
+    packed on the device by spf_pack_sw128 (six launches) into persistent buffers."""
+    dev = W[0].device
+    w1p = _img("c.w1p", dev, 65536)
+    pack_sw128_dev(w1p, W[0], 256, 64, col_off=39)                       # k-block 0: latent columns
+    pack_sw128_dev(w1p, W[0], 256, 39, col_off=0, row_off_bytes=32768)   # k-block 1: PE6 columns
+    imgs = [w1p]
+    for nm, w, tr in (("c.w2p", W[1], False), ("c.w3p", W[2], False), ("c.w3tp", W[2], True), ("c.w2tp", W[1], True)):
+        im = _img(nm, dev, 131072)
+        pack_sw128_dev(im, w, 256, 256, transpose=tr)
+        imgs.append(im)
+    w1ftp = _img("c.w1ftp", dev, 32768)
+    pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39)     # (W1[:, 39:103])^T : [64][256]
+    imgs.append(w1ftp)
     s = ColorWeightsTC()
     s.w1p, s.w2p, s.w3p, s.w3tp, s.w2tp, s.w1ftp = (i.data_ptr() for i in imgs)
     s.b1, s.b2, s.b3 = (v.data_ptr() for v in b)
     return s, imgs
+
+
+def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True):
+    """dW [256,N], db [256] (fp32) = spf_wgrad_tc over the rows the dgrad kernel wrote; no host sync."""
+    dev = dz.device
+    dW = torch.zeros(256, N, dtype=torch.float32, device=dev)
+    db = torch.zeros(256, dtype=torch.float32, device=dev) if want_db else None
+    call("spf_wgrad_tc", ptr(dz), ptr(act), int(lda), int(N), ptr(slots.count), int(rows_per_unit), slots.n, ptr(dW), ptr(db),
+         stream())
+    return dW, db
 
 
 def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -263,12 +282,16 @@ class ColorField(torch.autograd.Function):
         call("spf_color_bwd_tc" if tcm else "spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n,
              ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
              ptr(dz3), ptr(gfeat), stream())
-        r = slots.V * slots.K
-        # plain weight-gradient GEMMs (library): dW = dZ^T @ A over the compact pair rows
-        dW3, db3 = _mm_f32(dz3[:r], h2[:r]), dz3[:r].float().sum(0) if not tcm else dz3[:r].sum(0, dtype=torch.float32)
-        dW2, db2 = _mm_f32(dz2[:r], h1[:r]), dz2[:r].sum(0, dtype=torch.float32)
-        dW1p, db1 = _mm_f32(dz1[:r], in0[:r]), dz1[:r].sum(0, dtype=torch.float32)
-        dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1) if tcm else dW1p[:, :103]
+        if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
+            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K)
+            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K)
+            dW1p, db1 = _wgrad_tc(dz1, in0, 112, 112, slots, slots.K)
+            dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
+        else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
+            r = slots.V * slots.K
+            dW3, db3 = dz3[:r].t() @ h2[:r], dz3[:r].sum(0)
+            dW2, db2 = dz2[:r].t() @ h1[:r], dz2[:r].sum(0)
+            dW1, db1 = (dz1[:r].t() @ in0[:r])[:, :103], dz1[:r].sum(0)
         return gfeat, dW1, db1, dW2, db2, dW3, db3, None, None, None, None
 
 
@@ -296,23 +319,29 @@ class RadianceHead(torch.autograd.Function):
         need = any(ctx.needs_input_grad[:9])
         hbar_c = hbar.detach().contiguous()
         if tcm:
-            R1f = W[1][:, 21:].contiguous()
-            imgs = [pack_sw128(W[0]), pack_sw128(R1f), pack_sw128(W[2]), pack_sw128(W[3], n_pad=16),
-                    pack_sw128(W[3].t()), pack_sw128(W[2].t()), pack_sw128(R1f.t()), pack_sw128(W[0].t())]
+            imgs = []
+            for nm, w, N_, K_, tr, npad, co in (("h.w4p", W[0], 256, 256, False, 256, 0), ("h.r1fp", W[1], 256, 256, False, 256, 21),
+                                               ("h.r2p", W[2], 256, 256, False, 256, 0), ("h.r3p", W[3], 3, 256, False, 16, 0),
+                                               ("h.r3tp", W[3], 256, 3, True, 256, 0), ("h.r2tp", W[2], 256, 256, True, 256, 0),
+                                               ("h.r1ftp", W[1], 256, 256, True, 256, 21), ("h.w4tp", W[0], 256, 256, True, 256, 0)):
+                im = _img(nm, dev, image_bytes(npad, K_))
+                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co)
+                imgs.append(im)
             s = HeadWeightsTC()
             s.w4p, s.r1fp, s.r2p, s.r3p, s.r3tp, s.r2tp, s.r1ftp, s.w4tp = (i.data_ptr() for i in imgs)
             s.b4, s.rb2, s.rb3 = b[0].data_ptr(), b[2].data_ptr(), b[3].data_ptr()
             # per-ray constant part of R.0: PE3(dir) columns + bias, kept in fp32
             zpe = torch.addmm(b[1], positional_encoding(dirs, 3), W[1][:, :21].t()).contiguous()
-            hb = f = a1 = a2 = None
+            hb = f = a1 = a2 = pe = None
             if need:
                 hb = Arena.get(tg + ".hhb", (rows, 256), torch.bfloat16, dev)
                 f = Arena.get(tg + ".hf", (rows, 256), torch.bfloat16, dev)
                 a1 = Arena.get(tg + ".ha1", (rows, 256), torch.bfloat16, dev)
                 a2 = Arena.get(tg + ".ha2", (rows, 256), torch.bfloat16, dev)
-            call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(zpe), int(Smax),
-                 ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), stream())
-            ctx.saved_t = (s, imgs, W, b, hb, rgb, f, a1, a2, dirs)
+                pe = Arena.get(tg + ".hpe", (rows, 32), torch.bfloat16, dev)
+            call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(zpe), ptr(dirs),
+                 int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
+            ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
         else:
             Wt = [w.t().contiguous() for w in W]
             s = HeadWeightsF32()
@@ -327,7 +356,7 @@ class RadianceHead(torch.autograd.Function):
                 a2 = Arena.get(tg + ".ha2", (rows, 256), torch.float32, dev)
             call("spf_head_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(dirs), int(Smax),
                  ptr(rgb), ptr(f), ptr(a1), ptr(a2), stream())
-            ctx.saved_t = (s, Wt, W, b, hbar_c, rgb, f, a1, a2, dirs)
+            ctx.saved_t = (s, Wt, W, b, hbar_c, rgb.detach(), f, a1, a2, dirs)
         ctx.slots, ctx.Smax, ctx.tcm = slots, Smax, tcm
         return rgb
 
@@ -344,19 +373,30 @@ class RadianceHead(torch.autograd.Function):
         dzf = Arena.get(tg + ".hdzf", (rows, 256), adt, dev)
         dz1 = Arena.get(tg + ".hdz1", (rows, 256), adt, dev)
         dz2 = Arena.get(tg + ".hdz2", (rows, 256), adt, dev)
+        if tcm:
+            hb, pe = hb
+            dz3 = Arena.get(tg + ".hdz3b", (rows, 16), torch.bfloat16, dev)
+            drb3 = torch.zeros(3, dtype=torch.float32, device=dev)
+            call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
+                 ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), ptr(drb3), stream())
+            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1)
+            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1)
+            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False)
+            dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
+            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1)
+            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False)   # (a2^T @ dz3) = dR3^T, [256,16]
+            dR3 = dR3t[:, :3].t().contiguous()
+            return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)
-        call("spf_head_bwd_tc" if tcm else "spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
-             ptr(d_rgb.contiguous()), ptr(rgb), ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3),
-             stream())
+        call("spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
+             ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), stream())
         V = slots.V
         lst = slots.list[:V].long()
-        hb_v = hb[:V] if tcm else hb[lst]
-        dW4, db4 = _mm_f32(dzf[:V], hb_v), dzf[:V].sum(0, dtype=torch.float32)
-        pe = positional_encoding(dirs[lst // ctx.Smax], 3).to(adt)
-        dR1 = torch.cat([_mm_f32(dz1[:V], pe), _mm_f32(dz1[:V], f[:V])], dim=1)
-        drb1 = dz1[:V].sum(0, dtype=torch.float32)
-        dR2, drb2 = _mm_f32(dz2[:V], a1[:V]), dz2[:V].sum(0, dtype=torch.float32)
-        dR3, drb3 = dz3[:V, :3].t() @ a2[:V].float(), dz3[:V, :3].sum(0)
+        dW4, db4 = dzf[:V].t() @ hb[lst], dzf[:V].sum(0)
+        cat = torch.cat([positional_encoding(dirs[lst // ctx.Smax], 3), f[:V]], -1)
+        dR1, drb1 = dz1[:V].t() @ cat, dz1[:V].sum(0)
+        dR2, drb2 = dz2[:V].t() @ a1[:V], dz2[:V].sum(0)
+        dR3, drb3 = dz3[:V, :3].t() @ a2[:V], dz3[:V, :3].sum(0)
         return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
 
 
@@ -377,7 +417,9 @@ class Composite(torch.autograd.Function):
         call("spf_composite_fwd", ptr(sdf_c), ptr(delta), ptr(t), ptr(rgb_c), ptr(grad) if want_normal else None,
              ptr(pidx), K, ptr(nvalid), ptr(beta_c), R, Smax, ptr(weights), ptr(rgb), ptr(depth), ptr(acc), ptr(dist),
              ptr(normal), stream())
-        ctx.saved_t = (sdf_c, rgb_c, beta_c, delta, t, pidx, nvalid, weights)
+        # NB: save a detached alias, never the output object itself (output -> grad_fn -> ctx -> output is a reference
+        # cycle through C++ that keeps the whole autograd graph and its AccumulateGrad nodes alive forever)
+        ctx.saved_t = (sdf_c, rgb_c, beta_c, delta, t, pidx, nvalid, weights.detach())
         ctx.dims = (R, Smax, K)
         if normal is None:
             normal = torch.zeros(0, 3, device=dev)

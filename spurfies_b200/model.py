@@ -190,8 +190,11 @@ class ErrorBoundSampler_pn:
             not_converge = False
         if z_out is None:  # max_total_iters == 0: the reference would fail on `samples`; return the coarse samples
             z_out, self.last_points = z, pts
-        idx = torch.randint(z_out.shape[-1], (R,), device=dev)
-        z_samples_eik = torch.gather(z_out, 1, idx.unsqueeze(-1))  # ray_sampler.py:561-563 (unused downstream)
+        if rng is not None and "eik_idx" not in rng:
+            z_samples_eik = z_out[:, :1]  # ray_sampler.py:561-563 draws a random column; nothing downstream reads it
+        else:
+            idx = rng["eik_idx"].to(dev) if rng is not None else torch.randint(z_out.shape[-1], (R,), device=dev)
+            z_samples_eik = torch.gather(z_out, 1, idx.unsqueeze(-1))
         return z_out, z_samples_eik
 
 
@@ -381,8 +384,11 @@ class PointVolSDF(nn.Module):
                 output["grad_theta_dense"], output["grad_theta_mask"] = grad, slots.valid_mask()
             else:
                 output["grad_theta"] = grad[slots.list[:slots.V].long()]
-        self._last = {"slots": slots, "z_vals": z_vals, "ray_mask": ray_mask, "sdf": sdf, "delta": delta, "t": t,
-                      "rgb_s": rgb_s, "dist": dist, "acc": acc, "ray_dirs": ray_dirs, "cam_loc": cam_loc}
+        # detached views only: holding graph tensors here would keep last step's autograd graph (and its
+        # AccumulateGrad nodes) alive, which breaks CUDA-graph capture of the next step
+        self._last = {"slots": slots, "z_vals": z_vals, "ray_mask": ray_mask, "sdf": sdf.detach(), "delta": delta, "t": t,
+                      "rgb_s": rgb_s.detach(), "dist": dist.detach(), "acc": acc.detach(), "ray_dirs": ray_dirs,
+                      "cam_loc": cam_loc}
         return output
 
 

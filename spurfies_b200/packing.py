@@ -25,3 +25,21 @@ def pack_sw128(W: torch.Tensor, n_pad: int | None = None) -> torch.Tensor:
     src = (c[None, :] ^ (n[:, None] & 7))                                  # out chunk c holds in chunk c ^ (n & 7)
     t = torch.gather(t, 2, src[None, :, :, None].expand(nkb, n_pad, 8, 8))
     return t.contiguous().view(torch.uint8).reshape(-1)
+
+
+def pack_sw128_dev(out: torch.Tensor, W: torch.Tensor, N: int, K: int, transpose: bool = False, n_pad: int | None = None,
+                   col_off: int = 0, row_off_bytes: int = 0) -> None:
+    """Kernel version (spf_pack_sw128) for per-step packing of trainable weights: writes the image of
+    W[:, col_off:col_off+K] ([N, K]) -- or, with transpose, of W[:, col_off:col_off+N]^T where W is [K, .] -- into the
+    uint8 buffer `out` starting at byte `row_off_bytes`.  W must be fp32, CUDA, with unit column stride."""
+    import ctypes as C
+    from . import _lib
+    assert W.dtype == torch.float32 and W.is_cuda and W.stride(1) == 1
+    n_pad = n_pad or N
+    src = C.c_void_p(W.data_ptr() + 4 * col_off)
+    dst = C.c_void_p(out.data_ptr() + row_off_bytes)
+    _lib.call("spf_pack_sw128", src, int(W.stride(0)), int(N), int(K), int(bool(transpose)), int(n_pad), dst, _lib.stream())
+
+
+def image_bytes(N_pad: int, K: int) -> int:
+    return ((K + 63) // 64) * N_pad * 128

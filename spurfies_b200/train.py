@@ -24,10 +24,14 @@ class TrainStep:
         for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
             prm.requires_grad_(False)  # the local-prior SDF field is frozen (train.py:151-154)
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
+        cuda = self.params[0].is_cuda
+        self.opt = torch.optim.Adam(self.params, lr=lr, fused=cuda, capturable=cuda)
         self.grad_clip = grad_clip
         self.world_size = world_size
         self._flat = None
+        self._graph = None
+        self._static = None
+        self.graph_error = None
 
     def _allreduce_grads(self):
         if self.world_size <= 1:
@@ -55,7 +59,59 @@ class TrainStep:
                 p.grad.copy_(g)
             off += k
 
-    def __call__(self, batch: Dict[str, torch.Tensor], gt: Dict[str, torch.Tensor], rng=None) -> Dict[str, torch.Tensor]:
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def capture(self, batch, gt, rng) -> bool:
+        """Capture forward + loss + backward + (all-reduce) + clip + Adam into one CUDA graph.  Possible because the
+        bf16 step has no host synchronisation (slot counts stay on the device) and every big buffer is persistent.
+        Inputs are copied into static tensors before each replay.  Returns False (and stays eager) if capture fails."""
+        if self.model.precision != "bf16":
+            self.graph_error = "exact (fp32) mode sizes its library wgrad GEMMs on the host"
+            return False
+        try:
+            import gc
+            self.model._last = None
+            gc.collect()  # drop every reference to earlier eager steps' autograd graphs (see model.forward)
+            self._static = ({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()},
+                            {k: v.clone() for k, v in gt.items()}, {k: v.clone() for k, v in rng.items()})
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._eager(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_out = self._eager(*self._static)
+            self._graph = g
+            return True
+        except Exception as e:  # noqa: BLE001 - report and fall back to eager
+            import os, traceback
+            if os.environ.get("SPF_DEBUG_GRAPH"):
+                traceback.print_exc()
+            self._graph = None
+            self.graph_error = f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+            return False
+
+    def replay(self, batch, gt, rng):
+        sb, sg, sr = self._static
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                sb[k].copy_(v, non_blocking=True)
+        for k, v in gt.items():
+            sg[k].copy_(v, non_blocking=True)
+        for k, v in rng.items():
+            sr[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def __call__(self, batch, gt, rng=None) -> Dict[str, torch.Tensor]:
+        if self._graph is not None:
+            return self.replay(batch, gt, rng)
+        return self._eager(batch, gt, rng)
+
+    def _eager(self, batch: Dict[str, torch.Tensor], gt: Dict[str, torch.Tensor], rng=None) -> Dict[str, torch.Tensor]:
         self.model.train()
         out = self.model(batch, fast=1, rng=rng, dense_outputs=True)  # fast=1: train.py:345-346
         losses = self.loss(out, gt)

@@ -170,3 +170,23 @@ def test_color_field_tc_vs_fp32():
     # random-sign upstream: parameter-gradient sums are random walks, so mask flips show at ~sqrt(flip rate); the
     # end-to-end check with the real (coherent) loss gradient is tests/test_gpu_hotpath.py::test_bf16_mode_*
     assert errs["hbar"] < 2e-2 and all(v < 6e-2 for k, v in errs.items() if k != "d latent") and errs["d latent"] < 0.5, errs
+
+
+@pytest.mark.parametrize("n_units,rpu,N,lda", [(1000, 8, 256, 256), (37, 8, 112, 112), (5000, 1, 256, 256), (300, 1, 16, 64)])
+def test_wgrad_tc(n_units, rpu, N, lda):
+    """split-K tcgen05 weight-gradient kernel (MN-major operands, device-side row count) vs torch."""
+    from spurfies_b200 import _lib
+    g = torch.Generator().manual_seed(n_units)
+    rows = (n_units * rpu + 127) // 128 * 128
+    dz = torch.randn(rows + 256, 256, generator=g).cuda().to(torch.bfloat16)
+    act = torch.randn(rows + 256, lda, generator=g).cuda().to(torch.bfloat16)
+    count = torch.tensor([n_units], dtype=torch.int32, device="cuda")
+    dW = torch.zeros(256, N, device="cuda")
+    db = torch.zeros(256, device="cuda")
+    _lib.call("spf_wgrad_tc", _lib.ptr(dz), _lib.ptr(act), lda, N, _lib.ptr(count), rpu, n_units + 50, _lib.ptr(dW), _lib.ptr(db),
+              _lib.stream())
+    torch.cuda.synchronize()
+    ref = dz[:rows].float().t() @ act[:rows, :N].float()
+    refb = dz[:rows].float().sum(0)
+    assert float((dW - ref).abs().max() / ref.abs().max()) < 1e-4
+    assert float((db - refb).abs().max() / refb.abs().max()) < 1e-4
