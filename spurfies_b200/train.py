@@ -13,6 +13,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from .dist import FlatGradReducer
 from .model import PointVolSDF, VolSDFLoss
 
 
@@ -28,36 +29,13 @@ class TrainStep:
         self.opt = torch.optim.Adam(self.params, lr=lr, fused=cuda, capturable=cuda)
         self.grad_clip = grad_clip
         self.world_size = world_size
-        self._flat = None
+        self._reducer = FlatGradReducer(self.params, world_size)
         self._graph = None
         self._static = None
         self.graph_error = None
 
     def _allreduce_grads(self):
-        if self.world_size <= 1:
-            return
-        n = sum(p.numel() for p in self.params)
-        if self._flat is None or self._flat.numel() != n:
-            self._flat = torch.empty(n, dtype=torch.float32, device=self.params[0].device)
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            if p.grad is None:
-                self._flat[off:off + k].zero_()
-            else:
-                self._flat[off:off + k].copy_(p.grad.reshape(-1))
-            off += k
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.mul_(1.0 / self.world_size)
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            g = self._flat[off:off + k].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += k
+        self._reducer.reduce()
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def capture(self, batch, gt, rng) -> bool:
