@@ -105,6 +105,32 @@ def mlp(x, layers, act_last=False):
     return x
 
 
+# Arithmetic model of the product's tensor-core ("bf16") mode for the trainable colour path, used ONLY to check that
+# mode: operands of every matrix product (inputs, weights, inter-layer activations) are rounded to bf16, products are
+# accumulated in fp32, biases / LeakyReLU / interpolation / sigmoid stay fp32; the per-ray PE3(dir) columns of R.0 stay
+# fp32; F_color.6 (linear, no activation: pointneus_disent.py:83) is applied after the neighbour interpolation.
+# Off by default: the oracle then follows the reference's fp32 graph op for op.
+BF16_OPERANDS = False
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()  # differentiable (identity gradient)
+
+
+def _color_bf16_operands(p: Params, fin, dirs_v, w, norm, idx, V):
+    (W1, b1), (W2, b2), (W3, b3), (W4, b4) = p.F_color
+    (R1, rb1), (R2, rb2), (R3, rb3) = p.R
+    h = F.leaky_relu(F.linear(_bf(fin), _bf(W1), b1), LEAKY)
+    h = F.leaky_relu(F.linear(_bf(h), _bf(W2), b2), LEAKY)
+    h = F.leaky_relu(F.linear(_bf(h), _bf(W3), b3), LEAKY)
+    hbar = torch.zeros(V, 256).index_add_(0, idx, (w / norm[idx])[:, None] * h)
+    f = F.linear(_bf(hbar), _bf(W4), b4)
+    zpe = F.linear(positional_encoding(dirs_v, 3), R1[:, :21], rb1)
+    a1 = F.leaky_relu(F.linear(_bf(f), _bf(R1[:, 21:])) + zpe, LEAKY)
+    a2 = F.leaky_relu(F.linear(_bf(a1), _bf(R2), rb2), LEAKY)
+    return torch.sigmoid(F.linear(_bf(a2), _bf(R3), rb3))
+
+
 def get_beta(p: Params):
     return p.beta.abs() + p.beta_min  # density.py:28-30
 
@@ -398,11 +424,14 @@ def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: Sampl
                                         create_graph=True)[0]
         # get_color (pointneus_disent.py:325-346)
         fin = torch.cat([positional_encoding(x_pi, 6), p.neural_feats_color[nbr]], -1)
-        fcol = mlp(fin, p.F_color)
-        agg_feat = torch.zeros(V, 256).index_add_(0, idx, w[:, None] * fcol) / norm[:, None]
         dirs_v = dd.unsqueeze(1).expand(-1, S, -1)[vm]
-        h = mlp(torch.cat([positional_encoding(dirs_v, 3), agg_feat], -1), p.R)
-        colors = torch.sigmoid(h)
+        if BF16_OPERANDS:
+            colors = _color_bf16_operands(p, fin, dirs_v, w, norm, idx, V)
+        else:
+            fcol = mlp(fin, p.F_color)
+            agg_feat = torch.zeros(V, 256).index_add_(0, idx, w[:, None] * fcol) / norm[:, None]
+            h = mlp(torch.cat([positional_encoding(dirs_v, 3), agg_feat], -1), p.R)
+            colors = torch.sigmoid(h)
         sdf_filler = torch.ones(Rv, S, 1) * 1000
         sdf_filler[vm] = agg_sdf
         density_filler = torch.zeros(Rv, S, 1)
