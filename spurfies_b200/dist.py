@@ -57,11 +57,40 @@ class FlatGradReducer:
             self._flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
         return self._flat
 
+    def attach(self) -> torch.Tensor:
+        """Make every `p.grad` a view into the flat buffer.  Autograd then accumulates straight into it (in place), so
+        the all-reduce, the global-norm clip and the NaN guard are single passes over one tensor with no packing.
+        The owner must clear gradients with `zero()` (not `zero_grad(set_to_none=True)`, which would drop the views)."""
+        flat = self.flat()
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = flat[off:off + k].view_as(p)
+            off += k
+        return flat
+
+    def attached(self) -> bool:
+        if self._flat is None:
+            return False
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self._flat.data_ptr() + 4 * off or not p.grad.is_contiguous():
+                return False
+            off += p.numel()
+        return True
+
+    def zero(self) -> None:
+        self.flat().zero_()
+
     def reduce(self) -> None:
         """Average `p.grad` over the ranks in place (a missing grad counts as zero).  No-op for world_size 1."""
         if self.world_size <= 1:
             return
         flat = self.flat()
+        if self.attached():
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(1.0 / self.world_size)
+            return
         off = 0
         for p in self.params:
             k = p.numel()

@@ -93,15 +93,19 @@ class TrainStep:
         self.model.train()
         out = self.model(batch, fast=1, rng=rng, dense_outputs=True)  # fast=1: train.py:345-346
         losses = self.loss(out, gt)
-        self.opt.zero_grad(set_to_none=True)
+        if not self._reducer.attached():
+            self._reducer.attach()
+        flat = self._reducer.flat()
+        flat.zero_()                      # every p.grad is a view of `flat`: autograd accumulates into it in place
         losses["loss"].backward()
-        self._allreduce_grads()
-        if self.grad_clip > 0:
-            torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip, foreach=True)
-        # NaN / Inf guard (train.py:548-564): skip the update by zeroing the gradients, no host sync
-        finite = torch.stack([torch.isfinite(p.grad).all() for p in self.params if p.grad is not None]).all()
-        for p in self.params:
-            if p.grad is not None:
-                p.grad.mul_(finite.to(p.grad.dtype))
+        self._allreduce_grads()           # N > 1: one NCCL all-reduce of `flat`, no packing
+        # clip_grad_norm_(1.0) (train.py:360-361) and the NaN / Inf guard (train.py:548-564) share ONE reduction: the
+        # global norm is finite iff every gradient entry is.  When it is not, the gradients are zeroed (the reference
+        # drops them and skips the update; here Adam still decays its moments on such a step).  No host sync.
+        total = torch.linalg.vector_norm(flat, 2.0)
+        coef = torch.clamp(self.grad_clip / (total + 1e-6), max=1.0) if self.grad_clip > 0 else torch.ones_like(total)
+        coef = torch.where(torch.isfinite(total), coef, torch.zeros_like(coef))
+        flat.mul_(coef)
+        torch.nan_to_num_(flat, nan=0.0, posinf=0.0, neginf=0.0)
         self.opt.step()
         return losses

@@ -58,6 +58,16 @@ def _worker_reduce(rank, world, port, q):
     first = red.flat().data_ptr()
     red.reduce()
     ok = ok and red.flat().data_ptr() == first                      # persistent buffer (CUDA-graph capturable)
+    # attached mode: p.grad are views of the flat buffer, autograd accumulates into it, reduce() needs no packing
+    w = [torch.nn.Parameter(torch.ones(4, 2) * (rank + 1)), torch.nn.Parameter(torch.ones(3))]
+    red2 = FlatGradReducer(w, world)
+    flat = red2.attach()
+    (w[0].pow(2).sum() + (3.0 * w[1]).sum()).backward()
+    ok = ok and red2.attached() and torch.allclose(flat[:8], torch.full((8,), 2.0 * (rank + 1)))
+    red2.reduce()
+    ok = ok and red2.attached() and torch.allclose(w[0].grad, torch.full((4, 2), 3.0)) and torch.allclose(w[1].grad, torch.full((3,), 3.0))
+    red2.zero()
+    ok = ok and float(w[0].grad.abs().sum()) == 0.0
     mx = max_over_ranks([float(rank), 3.0 - rank], "cpu")
     ok = ok and mx == [1.0, 3.0]
     q.put((rank, bool(ok)))
