@@ -1,0 +1,195 @@
+// tile_engine.cuh -- CTA-pair (cta_group::2), warp-specialised tile engine for the per-pair MLP chains (mlp_tc2.cu).
+//
+// Why: in the first-generation kernels (mlp_tc.cu) every CTA streams a whole 256x256 bf16 weight image (128 KB) from L2
+// for every layer of every 128-row tile, and MMA / epilogue / weight load run back to back: ~3.5 us per tile-layer of
+// which 1.04 us is tensor time, and 5.3 TB/s of L2->SM weight traffic (44 % of the ~12 TB/s L2 cap) at only 41 % of the
+// tensor peak.  Here:
+//   * two CTAs of a cluster (one TPC) form a pair; the leader issues tcgen05.mma.cta_group::2 with M = 256: each CTA
+//     supplies its own 128 rows of A and HALF of the weight rows (N/2) -> each CTA loads 64 KB per layer instead of 128;
+//   * each CTA keeps TWO row tiles (X, Y) in flight against the same resident weights (two 256-column fp32 accumulators
+//     = all 512 TMEM columns): another 2x less weight traffic (32 KB per tile-layer), and the epilogue of one tile
+//     overlaps the MMAs of the other;
+//   * weights flow through a ring of 16 KB slots (one k-block of this CTA's half) filled by a producer thread with bulk
+//     copies (TMA engine) on mbarriers and released by tcgen05.commit, so the next layer's weights arrive while the
+//     current layer is still being multiplied;
+//   * roles: warps 0-7 epilogue (TMEM lane = tile row; warps 0-3 / 4-7 take the low / high 128 accumulator columns),
+//     warp 8 lane 0 = weight producer, warp 9 lane 0 = MMA issuer (leader CTA) or weight-arrival relay (peer CTA).
+//
+// Synchronisation (all mbarriers live at the same shared-memory offsets in both CTAs):
+//   w_full[s]   (1 + tx)  TMA landed this CTA's half of the chunk in slot s
+//   w_peer[s]   (1)       leader only: the peer's half landed (relay thread arrives remotely)
+//   w_empty[s]  (1)       commit-multicast: all MMAs that read slot s have completed (both CTAs may refill)
+//   a_ready[t]  (2)       leader only: both CTAs finished writing tile t's A operand and draining its accumulator
+//   acc_full[t] (1)       commit-multicast: tile t's accumulator holds the layer's result
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace eng {
+using namespace tc;
+
+constexpr int EPI_THREADS = 256;
+constexpr int THREADS = 320;
+constexpr int NSLOT = 6;
+constexpr int SLOT_BYTES = 16384;
+constexpr int A_BYTES = 65536;                       // 128 rows x 256 bf16, 4 k-blocks of 16 KB
+constexpr int OFF_A = 0;                             // A_X, A_Y
+constexpr int OFF_W = 2 * A_BYTES;
+constexpr int OFF_PART = OFF_W + NSLOT * SLOT_BYTES; // 2 tiles x 256 floats
+constexpr int OFF_BAR = OFF_PART + 2048;
+constexpr int SMEM_BYTES = OFF_BAR + 256;            // 231 680 <= 232 448
+constexpr int MAX_LAYERS = 8;
+
+struct Layer {
+  const uint8_t* img;   // packed image of W [N][K] (packing.py): k-block stride N*128 bytes
+  int nkb;              // k-blocks of 64
+  int ksteps;           // K / 16 actually multiplied
+  int N;                // output columns (multiple of 16, <= 256); each CTA holds N/2 weight rows
+};
+struct Chain {
+  Layer L[MAX_LAYERS];
+  int n;
+};
+
+struct Bars {
+  uint64_t* w_full;   // [NSLOT]
+  uint64_t* w_empty;  // [NSLOT]
+  uint64_t* w_peer;   // [NSLOT]
+  uint64_t* acc_full; // [2]
+  uint64_t* a_ready;  // [2]
+  uint32_t* tmem_ptr;
+};
+__device__ __forceinline__ Bars carve_bars(uint8_t* smem) {
+  Bars b;
+  b.w_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  b.w_empty = b.w_full + NSLOT;
+  b.w_peer = b.w_empty + NSLOT;
+  b.acc_full = b.w_peer + NSLOT;
+  b.a_ready = b.acc_full + 2;
+  b.tmem_ptr = reinterpret_cast<uint32_t*>(b.a_ready + 2);
+  return b;
+}
+
+// common prologue: barrier init, TMEM allocation (512 columns, both CTAs), cluster-wide visibility. Returns TMEM base.
+__device__ __forceinline__ uint32_t setup(uint8_t* smem, const Bars& b) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(b.w_full + s, 1); mbar_init(b.w_empty + s, 1); mbar_init(b.w_peer + s, 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(b.acc_full + t, 1); mbar_init(b.a_ready + t, 2); }
+    fence_mbar_init();
+  }
+  if ((threadIdx.x >> 5) == 0) tmem_alloc2(b.tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  return *b.tmem_ptr;
+}
+__device__ __forceinline__ void teardown(uint32_t tmem) {
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be signalling our barriers / the leader's MMAs still read our smem
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc2(tmem, 512);
+}
+
+// ---- weight producer (one thread per CTA) ----------------------------------------------------------
+__device__ __forceinline__ void producer_loop(const Chain& ch, int n_iter, uint32_t rank, uint8_t* smem, const Bars& b) {
+  uint32_t slot = 0, use = 0;
+  for (int it = 0; it < n_iter; ++it)
+    for (int l = 0; l < ch.n; ++l) {
+      const Layer L = ch.L[l];
+      const uint32_t bytes = (uint32_t)(L.N >> 1) * 128u;
+      for (int kb = 0; kb < L.nkb; ++kb) {
+        if (use > 0) mbar_wait(b.w_empty + slot, (use - 1) & 1);
+        mbar_expect_tx(b.w_full + slot, bytes);
+        bulk_g2s(smem + OFF_W + slot * SLOT_BYTES, L.img + (size_t)kb * ((size_t)L.N * 128) + (size_t)rank * bytes, bytes,
+                 b.w_full + slot);
+        if (++slot == NSLOT) { slot = 0; ++use; }
+      }
+    }
+}
+// ---- peer CTA: tell the leader when our half of each chunk has landed ----------------------------------
+__device__ __forceinline__ void relay_loop(const Chain& ch, int n_iter, const Bars& b) {
+  uint32_t slot = 0, use = 0;
+  for (int it = 0; it < n_iter; ++it)
+    for (int l = 0; l < ch.n; ++l)
+      for (int kb = 0; kb < ch.L[l].nkb; ++kb) {
+        mbar_wait(b.w_full + slot, use & 1);
+        mbar_arrive_remote(b.w_peer + slot, 0);
+        if (++slot == NSLOT) { slot = 0; ++use; }
+      }
+}
+// ---- leader CTA: MMA issue (one thread) ---------------------------------------------------------------
+__device__ __forceinline__ void mma_loop(const Chain& ch, int n_iter, uint8_t* smem, const Bars& b, uint32_t tmem) {
+  const uint32_t aA = smem_u32(smem + OFF_A), aW = smem_u32(smem + OFF_W);
+  uint32_t slot0 = 0, use0 = 0;
+  uint32_t ar_par = 0;   // bit t = parity of a_ready[t]
+  for (int it = 0; it < n_iter; ++it)
+    for (int l = 0; l < ch.n; ++l) {
+      const Layer L = ch.L[l];
+      const uint32_t idesc = idesc_bf16(256, L.N);
+      uint32_t slot = slot0, use = use0;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        slot = slot0; use = use0;
+        mbar_wait_cluster(b.a_ready + t, (ar_par >> t) & 1);
+        ar_par ^= 1u << t;
+        tc_fence_after();
+        for (int kb = 0; kb < L.nkb; ++kb) {
+          if (t == 0) {
+            mbar_wait(b.w_full + slot, use & 1);
+            mbar_wait_cluster(b.w_peer + slot, use & 1);
+            tc_fence_after();
+          }
+          const int ks_n = min(4, L.ksteps - 4 * kb);
+          for (int ks = 0; ks < ks_n; ++ks)
+            mma_bf16_2cta(tmem + t * 256, smem_desc_sw128(aA + t * A_BYTES + kb * 16384 + ks * 32),
+                          smem_desc_sw128(aW + slot * SLOT_BYTES + ks * 32), idesc, (kb | ks) != 0);
+          if (t == 1) mma_commit_2cta(b.w_empty + slot, 3);
+          if (++slot == NSLOT) { slot = 0; ++use; }
+        }
+        mma_commit_2cta(b.acc_full + t, 3);
+      }
+      slot0 = slot; use0 = use;
+    }
+}
+
+// ---- epilogue-side helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ void epi_bar() { named_bar_sync(1, EPI_THREADS); }
+// all epilogue threads: "tile t's A operand is written and its accumulator drained"
+__device__ __forceinline__ void signal_a_ready(const Bars& b, int t, uint32_t rank) {
+  tc_fence_before();
+  fence_proxy_async();
+  epi_bar();
+  if (threadIdx.x == 0) {
+    if (rank == 0) mbar_arrive_local(b.a_ready + t);
+    else mbar_arrive_remote(b.a_ready + t, 0);
+  }
+}
+__device__ __forceinline__ void wait_acc(const Bars& b, int t, uint32_t& par) {
+  mbar_wait(b.acc_full + t, (par >> t) & 1);
+  par ^= 1u << t;
+  tc_fence_after();
+}
+
+// write 32 consecutive columns [c0, c0+32) of this thread's row as bf16 into an A tile
+__device__ __forceinline__ void store_a32(uint8_t* sA, int row, int c0, const float* v) {
+  const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    *reinterpret_cast<uint4*>(sA + kb * 16384 + sw128_off(row, ch0 + q)) = u;
+  }
+}
+__device__ __forceinline__ void store_g32(__nv_bfloat16* dst, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
+}
+
+}  // namespace eng
