@@ -15,6 +15,7 @@ SOURCES = {
     "render.cu": ["-fmad=false"],
     "mlp_f32.cu": [],
     "mlp_tc.cu": [],
+    "mlp_tc2.cu": [],
 }
 
 
@@ -37,7 +38,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(CSRC, s.replace(".cu", ".o"))
         src = os.path.join(CSRC, s)
         if force or not os.path.exists(obj) or any(os.path.getmtime(obj) < os.path.getmtime(d) for d in deps if not d.endswith(".cu") or d == src):
-            cmd = [nvcc, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", *SOURCES[s], "-c", src, "-o", obj]
+            dbg = ["-DSPF_TIMELINE"] if os.environ.get("SPF_TIMELINE") == "1" else []
+            cmd = [nvcc, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", *SOURCES[s], *dbg, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.check_call(cmd)

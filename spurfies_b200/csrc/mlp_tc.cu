@@ -285,7 +285,7 @@ k_sdf_tc(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restri
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-extern "C" int spf_sdf_fwd_tc(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+extern "C" int spf_sdf_fwd_tc_gen1(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                               const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_g,
                               float rbf, float* sdf, float* grad, float* jw, void* stream_) {
   if (!W || !list || !count || !x || !pidx || !pts || !feat_g || !sdf) return SPF_ERR_INVALID;

@@ -38,197 +38,229 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
   const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
 
-  Chain ch;
-  ch.L[0] = {W.w1p, 1, 3, 256};
-  ch.L[1] = {W.w2p, 4, 16, 256};
-  ch.L[2] = {W.w3p, 4, 16, 256};
-  ch.L[3] = {W.w4p, 4, 16, 256};
-  ch.L[4] = {W.w4tp, 4, 16, 256};
-  ch.L[5] = {W.w3tp, 4, 16, 256};
-  ch.L[6] = {W.w2tp, 4, 16, 256};
-  ch.L[7] = {W.w1tp, 4, 16, 48};
-  ch.n = WITH_J ? 8 : 4;
-
+  Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b1..b4, v5
+  if (tid == 0) {
+    ch.L[0] = {W.w1p, 1, 3, 256};
+    ch.L[1] = {W.w2p, 4, 16, 256};
+    ch.L[2] = {W.w3p, 4, 16, 256};
+    ch.L[3] = {W.w4p, 4, 16, 256};
+    ch.L[4] = {W.w4tp, 4, 16, 256};
+    ch.L[5] = {W.w3tp, 4, 16, 256};
+    ch.L[6] = {W.w2tp, 4, 16, 256};
+    ch.L[7] = {W.w1tp, 4, 16, 48};
+    ch.n = WITH_J ? 8 : 4;
+  }
+  for (int i = tid; i < 256; i += THREADS) {
+    s_bias[i] = W.b1[i]; s_bias[256 + i] = W.b2[i]; s_bias[512 + i] = W.b3[i]; s_bias[768 + i] = W.b4[i];
+    s_bias[1024 + i] = W.v5[i];
+  }
   const uint32_t tmem = setup(smem, B);
 
-  if (warp == 8) {
+  if (warp == WARP_PRODUCER) {
     if (lane == 0) producer_loop(ch, n_iter, rank, smem, B);
-  } else if (warp == 9) {
-    if (lane == 0) {
-      if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);
-      else relay_loop(ch, n_iter, B);
-    }
+  } else if (warp == WARP_MMA) {
+    if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);   // whole warp, one elected lane issues
+    else if (lane == 0) relay_loop(ch, n_iter, B);
   } else {
-    // ---------------------------------------------------------------- epilogue warps
+    // ---------------------------------------------------------------- epilogue warps: group t owns tile t of this CTA
+    const int t = warp >> 3;
     const int row = 32 * (warp & 3) + lane;   // TMEM lane == pair row of the tile
-    const int half = warp >> 2;               // which 128 accumulator columns this thread reads
-    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int half = (warp >> 2) & 1;         // which 128 accumulator columns this thread reads
+    const uint32_t t_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256;
+    const uint32_t t_acc = t_row + half * 128;
+    uint8_t* sA = smem + OFF_A + t * A_BYTES;
+    float* part = s_part + t * 256;
     uint32_t acc_par = 0;
+    int sl_n = -1, p_n = -1;
+    {
+      const int li = (4 * cid + 2 * t + (int)rank) * 16 + (row >> 3);
+      if (n_iter > 0 && li < V) { sl_n = list[li]; p_n = pidx[(size_t)sl_n * 8 + (row & 7)]; }
+    }
     for (int it = 0; it < n_iter; ++it) {
-      const int st = cid + it * ncl;
-      int slot[2];
-      float wgt[2];
-      uint32_t bits[2][WITH_J ? 16 : 1];
-      float dot[2] = {0.0f, 0.0f};
+      const int tile = 4 * (cid + it * ncl) + 2 * t + (int)rank;
+      const int sl = sl_n, p = p_n;
       // ---------------- gather: A0 = [g (32) | x_pi hi (3) | x_pi lo (3) | 0 ...] as bf16, K = 48
+      float xp[3] = {0.f, 0.f, 0.f}, w = 0.f;
+      if (p >= 0) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        uint8_t* sA = smem + OFF_A + t * A_BYTES;
-        const int tile = 4 * st + 2 * t + (int)rank;
-        const int li = tile * 16 + (row >> 3);
-        const int sl = li < V ? list[li] : -1;
-        const int p = sl >= 0 ? pidx[(size_t)sl * 8 + (row & 7)] : -1;
-        float xp[3] = {0.f, 0.f, 0.f}, w = 0.f;
-        if (p >= 0) {
-#pragma unroll
-          for (int a = 0; a < 3; ++a) xp[a] = x[3 * (size_t)sl + a] - pts[3 * (size_t)p + a];
-          w = rbf_w2(xp[0], xp[1], xp[2], rbf);
-        }
-        slot[t] = sl;
-        wgt[t] = w;
-        if (half == 0) {
-          const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
-            uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-            *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
-          }
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32 + 24);
-          float4 a = p >= 0 ? src[0] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[1] : make_float4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sA + sw128_off(row, 3)) =
-              make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-          float hi[3], lo[3];
-#pragma unroll
-          for (int a3 = 0; a3 < 3; ++a3) {
-            hi[a3] = __bfloat162float(__float2bfloat16_rn(xp[a3]));
-            lo[a3] = xp[a3] - hi[a3];
-          }
-          *reinterpret_cast<uint4*>(sA + sw128_off(row, 4)) =
-              make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), 0u);
-          *reinterpret_cast<uint4*>(sA + sw128_off(row, 5)) = make_uint4(0, 0, 0, 0);
-        }
-        signal_a_ready(B, t, rank);
+        for (int a = 0; a < 3; ++a) xp[a] = x[3 * (size_t)sl + a] - pts[3 * (size_t)p + a];
+        w = rbf_w2(xp[0], xp[1], xp[2], rbf);
       }
-      // ---------------- forward chain
+      if (half == 0) {
+        const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32);
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const float* bias = l == 0 ? W.b1 : (l == 1 ? W.b2 : (l == 2 ? W.b3 : W.b4));
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          uint8_t* sA = smem + OFF_A + t * A_BYTES;
-          wait_acc(B, t, acc_par);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c0 = half * 128 + q * 32;
-            float v[32];
-            tmem_ld32(t_lane + t * 256 + c0, v);
-            float bb[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + j4);
-              bb[4 * j4] = b4.x; bb[4 * j4 + 1] = b4.y; bb[4 * j4 + 2] = b4.z; bb[4 * j4 + 3] = b4.w;
-            }
-            tmem_ld_wait();
-            uint32_t b = 0;
-            if (l < 3) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float tt = v[j] + bb[j];
-                b |= (tt > 0.0f ? 1u : 0u) << j;
-                v[j] = tt > 0.0f ? tt : LEAKY * tt;
-              }
-            } else {
-              float vv[32];
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(W.v5 + c0) + j4);
-                vv[4 * j4] = b4.x; vv[4 * j4 + 1] = b4.y; vv[4 * j4 + 2] = b4.z; vv[4 * j4 + 3] = b4.w;
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float tt = v[j] + bb[j];
-                const bool pos = tt > 0.0f;
-                b |= (pos ? 1u : 0u) << j;
-                tt = pos ? tt : LEAKY * tt;
-                dot[t] = fmaf(tt, vv[j], dot[t]);
-                v[j] = vv[j] * (pos ? 1.0f : LEAKY);   // g4 = v5 * lrelu'(z4)
-              }
-            }
-            if (WITH_J) bits[t][l * 4 + q] = b;
-            if (l < 3 || WITH_J) store_a32(sA, row, c0, v);
-          }
-          if (l == 3) s_part[t * 256 + half * 128 + row] = dot[t];
-          if (l < 3 || WITH_J) signal_a_ready(B, t, rank);
+        for (int q = 0; q < 3; ++q) {
+          float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
+          uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+          *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
         }
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32 + 24);
+        float4 a = p >= 0 ? src[0] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[1] : make_float4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA + sw128_off(row, 3)) =
+            make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        float hi[3], lo[3];
+#pragma unroll
+        for (int a3 = 0; a3 < 3; ++a3) {
+          hi[a3] = __bfloat162float(__float2bfloat16_rn(xp[a3]));
+          lo[a3] = xp[a3] - hi[a3];
+        }
+        *reinterpret_cast<uint4*>(sA + sw128_off(row, 4)) =
+            make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), 0u);
+        *reinterpret_cast<uint4*>(sA + sw128_off(row, 5)) = make_uint4(0, 0, 0, 0);
+      }
+      if ((tid & 255) == 0) TL(3, t, it);
+      signal_a_ready(B, t, rank);
+      // indices of the next super-tile: two dependent global loads taken off the next gather's critical path
+      sl_n = -1; p_n = -1;
+      if (it + 1 < n_iter) {
+        const int li = (tile + 4 * ncl) * 16 + (row >> 3);
+        if (li < V) { sl_n = list[li]; p_n = pidx[(size_t)sl_n * 8 + (row & 7)]; }
+      }
+      uint32_t bits[WITH_J ? 24 : 1];   // LeakyReLU sign bits of z1..z3 (local memory: the layer loop is a run-time loop)
+      float dot = 0.0f;
+      // ---------------- forward chain.  Epilogue cost matters as much as the MMAs here (K = 256 only): ~4.5 instructions
+      // per element -- fp32 bias add, LeakyReLU as max(z, 0.01 z), bf16x2 pack, and the LeakyReLU sign bits taken from
+      // the packed words (sign(h) == sign(z); 2 bits per word, accumulated with a shift + and-or).
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 256 + half * 128);
+        const float4* v54 = reinterpret_cast<const float4*>(s_bias + 1024 + half * 128);
+        wait_acc(B, t, acc_par);
+        if ((tid & 255) == 0) TL(0, t, l);
+        float v[2][16];
+        const int dbg = DBG_MODE;
+        if (dbg != 1) tmem_ld16(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (dbg != 1) {
+            tmem_ld_wait();
+            if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          }
+          float* vv = v[c & 1];
+          uint32_t pk[8];
+          uint32_t sb = 0;
+          if (dbg == 2) { if (vv[0] == 123.456f) part[0] = vv[1]; continue; }
+          if (l < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = bias4[c * 4 + q];
+              float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
+              z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
+              pk[2 * q] = pack_bf16(z0, z1);
+              pk[2 * q + 1] = pack_bf16(z2, z3);
+              if (WITH_J) {
+                sb = (sb >> 2) | (pk[2 * q] & 0x80008000u);
+                sb = (sb >> 2) | (pk[2 * q + 1] & 0x80008000u);
+              }
+            }
+            // word i of this chunk: its low / high element's "negative" bit sits at bit 1 + 2 i / 17 + 2 i of sb
+            if (WITH_J) bits[l * 8 + c] = sb;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = bias4[c * 4 + q];
+              const float4 vq = v54[c * 4 + q];
+              float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
+              dot = fmaf(fmaxf(z0, LEAKY * z0), vq.x, dot); dot = fmaf(fmaxf(z1, LEAKY * z1), vq.y, dot);
+              dot = fmaf(fmaxf(z2, LEAKY * z2), vq.z, dot); dot = fmaf(fmaxf(z3, LEAKY * z3), vq.w, dot);
+              if (WITH_J) {   // g4 = v5 * lrelu'(z4)
+                pk[2 * q] = pack_bf16(z0 > 0.0f ? vq.x : LEAKY * vq.x, z1 > 0.0f ? vq.y : LEAKY * vq.y);
+                pk[2 * q + 1] = pack_bf16(z2 > 0.0f ? vq.z : LEAKY * vq.z, z3 > 0.0f ? vq.w : LEAKY * vq.w);
+              }
+            }
+          }
+          if (l < 3 || WITH_J) {
+            const int c0 = half * 128 + c * 16;
+            uint8_t* dstA = sA + (c0 >> 6) * 16384;
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        if (l == 3) part[half * 128 + row] = dot;
+        if ((tid & 255) == 0) TL(1, t, l);
+        if (l < 3 || WITH_J) signal_a_ready(B, t, rank);
+        if ((tid & 255) == 0) TL(2, t, l);
       }
       if (WITH_J) {
         // ---------------- d sdf / d input chain: g_l = (g_{l+1} @ W_{l+1}) * lrelu'(z_l), J = g1 @ W1
-#pragma unroll
+#pragma unroll 1
         for (int l = 2; l >= 0; --l) {
+          uint32_t bw[8];
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            uint8_t* sA = smem + OFF_A + t * A_BYTES;
-            wait_acc(B, t, acc_par);
+          for (int q = 0; q < 8; ++q) bw[q] = bits[l * 8 + q];   // issued before the wait: latency hidden
+          wait_acc(B, t, acc_par);
+          if ((tid & 255) == 0) TL(0, t, 6 - l);
+          float v[2][16];
+          const int dbg = DBG_MODE;
+          if (dbg != 1) tmem_ld16(t_acc, v[0]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c0 = half * 128 + q * 32;
-              float v[32];
-              tmem_ld32(t_lane + t * 256 + c0, v);
+          for (int c = 0; c < 8; ++c) {
+            if (dbg != 1) {
               tmem_ld_wait();
-              const uint32_t b = bits[t][l * 4 + q];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= ((b >> j) & 1u) ? 1.0f : LEAKY;
-              store_a32(sA, row, c0, v);
+              if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
             }
-            signal_a_ready(B, t, rank);
+            float* vv = v[c & 1];
+            if (dbg == 2) { if (vv[0] == 123.456f) part[0] = vv[1]; continue; }
+            const uint32_t sb = bw[c];
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float m0 = (sb & (2u << (2 * i))) ? LEAKY : 1.0f;
+              const float m1 = (sb & (0x20000u << (2 * i))) ? LEAKY : 1.0f;
+              pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+            }
+            const int c0 = half * 128 + c * 16;
+            uint8_t* dstA = sA + (c0 >> 6) * 16384;
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
+          if ((tid & 255) == 0) TL(1, t, 6 - l);
+          signal_a_ready(B, t, rank);
+          if ((tid & 255) == 0) TL(2, t, 6 - l);
         }
       } else {
-        epi_bar();   // s_part visible to the other column half
+        epi_bar(t);   // `part` visible to the other column half
       }
       // ---------------- Jacobian rows + neighbour interpolation
+      float norm = w;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int tile = 4 * st + 2 * t + (int)rank;
-        const int sl = slot[t];
-        float norm = wgt[t];
+      for (int o = 1; o < 8; o <<= 1) norm += __shfl_xor_sync(SPF_FULL, norm, o);
+      const float wn = sl >= 0 ? w / norm : 0.0f;
+      if (WITH_J) {
+        wait_acc(B, t, acc_par);
+        if ((tid & 255) == 0) TL(0, t, 7);
+        if (half == 0) {
+          float v[32];
+          tmem_ld32(t_row, v);        // d sdf_k / d latent (32 columns)
+          tmem_ld_wait();
+          if (jw && tile < ntiles) {
+            float4* dst = reinterpret_cast<float4*>(jw + ((size_t)tile * 128 + row) * 32);
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) norm += __shfl_xor_sync(SPF_FULL, norm, o);
-        const float wn = sl >= 0 ? wgt[t] / norm : 0.0f;
-        if (WITH_J) {
-          wait_acc(B, t, acc_par);
-          if (half == 0) {
-            float v[32];
-            tmem_ld32(t_lane + t * 256, v);        // d sdf_k / d latent (32 columns)
-            tmem_ld_wait();
-            if (jw && tile < ntiles) {
-              float4* dst = reinterpret_cast<float4*>(jw + ((size_t)tile * 128 + row) * 32);
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(wn * v[4 * q], wn * v[4 * q + 1], wn * v[4 * q + 2], wn * v[4 * q + 3]);
+          }
+          float g[16];
+          tmem_ld16(t_row + 32, g);   // columns 32..34 = d sdf_k / d (x - p)
+          tmem_ld_wait();
+          if (grad) {
+            float g0 = wn * g[0], g1 = wn * g[1], g2 = wn * g[2];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) dst[q] = make_float4(wn * v[4 * q], wn * v[4 * q + 1], wn * v[4 * q + 2], wn * v[4 * q + 3]);
+            for (int o = 1; o < 8; o <<= 1) {
+              g0 += __shfl_xor_sync(SPF_FULL, g0, o); g1 += __shfl_xor_sync(SPF_FULL, g1, o); g2 += __shfl_xor_sync(SPF_FULL, g2, o);
             }
-            tmem_ld32(t_lane + t * 256 + 32, v);   // columns 32..34 = d sdf_k / d (x - p)
-            tmem_ld_wait();
-            if (grad) {
-              float g0 = wn * v[0], g1 = wn * v[1], g2 = wn * v[2];
-#pragma unroll
-              for (int o = 1; o < 8; o <<= 1) {
-                g0 += __shfl_xor_sync(SPF_FULL, g0, o); g1 += __shfl_xor_sync(SPF_FULL, g1, o); g2 += __shfl_xor_sync(SPF_FULL, g2, o);
-              }
-              if (sl >= 0 && (row & 7) == 0) { grad[3 * (size_t)sl] = g0; grad[3 * (size_t)sl + 1] = g1; grad[3 * (size_t)sl + 2] = g2; }
-            }
+            if (sl >= 0 && (row & 7) == 0) { grad[3 * (size_t)sl] = g0; grad[3 * (size_t)sl + 1] = g1; grad[3 * (size_t)sl + 2] = g2; }
           }
         }
-        if (half == 0) {
-          float agg = wn * (s_part[t * 256 + row] + s_part[t * 256 + 128 + row] + W.c5);
+      }
+      if (half == 0) {
+        float agg = wn * (part[row] + part[128 + row] + W.c5);
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) agg += __shfl_xor_sync(SPF_FULL, agg, o);
-          if (sl >= 0 && (row & 7) == 0) sdf[sl] = agg;
-        }
+        for (int o = 1; o < 8; o <<= 1) agg += __shfl_xor_sync(SPF_FULL, agg, o);
+        if (sl >= 0 && (row & 7) == 0) sdf[sl] = agg;
       }
       tc_fence_before();
-      epi_bar();   // s_part reads done before the next iteration overwrites it; TMEM reads ordered before the next gather's arrive
+      epi_bar(t);   // `part` reads and TMEM reads done before the next iteration reuses them
     }
   }
   teardown(tmem);
@@ -265,3 +297,17 @@ extern "C" int spf_sdf_fwd_tc(const spf_geo_weights_tc* W, const int32_t* list, 
   SPF_CHECK_LAUNCH("k_sdf_tc2");
   return SPF_OK;
 }
+
+#ifdef SPF_TIMELINE
+extern "C" int spf_debug_timeline(unsigned long long* host_out, int max_events) {
+  unsigned n = 0;
+  cudaMemcpyFromSymbol(&n, eng::g_tl_n, sizeof(n));
+  if ((int)n > max_events) n = max_events;
+  if (n > 8192) n = 8192;
+  cudaMemcpyFromSymbol(host_out, eng::g_tl, sizeof(unsigned long long) * 4 * n);
+  unsigned z = 0;
+  cudaMemcpyToSymbol(eng::g_tl_n, &z, sizeof(z));
+  return (int)n;
+}
+extern "C" void spf_debug_mode(int m) { cudaMemcpyToSymbol(eng::g_dbg_mode, &m, sizeof(m)); }
+#endif

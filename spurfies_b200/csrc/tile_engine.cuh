@@ -12,8 +12,10 @@
 //   * weights flow through a ring of 16 KB slots (one k-block of this CTA's half) filled by a producer thread with bulk
 //     copies (TMA engine) on mbarriers and released by tcgen05.commit, so the next layer's weights arrive while the
 //     current layer is still being multiplied;
-//   * roles: warps 0-7 epilogue (TMEM lane = tile row; warps 0-3 / 4-7 take the low / high 128 accumulator columns),
-//     warp 8 lane 0 = weight producer, warp 9 lane 0 = MMA issuer (leader CTA) or weight-arrival relay (peer CTA).
+//   * roles: warps 0-7 = epilogue of tile X, warps 8-15 = epilogue of tile Y (TMEM lane = tile row; within a group
+//     warps 0-3 / 4-7 take the low / high 128 accumulator columns), so the two tiles' epilogues hide each other's
+//     latencies; warp 16 lane 0 = weight producer, warp 17 lane 0 = MMA issuer (leader CTA) or weight-arrival relay
+//     (peer CTA).
 //
 // Synchronisation (all mbarriers live at the same shared-memory offsets in both CTAs):
 //   w_full[s]   (1 + tx)  TMA landed this CTA's half of the chunk in slot s
@@ -28,16 +30,37 @@
 namespace eng {
 using namespace tc;
 
-constexpr int EPI_THREADS = 256;
-constexpr int THREADS = 320;
-constexpr int NSLOT = 6;
+// ---- optional timeline instrumentation (development only: build with SPF_TIMELINE=1) --------------------
+#ifdef SPF_TIMELINE
+__device__ unsigned long long g_tl[4 * 8192];
+__device__ unsigned int g_tl_n;
+__device__ __forceinline__ void tl(int ev, int t, int l) {
+  if (blockIdx.x != 0 || (ev >= 10 && (threadIdx.x & 31) != 0)) return;
+  unsigned i = atomicAdd(&g_tl_n, 1u);
+  if (i < 8192) { g_tl[4 * i] = ev; g_tl[4 * i + 1] = t; g_tl[4 * i + 2] = l; g_tl[4 * i + 3] = clock64(); }
+}
+#define TL(ev, t, l) tl(ev, t, l)
+__device__ int g_dbg_mode;   // 0 normal, 1 epilogue skips TMEM loads, 2 epilogue loads but skips math + smem stores
+#define DBG_MODE g_dbg_mode
+#else
+#define TL(ev, t, l)
+#define DBG_MODE 0
+#endif
+
+constexpr int EPI_THREADS = 256;                     // per tile: 8 warps (TMEM lane quarter x column half)
+constexpr int N_EPI_WARPS = 16;                      // warps 0-7: tile X, warps 8-15: tile Y
+constexpr int WARP_PRODUCER = 16, WARP_MMA = 17;
+constexpr int THREADS = 576;
+constexpr int NSLOT = 5;
 constexpr int SLOT_BYTES = 16384;
 constexpr int A_BYTES = 65536;                       // 128 rows x 256 bf16, 4 k-blocks of 16 KB
 constexpr int OFF_A = 0;                             // A_X, A_Y
 constexpr int OFF_W = 2 * A_BYTES;
 constexpr int OFF_PART = OFF_W + NSLOT * SLOT_BYTES; // 2 tiles x 256 floats
-constexpr int OFF_BAR = OFF_PART + 2048;
-constexpr int SMEM_BYTES = OFF_BAR + 256;            // 231 680 <= 232 448
+constexpr int OFF_BIAS = OFF_PART + 2048;            // 5 x 256 floats (per-kernel use)
+constexpr int OFF_CHAIN = OFF_BIAS + 5120;           // the layer table (struct Chain)
+constexpr int OFF_BAR = OFF_CHAIN + 256;
+constexpr int SMEM_BYTES = OFF_BAR + 256;            // 220 928 <= 232 448
 constexpr int MAX_LAYERS = 8;
 
 struct Layer {
@@ -118,9 +141,12 @@ __device__ __forceinline__ void relay_loop(const Chain& ch, int n_iter, const Ba
         if (++slot == NSLOT) { slot = 0; ++use; }
       }
 }
-// ---- leader CTA: MMA issue (one thread) ---------------------------------------------------------------
+// ---- leader CTA: MMA issue.  Run by ALL 32 lanes of the MMA warp (warp-uniform control flow, every lane polls the
+// barriers); one elected lane issues.  Descriptors are a precomputed base plus a small immediate: the issue path
+// must stay far below the 128 cycles one M256 N256 K16 instruction takes to execute.
 __device__ __forceinline__ void mma_loop(const Chain& ch, int n_iter, uint8_t* smem, const Bars& b, uint32_t tmem) {
-  const uint32_t aA = smem_u32(smem + OFF_A), aW = smem_u32(smem + OFF_W);
+  const uint64_t adesc0 = smem_desc_sw128(smem_u32(smem + OFF_A));
+  const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + OFF_W));
   uint32_t slot0 = 0, use0 = 0;
   uint32_t ar_par = 0;   // bit t = parity of a_ready[t]
   for (int it = 0; it < n_iter; ++it)
@@ -134,41 +160,80 @@ __device__ __forceinline__ void mma_loop(const Chain& ch, int n_iter, uint8_t* s
         mbar_wait_cluster(b.a_ready + t, (ar_par >> t) & 1);
         ar_par ^= 1u << t;
         tc_fence_after();
+        TL(10, t, l);
         for (int kb = 0; kb < L.nkb; ++kb) {
           if (t == 0) {
             mbar_wait(b.w_full + slot, use & 1);
             mbar_wait_cluster(b.w_peer + slot, use & 1);
             tc_fence_after();
           }
-          const int ks_n = min(4, L.ksteps - 4 * kb);
-          for (int ks = 0; ks < ks_n; ++ks)
-            mma_bf16_2cta(tmem + t * 256, smem_desc_sw128(aA + t * A_BYTES + kb * 16384 + ks * 32),
-                          smem_desc_sw128(aW + slot * SLOT_BYTES + ks * 32), idesc, (kb | ks) != 0);
-          if (t == 1) mma_commit_2cta(b.w_empty + slot, 3);
+          const int ks_n = L.ksteps - 4 * kb;
+          const uint64_t ad = adesc0 + (uint64_t)(t * (A_BYTES >> 4) + kb * (16384 >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ks_n) mma_bf16_2cta(tmem + t * 256, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+            if (t == 1) mma_commit_2cta(b.w_empty + slot, 3);
+          }
+          __syncwarp();
           if (++slot == NSLOT) { slot = 0; ++use; }
         }
-        mma_commit_2cta(b.acc_full + t, 3);
+        if (elect_one()) mma_commit_2cta(b.acc_full + t, 3);
+        __syncwarp();
+        TL(11, t, l);
       }
       slot0 = slot; use0 = use;
     }
 }
 
-// ---- epilogue-side helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ void epi_bar() { named_bar_sync(1, EPI_THREADS); }
-// all epilogue threads: "tile t's A operand is written and its accumulator drained"
+// ---- epilogue-side helpers (t = tile / warp group 0 or 1) ------------------------------------------------
+__device__ __forceinline__ void epi_bar(int t) { named_bar_sync(1 + t, EPI_THREADS); }
+// all epilogue threads of group t: "tile t's A operand is written and its accumulator drained"
 __device__ __forceinline__ void signal_a_ready(const Bars& b, int t, uint32_t rank) {
   tc_fence_before();
   fence_proxy_async();
-  epi_bar();
-  if (threadIdx.x == 0) {
+  epi_bar(t);
+  if ((threadIdx.x & (EPI_THREADS - 1)) == 0) {
     if (rank == 0) mbar_arrive_local(b.a_ready + t);
     else mbar_arrive_remote(b.a_ready + t, 0);
   }
 }
 __device__ __forceinline__ void wait_acc(const Bars& b, int t, uint32_t& par) {
-  mbar_wait(b.acc_full + t, (par >> t) & 1);
-  par ^= 1u << t;
+  mbar_wait(b.acc_full + t, par);
+  par ^= 1u;
   tc_fence_after();
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// write 16 consecutive columns [c0, c0+16) of this thread's row as bf16 into an A tile
+__device__ __forceinline__ void store_a16(uint8_t* sA, int row, int c0, const float* v) {
+  const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    *reinterpret_cast<uint4*>(sA + kb * 16384 + sw128_off(row, ch0 + q)) = u;
+  }
+}
+__device__ __forceinline__ void store_g16(__nv_bfloat16* dst, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
 }
 
 // write 32 consecutive columns [c0, c0+32) of this thread's row as bf16 into an A tile

@@ -177,6 +177,18 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// one (compiler-visible) elected lane of a fully active warp: lets ptxas issue uniform-datapath instructions
+// (tcgen05.mma / commit) without the per-thread serialisation loop it wraps around them in divergent code
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 // named barrier among `nthreads` threads (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

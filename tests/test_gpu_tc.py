@@ -119,7 +119,7 @@ def test_geometry_field_tc_vs_fp32():
         fields.set_precision(mode)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out[mode] = geo_sdf_raw(pack, slots, q, model.neural_pts, model.neural_feats_geometry.detach(), 45.0, True, True)
+        out[mode] = tuple(o.clone() for o in geo_sdf_raw(pack, slots, q, model.neural_pts, model.neural_feats_geometry.detach(), 45.0, True, True))  # jw lives in the shared arena: clone
         torch.cuda.synchronize()
         out[mode + "_t"] = time.perf_counter() - t0
     fields.set_precision("fp32")
