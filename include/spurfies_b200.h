@@ -210,11 +210,13 @@ typedef struct {
   const uint8_t* w1ftp;                                       /* pack(F_color.0.weight[:, 39:103]^T) -> [64][256] */
   const float* b1; const float* b2; const float* b3;
 } spf_color_weights_tc;
-/* as spf_color_fwd_f32; saved tensors are bf16: in0 [rows,112] (permuted columns), h1, h2 [rows,256] */
+/* as spf_color_fwd_f32; saved tensors are bf16 in the TILE layout (see spf_wgrad_tc): in0 [rows,128] (permuted
+ * columns, 112 used), h1, h2 [rows,256]; m3 is
+ * [rows,24]: the LeakyReLU sign words of z1, z2, z3 (8 words per layer), consumed by spf_color_bwd_tc */
 int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c, float rbf,
                      float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn, void* stream);
-/* as spf_color_bwd_f32; dz1..3 are bf16 [rows,256] */
+/* as spf_color_bwd_f32; dz1..3 are bf16 [rows,256] in the TILE layout; h1 / h2 are not read (the sign words in m3 are) */
 int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                      const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
@@ -242,10 +244,12 @@ int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int
 int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
                    void* stream);
 /* weight gradient of one linear layer: dW[256][N] += dZ^T @ A, db[256] += colsum(dZ) (both accumulated in fp32), over
- * the first ceil(count * rows_per_unit / 128) * 128 rows of dZ [.,256] / A [.,lda] (bf16, row-major): exactly the rows
- * the dgrad kernels write.  N multiple of 16, <= 256.  No host synchronisation. */
+ * the first ceil(count * rows_per_unit / 128) * 128 rows of dZ [.,256] / A [.,lda] (bf16): exactly the rows the dgrad
+ * kernels write.  N multiple of 16, <= 256.  layout bit 0 / bit 1: dZ / A is stored in the tile layout written by the
+ * colour-field kernels (128-row tiles, k-blocks of 64 columns, 128-byte rows, 16-byte chunk c of row r at position
+ * c ^ (r & 7); A then has ceil(lda / 64) k-blocks per tile) instead of row-major.  No host synchronisation. */
 int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count, int32_t rows_per_unit,
-                 int64_t n_max, float* dW, float* db, void* stream);
+                 int64_t n_max, int32_t layout, float* dW, float* db, void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

@@ -1,4 +1,6 @@
-// mlp_tc.cu -- bf16 tensor-core mode of the per-pair field kernels.
+// mlp_tc.cu -- bf16 tensor-core mode, single-CTA kernels: the radiance head (per SAMPLE, 8x fewer rows than the per-pair
+// fields, which live in mlp_tc2.cu on the CTA-pair tile engine), the split-K weight-gradient kernel, weight packing and
+// the tcgen05 building-block self test.  The description below is the single-CTA tile scheme the head kernels use.
 //
 // One persistent CTA per SM walks tiles of 128 pair rows (16 slots x 8 neighbours).  Per tile the whole MLP chain
 // runs on-chip:
@@ -76,542 +78,6 @@ __device__ __forceinline__ void store_g32(__nv_bfloat16* dst, const float* v) {
     u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
     reinterpret_cast<uint4*>(dst)[q] = u;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// geometry field, bf16 tensor-core mode
-// ------------------------------------------------------------------------------------------------
-template <bool WITH_J>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_sdf_tc(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restrict__ count, const float* __restrict__ x,
-         const int* __restrict__ pidx, const float* __restrict__ pts, const float* __restrict__ feat_g, float rbf,
-         float* __restrict__ sdf, float* __restrict__ grad, float* __restrict__ jw) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + OFF_A;
-  uint8_t* sW = smem + OFF_W;
-  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  float* s_v5 = reinterpret_cast<float*>(smem + OFF_V5);
-  float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
-  int* s_slot = reinterpret_cast<int*>(smem + OFF_SLOT);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_m + 1);
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + OFF_BITS);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane;   // TMEM lane == pair row of the tile
-  const int half = warp >> 2;               // which 128 accumulator columns this thread reads
-  const int V = *count;
-  const int ntiles = (V + TC_SLOTS - 1) / TC_SLOTS;
-  if ((int)blockIdx.x >= ntiles) return;
-  constexpr int NW = WITH_J ? 8 : 4;
-  const WImg imgs[8] = {{W.w1p, 32768u}, {W.w2p, 131072u}, {W.w3p, 131072u}, {W.w4p, 131072u},
-                        {W.w4tp, 131072u}, {W.w3tp, 131072u}, {W.w2tp, 131072u}, {W.w1tp, 4u * 48u * 128u}};
-  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(s_tmem, 256);
-  for (int i = tid; i < 256; i += TC_THREADS) {
-    s_bias[i] = W.b1[i]; s_bias[256 + i] = W.b2[i]; s_bias[512 + i] = W.b3[i]; s_bias[768 + i] = W.b4[i];
-    s_v5[i] = W.v5[i];
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  uint32_t wpar = 0, mpar = 0;
-  if (tid == 0) load_weights(sW, imgs[0], bar_w);
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  int tile_i = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
-    if (tid < TC_SLOTS) s_slot[tid] = (tile * TC_SLOTS + tid < V) ? list[tile * TC_SLOTS + tid] : -1;
-    __syncthreads();
-    // ---------------- gather: A0 = [g (32) | x_pi hi (3) | x_pi lo (3) | 0 ...] as bf16, K = 48
-    const int slot = s_slot[row >> 3];
-    const int p = slot >= 0 ? pidx[(size_t)slot * 8 + (row & 7)] : -1;
-    float xp[3] = {0.f, 0.f, 0.f}, w = 0.f;
-    if (p >= 0) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) xp[a] = x[3 * (size_t)slot + a] - pts[3 * (size_t)p + a];
-      w = rbf_w(xp[0], xp[1], xp[2], rbf);
-    }
-    if (half == 0) {
-      const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
-        uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-        *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
-      }
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32 + 24);
-      float4 a = p >= 0 ? src[0] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[1] : make_float4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 3)) =
-          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-      float hi[3], lo[3];
-#pragma unroll
-      for (int a3 = 0; a3 < 3; ++a3) {
-        hi[a3] = __bfloat162float(__float2bfloat16_rn(xp[a3]));
-        lo[a3] = xp[a3] - hi[a3];
-      }
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 4)) =
-          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), 0u);
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 5)) = make_uint4(0, 0, 0, 0);
-    }
-    float dot = 0.0f;
-    // ---------------- forward chain
-#pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, l == 0 ? 3 : 16, 256, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0) {
-        const bool last = (l == NW - 1) && (tile_i == my_tiles - 1);
-        if (!last) load_weights(sW, imgs[(l + 1) % NW], bar_w);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c0 = half * 128 + q * 32;
-        float v[32];
-        tmem_ld32(t_lane + c0, v);
-        tmem_ld_wait();
-        uint32_t b = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = v[j] + s_bias[l * 256 + c0 + j];
-          b |= (t > 0.0f ? 1u : 0u) << j;
-          t = t > 0.0f ? t : LEAKY * t;
-          if (l == 3) {
-            dot = fmaf(t, s_v5[c0 + j], dot);
-            if (WITH_J) t = s_v5[c0 + j] * (((b >> j) & 1u) ? 1.0f : LEAKY);   // g4 = v5 * lrelu'(z4)
-          }
-          v[j] = t;
-        }
-        if (WITH_J) s_bits[(l * 4 + q) * TC_THREADS + tid] = b;
-        if (l < 3 || WITH_J) store_a32(sA, row, c0, v);
-      }
-    }
-    s_part[half * 128 + row] = dot;
-    // RBF normalisation over the slot's 8 neighbours (8 consecutive lanes)
-    float norm = w;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) norm += __shfl_xor_sync(SPF_FULL, norm, o);
-    const float wn = slot >= 0 ? w / norm : 0.0f;
-    if (WITH_J) {
-      // ---------------- d sdf / d input chain: g_l = (g_{l+1} @ W_{l+1}) * lrelu'(z_l), J = g1 @ W1
-#pragma unroll 1
-      for (int l = 2; l >= 0; --l) {
-        const int wi = 4 + (2 - l);  // w4tp, w3tp, w2tp
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          mbar_wait(bar_w, wpar);
-          tc_fence_after();
-          issue_layer(aA, aW, 16, 256, tmem, bar_m);
-        }
-        wpar ^= 1;
-        mbar_wait(bar_m, mpar);
-        mpar ^= 1;
-        tc_fence_after();
-        if (tid == 0) load_weights(sW, imgs[wi + 1], bar_w);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = half * 128 + q * 32;
-          float v[32];
-          tmem_ld32(t_lane + c0, v);
-          tmem_ld_wait();
-          const uint32_t b = s_bits[(l * 4 + q) * TC_THREADS + tid];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ((b >> j) & 1u) ? 1.0f : LEAKY;
-          store_a32(sA, row, c0, v);
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, 16, 48, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0 && tile_i != my_tiles - 1) load_weights(sW, imgs[0], bar_w);
-      if (half == 0) {
-        float v[32];
-        tmem_ld32(t_lane, v);      // d sdf_k / d latent (32 columns)
-        tmem_ld_wait();
-        if (jw) {
-          float4* dst = reinterpret_cast<float4*>(jw + ((size_t)tile * TC_ROWS + row) * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(wn * v[4 * q], wn * v[4 * q + 1], wn * v[4 * q + 2], wn * v[4 * q + 3]);
-        }
-        tmem_ld32(t_lane + 32, v);  // columns 32..34 = d sdf_k / d (x - p)
-        tmem_ld_wait();
-        if (grad) {
-          float g0 = wn * v[0], g1 = wn * v[1], g2 = wn * v[2];
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            g0 += __shfl_xor_sync(SPF_FULL, g0, o); g1 += __shfl_xor_sync(SPF_FULL, g1, o); g2 += __shfl_xor_sync(SPF_FULL, g2, o);
-          }
-          if (slot >= 0 && (row & 7) == 0) { grad[3 * (size_t)slot] = g0; grad[3 * (size_t)slot + 1] = g1; grad[3 * (size_t)slot + 2] = g2; }
-        }
-      }
-    } else {
-      __syncthreads();  // s_part visible
-      if (tid == 0 && tile_i != my_tiles - 1) { /* next tile's first image was already requested after layer 4 */ }
-    }
-    // ---------------- neighbour interpolation of the SDF
-    if (half == 0) {
-      float agg = wn * (s_part[row] + s_part[128 + row] + W.c5);
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) agg += __shfl_xor_sync(SPF_FULL, agg, o);
-      if (slot >= 0 && (row & 7) == 0) sdf[slot] = agg;
-    }
-    tc_fence_before();
-    __syncthreads();  // s_slot / s_part / TMEM reuse by the next tile
-  }
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-extern "C" int spf_sdf_fwd_tc_gen1(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                              const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_g,
-                              float rbf, float* sdf, float* grad, float* jw, void* stream_) {
-  if (!W || !list || !count || !x || !pidx || !pts || !feat_g || !sdf) return SPF_ERR_INVALID;
-  if (K != 8) return SPF_ERR_UNSUPPORTED;
-  if (n_max <= 0) return SPF_OK;
-  cudaStream_t st = (cudaStream_t)stream_;
-  const bool with_j = grad || jw;
-  int64_t tiles = (n_max + TC_SLOTS - 1) / TC_SLOTS;
-  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  if (with_j) {
-    SPF_CUDA(cudaFuncSetAttribute(k_sdf_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "sdf_tc attr");
-    k_sdf_tc<true><<<grid, TC_THREADS, TC_SMEM, st>>>(*W, list, count, x, pidx, pts, feat_g, rbf, sdf, grad, jw);
-  } else {
-    SPF_CUDA(cudaFuncSetAttribute(k_sdf_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "sdf_tc attr");
-    k_sdf_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(*W, list, count, x, pidx, pts, feat_g, rbf, sdf, grad, jw);
-  }
-  SPF_CHECK_LAUNCH("k_sdf_tc");
-  return SPF_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// colour field forward, bf16 tensor-core mode.  Input columns are permuted (the weight image is packed the same
-// way): [c_k (64) | PE6(x - p_k) (39) | 0 (9)], K = 112.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_color_fwd_tc(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
-               const float* __restrict__ x, const int* __restrict__ pidx, const float* __restrict__ pts,
-               const float* __restrict__ feat_c, float rbf, float* __restrict__ hbar, __nv_bfloat16* __restrict__ in0,
-               __nv_bfloat16* __restrict__ h1, __nv_bfloat16* __restrict__ h2, uint32_t* __restrict__ m3,
-               float* __restrict__ wn_out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + OFF_A;
-  uint8_t* sW = smem + OFF_W;
-  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  int* s_slot = reinterpret_cast<int*>(smem + OFF_SLOT);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_m + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  const int V = *count;
-  const int ntiles = (V + TC_SLOTS - 1) / TC_SLOTS;
-  if ((int)blockIdx.x >= ntiles) return;
-  const WImg imgs[3] = {{W.w1p, 65536u}, {W.w2p, 131072u}, {W.w3p, 131072u}};
-  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(s_tmem, 256);
-  for (int i = tid; i < 256; i += TC_THREADS) { s_bias[i] = W.b1[i]; s_bias[256 + i] = W.b2[i]; s_bias[512 + i] = W.b3[i]; }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  uint32_t wpar = 0, mpar = 0;
-  if (tid == 0) load_weights(sW, imgs[0], bar_w);
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  int tile_i = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
-    if (tid < TC_SLOTS) s_slot[tid] = (tile * TC_SLOTS + tid < V) ? list[tile * TC_SLOTS + tid] : -1;
-    __syncthreads();
-    const size_t grow = (size_t)tile * TC_ROWS + row;  // compact pair row
-    const int slot = s_slot[row >> 3];
-    const int p = slot >= 0 ? pidx[(size_t)slot * 8 + (row & 7)] : -1;
-    float xp[3] = {0.f, 0.f, 0.f}, w = 0.f;
-    if (p >= 0) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) xp[a] = x[3 * (size_t)slot + a] - pts[3 * (size_t)p + a];
-      w = rbf_w(xp[0], xp[1], xp[2], rbf);
-    }
-    float norm = w;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) norm += __shfl_xor_sync(SPF_FULL, norm, o);
-    const float wn = slot >= 0 ? w / norm : 0.0f;
-    if (half == 0) {
-      if (wn_out) wn_out[grow] = wn;
-      const float4* src = reinterpret_cast<const float4*>(feat_c + (size_t)(p >= 0 ? p : 0) * 64);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
-        uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-        *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
-        if (in0) reinterpret_cast<uint4*>(in0 + grow * 112)[q] = u;
-      }
-    } else {
-      // PE6 (embedder.py:10-36): [x, sin(2^0 x), cos(2^0 x), ..., sin(2^5 x), cos(2^5 x)] -> 39 values, padded to 48
-      float pe[48];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) pe[a] = xp[a];
-      float fr = 1.0f;
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          float sv, cv;
-          sincosf(xp[a] * fr, &sv, &cv);
-          pe[3 + 6 * l + a] = p >= 0 ? sv : 0.0f;
-          pe[6 + 6 * l + a] = p >= 0 ? cv : 0.0f;
-        }
-        fr *= 2.0f;
-      }
-#pragma unroll
-      for (int j = 39; j < 48; ++j) pe[j] = 0.0f;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        uint4 u = make_uint4(pack_bf16(pe[8 * q], pe[8 * q + 1]), pack_bf16(pe[8 * q + 2], pe[8 * q + 3]),
-                             pack_bf16(pe[8 * q + 4], pe[8 * q + 5]), pack_bf16(pe[8 * q + 6], pe[8 * q + 7]));
-        *reinterpret_cast<uint4*>(sA + 16384 + sw128_off(row, q)) = u;
-        if (in0) reinterpret_cast<uint4*>(in0 + grow * 112 + 64)[q] = u;
-      }
-    }
-#pragma unroll 1
-    for (int l = 0; l < 3; ++l) {
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, l == 0 ? 7 : 16, 256, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0 && !(l == 2 && tile_i == my_tiles - 1)) load_weights(sW, imgs[(l + 1) % 3], bar_w);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c0 = half * 128 + q * 32;
-        float v[32];
-        tmem_ld32(t_lane + c0, v);
-        tmem_ld_wait();
-        uint32_t b = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = v[j] + s_bias[l * 256 + c0 + j];
-          b |= (t > 0.0f ? 1u : 0u) << j;
-          v[j] = t > 0.0f ? t : LEAKY * t;
-        }
-        if (l < 2) {
-          store_a32(sA, row, c0, v);
-          __nv_bfloat16* dst = (l == 0 ? h1 : h2);
-          if (dst) store_g32(dst + grow * 256 + c0, v);
-        } else {
-          if (m3) m3[grow * 8 + half * 4 + q] = b;
-          // hbar[slot][c0..c0+32) = sum over the slot's 8 rows of wn * h3: transpose-reduce over 8 lanes
-          float a16[16], a8[8], a4[4];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float lo = wn * v[j], hi = wn * v[j + 16];
-            float recv = __shfl_xor_sync(SPF_FULL, (lane & 4) ? lo : hi, 4);
-            a16[j] = ((lane & 4) ? hi : lo) + recv;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float recv = __shfl_xor_sync(SPF_FULL, (lane & 2) ? a16[j] : a16[j + 8], 2);
-            a8[j] = ((lane & 2) ? a16[j + 8] : a16[j]) + recv;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float recv = __shfl_xor_sync(SPF_FULL, (lane & 1) ? a8[j] : a8[j + 4], 1);
-            a4[j] = ((lane & 1) ? a8[j + 4] : a8[j]) + recv;
-          }
-          if (slot >= 0) {
-            const int off = ((lane >> 2) & 1) * 16 + ((lane >> 1) & 1) * 8 + (lane & 1) * 4;
-            *reinterpret_cast<float4*>(hbar + (size_t)slot * 256 + c0 + off) = make_float4(a4[0], a4[1], a4[2], a4[3]);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-extern "C" int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                                const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c,
-                                float rbf, float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn,
-                                void* stream_) {
-  if (!W || !list || !count || !x || !pidx || !pts || !feat_c || !hbar) return SPF_ERR_INVALID;
-  if (K != 8) return SPF_ERR_UNSUPPORTED;
-  if (n_max <= 0) return SPF_OK;
-  int64_t tiles = (n_max + TC_SLOTS - 1) / TC_SLOTS;
-  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  SPF_CUDA(cudaFuncSetAttribute(k_color_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "color_tc attr");
-  k_color_fwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(*W, list, count, x, pidx, pts, feat_c, rbf, hbar,
-                                                                      (__nv_bfloat16*)in0, (__nv_bfloat16*)h1,
-                                                                      (__nv_bfloat16*)h2, m3, wn);
-  SPF_CHECK_LAUNCH("k_color_fwd_tc");
-  return SPF_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// colour field backward (dgrad chain), bf16 tensor-core mode.  dz rows are written (bf16) for the wgrad GEMMs.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_color_bwd_tc(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
-               const int* __restrict__ pidx, const float* __restrict__ d_hbar, const __nv_bfloat16* __restrict__ h1,
-               const __nv_bfloat16* __restrict__ h2, const uint32_t* __restrict__ m3, const float* __restrict__ wn_in,
-               __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
-               float* __restrict__ gfeat) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + OFF_A;
-  uint8_t* sW = smem + OFF_W;
-  int* s_slot = reinterpret_cast<int*>(smem + OFF_SLOT);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_m + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  const int V = *count;
-  const int ntiles = (V + TC_SLOTS - 1) / TC_SLOTS;
-  if ((int)blockIdx.x >= ntiles) return;
-  const WImg imgs[3] = {{W.w3tp, 131072u}, {W.w2tp, 131072u}, {W.w1ftp, 32768u}};
-  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(s_tmem, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  uint32_t wpar = 0, mpar = 0;
-  if (tid == 0) load_weights(sW, imgs[0], bar_w);
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  int tile_i = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
-    if (tid < TC_SLOTS) s_slot[tid] = (tile * TC_SLOTS + tid < V) ? list[tile * TC_SLOTS + tid] : -1;
-    __syncthreads();
-    const size_t grow = (size_t)tile * TC_ROWS + row;
-    const int slot = s_slot[row >> 3];
-    const float wn = slot >= 0 ? wn_in[grow] : 0.0f;
-    // dz3 = wn * d_hbar[slot] * lrelu'(z3)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c0 = half * 128 + q * 32;
-      float v[32];
-      const uint32_t b = slot >= 0 ? m3[grow * 8 + half * 4 + q] : 0u;
-      const float4* src = reinterpret_cast<const float4*>(d_hbar + (size_t)(slot >= 0 ? slot : 0) * 256 + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float4 d = slot >= 0 ? src[j4] : make_float4(0, 0, 0, 0);
-        v[4 * j4 + 0] = wn * d.x * (((b >> (4 * j4 + 0)) & 1u) ? 1.0f : LEAKY);
-        v[4 * j4 + 1] = wn * d.y * (((b >> (4 * j4 + 1)) & 1u) ? 1.0f : LEAKY);
-        v[4 * j4 + 2] = wn * d.z * (((b >> (4 * j4 + 2)) & 1u) ? 1.0f : LEAKY);
-        v[4 * j4 + 3] = wn * d.w * (((b >> (4 * j4 + 3)) & 1u) ? 1.0f : LEAKY);
-      }
-      store_a32(sA, row, c0, v);
-      store_g32(dz3 + grow * 256 + c0, v);
-    }
-#pragma unroll 1
-    for (int l = 0; l < 3; ++l) {
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, 16, l == 2 ? 64 : 256, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0 && !(l == 2 && tile_i == my_tiles - 1)) load_weights(sW, imgs[(l + 1) % 3], bar_w);
-      if (l < 2) {
-        const __nv_bfloat16* act = (l == 0 ? h2 : h1) + grow * 256;
-        __nv_bfloat16* dzo = (l == 0 ? dz2 : dz1) + grow * 256;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = half * 128 + q * 32;
-          float v[32];
-          tmem_ld32(t_lane + c0, v);
-          uint4 a[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = reinterpret_cast<const uint4*>(act + c0)[u];
-          tmem_ld_wait();
-          const uint16_t* ah = reinterpret_cast<const uint16_t*>(a);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // bf16 sign test: positive and non-zero (LeakyReLU'(z) = 1 iff z > 0 iff h > 0)
-            const uint16_t hb = ah[j];
-            const bool pos = ((hb & 0x8000u) == 0) && ((hb & 0x7fffu) != 0);
-            v[j] *= pos ? 1.0f : LEAKY;
-          }
-          store_a32(sA, row, c0, v);
-          store_g32(dzo + c0, v);
-        }
-      } else if (half == 0) {
-        // d latent = dz1 @ W1[:, latent columns]  -> scatter-add (vector atomics, 16 B each)
-        const int p = slot >= 0 ? pidx[(size_t)slot * 8 + (row & 7)] : -1;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float v[32];
-          tmem_ld32(t_lane + q * 32, v);
-          tmem_ld_wait();
-          if (p >= 0) {
-            float4* dst = reinterpret_cast<float4*>(gfeat + (size_t)p * 64 + q * 32);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) atomicAdd(dst + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                                const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
-                                const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
-                                void* stream_) {
-  if (!W || !list || !count || !pidx || !d_hbar || !h1 || !h2 || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad)
-    return SPF_ERR_INVALID;
-  if (K != 8) return SPF_ERR_UNSUPPORTED;
-  if (n_max <= 0) return SPF_OK;
-  int64_t tiles = (n_max + TC_SLOTS - 1) / TC_SLOTS;
-  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  SPF_CUDA(cudaFuncSetAttribute(k_color_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "colorb_tc attr");
-  k_color_bwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(
-      *W, list, count, pidx, d_hbar, (const __nv_bfloat16*)h1, (const __nv_bfloat16*)h2, m3, wn, (__nv_bfloat16*)dz1,
-      (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, feat_c_grad);
-  SPF_CHECK_LAUNCH("k_color_bwd_tc");
-  return SPF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -890,7 +356,7 @@ extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ act, int lda, int N,
-           const int* __restrict__ count, int rows_per_unit, float* __restrict__ dW, float* __restrict__ db) {
+           const int* __restrict__ count, int rows_per_unit, int layout, float* __restrict__ dW, float* __restrict__ db) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);  // [WG_STAGES] stage free
   uint64_t* bar_done = bar_s + WG_STAGES;
@@ -915,17 +381,27 @@ k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict
   const uint32_t idesc = idesc_bf16_mn(128, N);
   float bsum = 0.0f;
 
+  // operand addressing: row-major [rows, ld] or the tile engine's TILE layout (tile_engine.cuh: 128-row tiles, k-blocks
+  // of 64 columns, 128-byte rows, 16-byte chunk c of row r at position c ^ (r & 7)) -- there a 64-row x 64-column
+  // panel is one contiguous 8 KB run that already has the swizzle this kernel's MN-major descriptors expect
+  const int act_nkb = (lda + 63) >> 6;
+  auto src_chunk = [&](const __nv_bfloat16* base, bool tiled, long long row, int chunk, int ld, int nkb) -> const void* {
+    if (!tiled) return base + row * ld + chunk * 8;
+    const long long off = (row >> 7) * ((long long)nkb * 16384) + (long long)(chunk >> 3) * 16384 + (row & 127) * 128 +
+                          (((chunk & 7) ^ (int)(row & 7)) << 4);
+    return reinterpret_cast<const uint8_t*>(base) + off;
+  };
   auto load_tile = [&](int it) {
     const int st = it % WG_STAGES;
     const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * 64;
     const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
     for (int e = tid; e < 64 * 32; e += TC_THREADS) {
       const int k = e >> 5, mc = e & 31;
-      cp_async16(sdz + (mc >> 3) * 8192 + k * 128 + (((mc & 7) ^ (k & 7)) << 4), dz + (r0 + k) * 256 + mc * 8);
+      cp_async16(sdz + (mc >> 3) * 8192 + k * 128 + (((mc & 7) ^ (k & 7)) << 4), src_chunk(dz, layout & 1, r0 + k, mc, 256, 4));
     }
     for (int e = tid; e < 64 * nchunk_act; e += TC_THREADS) {
       const int k = e / nchunk_act, nc = e - k * nchunk_act;
-      cp_async16(sact + (nc >> 3) * 8192 + k * 128 + (((nc & 7) ^ (k & 7)) << 4), act + (r0 + k) * lda + nc * 8);
+      cp_async16(sact + (nc >> 3) * 8192 + k * 128 + (((nc & 7) ^ (k & 7)) << 4), src_chunk(act, layout & 2, r0 + k, nc, lda, act_nkb));
     }
   };
 
@@ -992,7 +468,7 @@ k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict
 }
 
 extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count,
-                            int32_t rows_per_unit, int64_t n_max, float* dW, float* db, void* stream_) {
+                            int32_t rows_per_unit, int64_t n_max, int32_t layout, float* dW, float* db, void* stream_) {
   if (!dz || !act || !count || !dW) return SPF_ERR_INVALID;
   if (N % 16 || N < 16 || N > 256 || lda < N || lda % 8 || rows_per_unit < 1) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
@@ -1000,7 +476,7 @@ extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_
   int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
   SPF_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
   k_wgrad_tc<<<grid, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)act, lda,
-                                                                  N, count, rows_per_unit, dW, db);
+                                                                  N, count, rows_per_unit, layout, dW, db);
   SPF_CHECK_LAUNCH("k_wgrad_tc");
   return SPF_OK;
 }

@@ -1,11 +1,11 @@
 // mlp_tc2.cu -- second-generation bf16 tensor-core field kernels on the CTA-pair tile engine (tile_engine.cuh):
 // tcgen05.mma.cta_group::2 (M = 256 over two CTAs), two row tiles in flight per CTA, weights through a TMA-fed ring,
 // warp-specialised producer / MMA issuer / epilogue.  Same arithmetic, same saved-tensor layouts and same C ABI as
-// mlp_tc.cu (whose kernels remain the single-CTA fallback for the radiance head and the self test).
+// the first-generation single-CTA kernels they replace (profiles/r01b_*); mlp_tc.cu keeps the radiance head, the
+// weight-gradient kernel and the self test.
 //
 // Row mapping: super-tile st (512 pair rows) -> 128-row tiles  tile = 4*st + 2*t + rank  (t = 0/1: tile X/Y of the CTA,
-// rank = CTA rank in the pair); compact pair row = tile*128 + row, exactly as in mlp_tc.cu, so every saved tensor is
-// interchangeable between the two generations.
+// rank = CTA rank in the pair); compact pair row = tile*128 + row.
 #include <stdlib.h>
 #include "tile_engine.cuh"
 
@@ -266,19 +266,9 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
   teardown(tmem);
 }
 
-static bool use_gen1() {
-  const char* e = getenv("SPF_TC_GEN1");
-  return e && e[0] == '1';
-}
-
-extern "C" int spf_sdf_fwd_tc_gen1(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                                   const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_g,
-                                   float rbf, float* sdf, float* grad, float* jw, void* stream_);
-
 extern "C" int spf_sdf_fwd_tc(const spf_geo_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                               const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_g,
                               float rbf, float* sdf, float* grad, float* jw, void* stream_) {
-  if (use_gen1()) return spf_sdf_fwd_tc_gen1(W, list, count, n_max, x, pidx, K, pts, feat_g, rbf, sdf, grad, jw, stream_);
   if (!W || !list || !count || !x || !pidx || !pts || !feat_g || !sdf) return SPF_ERR_INVALID;
   if (K != 8) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
@@ -295,6 +285,357 @@ extern "C" int spf_sdf_fwd_tc(const spf_geo_weights_tc* W, const int32_t* list, 
     k_sdf_tc2<false><<<grid, THREADS, SMEM_BYTES, st>>>(*W, list, count, x, pidx, pts, feat_g, rbf, sdf, grad, jw);
   }
   SPF_CHECK_LAUNCH("k_sdf_tc2");
+  return SPF_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// colour field forward.  Input columns are permuted (the weight image is packed the same way):
+// [c_k (64) | PE6(x - p_k) (39) | 0 (9)], K = 112.  Saved for the backward, by compact pair row: in0 [.,112], h1, h2
+// [.,256] (bf16, in the engine's TILE layout -- see signal_a_ready), wn, and the LeakyReLU sign words of z1..z3: m [., 24] (8 words per layer; word w of a layer covers
+// columns 32 w .. 32 w + 31: the "negative" bit of column 32 w + 2 i (+1) of the first 16 sits at bit 1 + 2 i (17 + 2 i),
+// of the second 16 one position lower).
+// ------------------------------------------------------------------------------------------------
+#define M_STRIDE 24
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
+                const float* __restrict__ x, const int* __restrict__ pidx, const float* __restrict__ pts,
+                const float* __restrict__ feat_c, float rbf, float* __restrict__ hbar, __nv_bfloat16* __restrict__ in0,
+                __nv_bfloat16* __restrict__ h1, __nv_bfloat16* __restrict__ h2, uint32_t* __restrict__ msign,
+                float* __restrict__ wn_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Bars B = carve_bars(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int V = *count;
+  const int ntiles = (V + 15) / 16;
+  const int nsuper = (ntiles + 3) / 4;
+  const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
+  Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b1..b3
+  if (tid == 0) {
+    ch.L[0] = {W.w1p, 2, 7, 256};
+    ch.L[1] = {W.w2p, 4, 16, 256};
+    ch.L[2] = {W.w3p, 4, 16, 256};
+    ch.n = 3;
+  }
+  for (int i = tid; i < 256; i += THREADS) { s_bias[i] = W.b1[i]; s_bias[256 + i] = W.b2[i]; s_bias[512 + i] = W.b3[i]; }
+  const uint32_t tmem = setup(smem, B);
+
+  if (warp == WARP_PRODUCER) {
+    if (lane == 0) producer_loop(ch, n_iter, rank, smem, B);
+  } else if (warp == WARP_MMA) {
+    if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);
+    else if (lane == 0) relay_loop(ch, n_iter, B);
+  } else {
+    const int t = warp >> 3;
+    const int row = 32 * (warp & 3) + lane;
+    const int half = (warp >> 2) & 1;
+    const uint32_t t_acc = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256 + half * 128;
+    uint8_t* sA = smem + OFF_A + t * A_BYTES;
+    uint32_t acc_par = 0;
+    int sl_n = -1, p_n = -1;
+    {
+      const int li = (4 * cid + 2 * t + (int)rank) * 16 + (row >> 3);
+      if (n_iter > 0 && li < V) { sl_n = list[li]; p_n = pidx[(size_t)sl_n * 8 + (row & 7)]; }
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = 4 * (cid + it * ncl) + 2 * t + (int)rank;
+      const bool tile_ok = tile < ntiles;
+      const size_t grow = (size_t)tile * 128 + row;   // compact pair row
+      const int sl = sl_n, p = p_n;
+      float xp[3] = {0.f, 0.f, 0.f}, w = 0.f;
+      if (p >= 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xp[a] = x[3 * (size_t)sl + a] - pts[3 * (size_t)p + a];
+        w = rbf_w2(xp[0], xp[1], xp[2], rbf);
+      }
+      float norm = w;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) norm += __shfl_xor_sync(SPF_FULL, norm, o);
+      const float wn = sl >= 0 ? w / norm : 0.0f;
+      if (half == 0) {
+        if (wn_out && tile_ok) wn_out[grow] = wn;
+        const float4* src = reinterpret_cast<const float4*>(feat_c + (size_t)(p >= 0 ? p : 0) * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
+          uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+          *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
+        }
+      } else {
+        // PE6 (embedder.py:10-36): [x, sin(2^0 x), cos(2^0 x), ..., sin(2^5 x), cos(2^5 x)] -> 39 values, padded to 48
+        float pe[48];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pe[a] = xp[a];
+        float fr = 1.0f;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            float sv, cv;
+            sincosf(xp[a] * fr, &sv, &cv);
+            pe[3 + 6 * l + a] = p >= 0 ? sv : 0.0f;
+            pe[6 + 6 * l + a] = p >= 0 ? cv : 0.0f;
+          }
+          fr *= 2.0f;
+        }
+#pragma unroll
+        for (int j = 39; j < 48; ++j) pe[j] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          uint4 u = make_uint4(pack_bf16(pe[8 * q], pe[8 * q + 1]), pack_bf16(pe[8 * q + 2], pe[8 * q + 3]),
+                               pack_bf16(pe[8 * q + 4], pe[8 * q + 5]), pack_bf16(pe[8 * q + 6], pe[8 * q + 7]));
+          *reinterpret_cast<uint4*>(sA + 16384 + sw128_off(row, q)) = u;
+        }
+      }
+      if ((tid & 255) == 0) TL(3, t, it);
+      signal_a_ready(B, t, rank, (in0 && tile_ok) ? in0 + (size_t)tile * (2 * 8192) : nullptr, sA, 2 * 16384);
+      if ((tid & 255) == 0) TL(4, t, it);
+      sl_n = -1; p_n = -1;
+      if (it + 1 < n_iter) {
+        const int li = (tile + 4 * ncl) * 16 + (row >> 3);
+        if (li < V) { sl_n = list[li]; p_n = pidx[(size_t)sl_n * 8 + (row & 7)]; }
+      }
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 256 + half * 128);
+        __nv_bfloat16* hdst = (l == 0 ? h1 : h2);
+        wait_acc(B, t, acc_par);
+        drain_store(t);
+        if ((tid & 255) == 0) TL(0, t, l);
+        float v[2][16];
+        uint32_t sb_prev = 0;
+        tmem_ld16(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_wait();
+          if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          float* vv = v[c & 1];
+          const int c0 = half * 128 + c * 16;
+          uint32_t pk[8];
+          uint32_t sb = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = bias4[c * 4 + q];
+            float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
+            z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
+            vv[4 * q] = z0; vv[4 * q + 1] = z1; vv[4 * q + 2] = z2; vv[4 * q + 3] = z3;
+            pk[2 * q] = pack_bf16(z0, z1);
+            pk[2 * q + 1] = pack_bf16(z2, z3);
+            sb = (sb >> 2) | (pk[2 * q] & 0x80008000u);
+            sb = (sb >> 2) | (pk[2 * q + 1] & 0x80008000u);
+          }
+          if (c & 1) {
+            if (msign && tile_ok) msign[grow * M_STRIDE + l * 8 + half * 4 + (c >> 1)] = sb_prev | (sb >> 1);
+          } else {
+            sb_prev = sb;
+          }
+          if (l < 2) {
+            uint8_t* dstA = sA + (c0 >> 6) * 16384;
+            const uint4 u0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), u1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = u0;
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = u1;
+          } else {
+            // hbar[slot][c0..c0+16) = sum over the slot's 8 rows of wn * h3: transpose-reduce over 8 lanes
+            float a8[8], a4[4], a2[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float lo = wn * vv[j], hi = wn * vv[j + 8];
+              const float recv = __shfl_xor_sync(SPF_FULL, (lane & 4) ? lo : hi, 4);
+              a8[j] = ((lane & 4) ? hi : lo) + recv;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float recv = __shfl_xor_sync(SPF_FULL, (lane & 2) ? a8[j] : a8[j + 4], 2);
+              a4[j] = ((lane & 2) ? a8[j + 4] : a8[j]) + recv;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float recv = __shfl_xor_sync(SPF_FULL, (lane & 1) ? a4[j] : a4[j + 2], 1);
+              a2[j] = ((lane & 1) ? a4[j + 2] : a4[j]) + recv;
+            }
+            if (sl >= 0) {
+              const int off = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+              *reinterpret_cast<float2*>(hbar + (size_t)sl * 256 + c0 + off) = make_float2(a2[0], a2[1]);
+            }
+          }
+        }
+        if ((tid & 255) == 0) TL(1, t, l);
+        if (l < 2) signal_a_ready(B, t, rank, (hdst && tile_ok) ? hdst + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+        if ((tid & 255) == 0) TL(2, t, l);
+      }
+      tc_fence_before();
+      epi_bar(t);
+      if ((tid & 255) == 0) TL(5, t, it);
+    }
+  }
+  teardown(tmem);
+}
+
+
+static int pair_grid(int64_t n_max) {
+  const int64_t supers = (n_max + 63) / 64;               // 64 slots = 512 pair rows per cluster iteration
+  const int max_cl = spf_num_sms() / 2;
+  return 2 * (int)(supers < max_cl ? supers : max_cl);
+}
+
+extern "C" int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                                const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c,
+                                float rbf, float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn,
+                                void* stream_) {
+  if (!W || !list || !count || !x || !pidx || !pts || !feat_c || !hbar) return SPF_ERR_INVALID;
+  if (K != 8) return SPF_ERR_UNSUPPORTED;
+  if (n_max <= 0) return SPF_OK;
+  SPF_CUDA(cudaFuncSetAttribute(k_color_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "color_tc2 attr");
+  k_color_fwd_tc2<<<pair_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
+      *W, list, count, x, pidx, pts, feat_c, rbf, hbar, (__nv_bfloat16*)in0, (__nv_bfloat16*)h1, (__nv_bfloat16*)h2, m3, wn);
+  SPF_CHECK_LAUNCH("k_color_fwd_tc2");
+  return SPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// colour field backward (dgrad chain).  dz rows are written (bf16) for the wgrad GEMMs; d latent is scatter-added.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mask_pack16(const float* vv, uint32_t sb, float scale, uint32_t* pk) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float m0 = (sb & (2u << (2 * i))) ? LEAKY * scale : scale;
+    const float m1 = (sb & (0x20000u << (2 * i))) ? LEAKY * scale : scale;
+    pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
+                const int* __restrict__ pidx, const float* __restrict__ d_hbar, const uint32_t* __restrict__ msign,
+                const float* __restrict__ wn_in, __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2,
+                __nv_bfloat16* __restrict__ dz3, float* __restrict__ gfeat) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Bars B = carve_bars(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int V = *count;
+  const int ntiles = (V + 15) / 16;
+  const int nsuper = (ntiles + 3) / 4;
+  const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
+  Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
+  if (tid == 0) {
+    ch.L[0] = {W.w3tp, 4, 16, 256};
+    ch.L[1] = {W.w2tp, 4, 16, 256};
+    ch.L[2] = {W.w1ftp, 4, 16, 64};
+    ch.n = 3;
+  }
+  const uint32_t tmem = setup(smem, B);
+
+  if (warp == WARP_PRODUCER) {
+    if (lane == 0) producer_loop(ch, n_iter, rank, smem, B);
+  } else if (warp == WARP_MMA) {
+    if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);
+    else if (lane == 0) relay_loop(ch, n_iter, B);
+  } else {
+    const int t = warp >> 3;
+    const int row = 32 * (warp & 3) + lane;
+    const int half = (warp >> 2) & 1;
+    const uint32_t t_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256;
+    const uint32_t t_acc = t_row + half * 128;
+    uint8_t* sA = smem + OFF_A + t * A_BYTES;
+    uint32_t acc_par = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = 4 * (cid + it * ncl) + 2 * t + (int)rank;
+      const size_t grow = (size_t)tile * 128 + row;
+      const int li = tile * 16 + (row >> 3);
+      const int sl = li < V ? list[li] : -1;
+      const float wn = sl >= 0 ? wn_in[grow] : 0.0f;
+      // dz3 = wn * d_hbar[slot] * lrelu'(z3)
+      {
+        uint4 mw = make_uint4(0, 0, 0, 0);
+        if (sl >= 0) mw = *reinterpret_cast<const uint4*>(msign + grow * M_STRIDE + 16 + half * 4);
+        const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
+        const float4* src = reinterpret_cast<const float4*>(d_hbar + (size_t)(sl >= 0 ? sl : 0) * 256 + half * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float vv[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 d = sl >= 0 ? src[c * 4 + q] : make_float4(0, 0, 0, 0);
+            vv[4 * q] = d.x; vv[4 * q + 1] = d.y; vv[4 * q + 2] = d.z; vv[4 * q + 3] = d.w;
+          }
+          const uint32_t sb = (c & 1) ? (mwa[c >> 1] << 1) : mwa[c >> 1];
+          uint32_t pk[8];
+          mask_pack16(vv, sb, wn, pk);
+          const int c0 = half * 128 + c * 16;
+          uint8_t* dstA = sA + (c0 >> 6) * 16384;
+          const uint4 u0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), u1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = u0;
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = u1;
+        }
+      }
+      signal_a_ready(B, t, rank, tile < ntiles ? dz3 + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) {
+        // dz2 = (dz3 @ W3) * lrelu'(z2) ; dz1 = (dz2 @ W2) * lrelu'(z1)
+        uint4 mw = make_uint4(0, 0, 0, 0);
+        if (sl >= 0) mw = *reinterpret_cast<const uint4*>(msign + grow * M_STRIDE + (1 - l) * 8 + half * 4);
+        const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
+        __nv_bfloat16* dzo = (l == 0 ? dz2 : dz1);
+        wait_acc(B, t, acc_par);
+        drain_store(t);
+        float v[2][16];
+        tmem_ld16(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_wait();
+          if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          const uint32_t sb = (c & 1) ? (mwa[c >> 1] << 1) : mwa[c >> 1];
+          uint32_t pk[8];
+          mask_pack16(v[c & 1], sb, 1.0f, pk);
+          const int c0 = half * 128 + c * 16;
+          uint8_t* dstA = sA + (c0 >> 6) * 16384;
+          const uint4 u0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), u1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = u0;
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = u1;
+        }
+        signal_a_ready(B, t, rank, tile < ntiles ? dzo + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      }
+      // d latent = dz1 @ W1[:, latent columns]  -> scatter-add (vector atomics, 16 B each)
+      wait_acc(B, t, acc_par);
+      drain_store(t);   // the next iteration's prologue overwrites the A tile
+      if (half == 0) {
+        const int p = sl >= 0 ? pidx[(size_t)sl * 8 + (row & 7)] : -1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float v[32];
+          tmem_ld32(t_row + q * 32, v);
+          tmem_ld_wait();
+          if (p >= 0) {
+            float4* dst = reinterpret_cast<float4*>(gfeat + (size_t)p * 64 + q * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) atomicAdd(dst + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      epi_bar(t);
+    }
+  }
+  teardown(tmem);
+}
+
+extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                                const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
+                                const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
+                                void* stream_) {
+  if (!W || !list || !count || !pidx || !d_hbar || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad) return SPF_ERR_INVALID;
+  if (K != 8) return SPF_ERR_UNSUPPORTED;
+  if (n_max <= 0) return SPF_OK;
+  SPF_CUDA(cudaFuncSetAttribute(k_color_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "colorb_tc2 attr");
+  k_color_bwd_tc2<<<pair_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
+      *W, list, count, pidx, d_hbar, m3, wn, (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, feat_c_grad);
+  SPF_CHECK_LAUNCH("k_color_bwd_tc2");
   return SPF_OK;
 }
 

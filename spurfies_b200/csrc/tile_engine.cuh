@@ -189,15 +189,26 @@ __device__ __forceinline__ void mma_loop(const Chain& ch, int n_iter, uint8_t* s
 
 // ---- epilogue-side helpers (t = tile / warp group 0 or 1) ------------------------------------------------
 __device__ __forceinline__ void epi_bar(int t) { named_bar_sync(1 + t, EPI_THREADS); }
-// all epilogue threads of group t: "tile t's A operand is written and its accumulator drained"
-__device__ __forceinline__ void signal_a_ready(const Bars& b, int t, uint32_t rank) {
+// all epilogue threads of group t: "tile t's A operand is written and its accumulator drained".
+// Optionally the elected thread also saves the first `bytes` of the A tile to global memory AS IS (k-block-major,
+// 128B-swizzled "tile layout": tile i of a [rows, 64 nkb] bf16 tensor lives at byte i * nkb * 16384, k-block kb at
+// + kb * 16384, row r at + r * 128, 16-byte chunk c at position c ^ (r & 7)) with one TMA bulk store -- coalesced,
+// off the epilogue threads' store path, and exactly the layout the weight-gradient kernel consumes.
+__device__ __forceinline__ void signal_a_ready(const Bars& b, int t, uint32_t rank, void* gdst = nullptr,
+                                               const uint8_t* ssrc = nullptr, uint32_t bytes = 0) {
   tc_fence_before();
   fence_proxy_async();
   epi_bar(t);
   if ((threadIdx.x & (EPI_THREADS - 1)) == 0) {
+    if (gdst) { bulk_s2g(gdst, ssrc, bytes); bulk_commit(); }
     if (rank == 0) mbar_arrive_local(b.a_ready + t);
     else mbar_arrive_remote(b.a_ready + t, 0);
   }
+}
+// before group t overwrites its A tile again: the bulk store issued by signal_a_ready must have read it
+__device__ __forceinline__ void drain_store(int t) {
+  if ((threadIdx.x & (EPI_THREADS - 1)) == 0) bulk_wait_read0();
+  epi_bar(t);
 }
 __device__ __forceinline__ void wait_acc(const Bars& b, int t, uint32_t& par) {
   mbar_wait(b.acc_full + t, par);

@@ -216,12 +216,14 @@ def _color_struct_tc(W, b):
     return s, imgs
 
 
-def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True):
-    """dW [256,N], db [256] (fp32) = spf_wgrad_tc over the rows the dgrad kernel wrote; no host sync."""
+def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True, layout=0):
+    """dW [256,N], db [256] (fp32) = spf_wgrad_tc over the rows the dgrad kernel wrote; no host sync.
+    layout bit 0 / 1: dz / act is in the colour kernels' tile layout (include/spurfies_b200.h)."""
     dev = dz.device
     dW = torch.zeros(256, N, dtype=torch.float32, device=dev)
     db = torch.zeros(256, dtype=torch.float32, device=dev) if want_db else None
-    call("spf_wgrad_tc", ptr(dz), ptr(act), int(lda), int(N), ptr(slots.count), int(rows_per_unit), slots.n, ptr(dW), ptr(db),
+    call("spf_wgrad_tc", ptr(dz), ptr(act), int(lda), int(N), ptr(slots.count), int(rows_per_unit), slots.n, int(layout), ptr(dW),
+         ptr(db),
          stream())
     return dW, db
 
@@ -255,10 +257,10 @@ class ColorField(torch.autograd.Function):
         in0 = h1 = h2 = m3 = wn = None
         if need:
             adt = torch.bfloat16 if tcm else torch.float32
-            in0 = Arena.get(tg + ".in0", (rows, 112 if tcm else 104), adt, dev)
+            in0 = Arena.get(tg + ".in0", (rows, 128 if tcm else 104), adt, dev)  # tc: tile layout, 2 k-blocks
             h1 = Arena.get(tg + ".h1", (rows, 256), adt, dev)
             h2 = Arena.get(tg + ".h2", (rows, 256), adt, dev)
-            m3 = Arena.get(tg + ".m3", (rows, 8), torch.int32, dev)
+            m3 = Arena.get(tg + ".m3", (rows, 24), torch.int32, dev)  # LeakyReLU sign words of z1..z3 (8 per layer)
             wn = Arena.get(tg + ".wn", (rows,), torch.float32, dev)
         call("spf_color_fwd_tc" if tcm else "spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
              ptr(x.contiguous()), ptr(slots.pidx), K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0),
@@ -283,9 +285,9 @@ class ColorField(torch.autograd.Function):
              ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
              ptr(dz3), ptr(gfeat), stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
-            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K)
-            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K)
-            dW1p, db1 = _wgrad_tc(dz1, in0, 112, 112, slots, slots.K)
+            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K, layout=3)
+            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K, layout=3)
+            dW1p, db1 = _wgrad_tc(dz1, in0, 128, 112, slots, slots.K, layout=3)
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
         else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
             r = slots.V * slots.K

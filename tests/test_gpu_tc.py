@@ -172,8 +172,22 @@ def test_color_field_tc_vs_fp32():
     assert errs["hbar"] < 2e-2 and all(v < 6e-2 for k, v in errs.items() if k != "d latent") and errs["d latent"] < 0.5, errs
 
 
+def _to_tile_layout(t, nkb):
+    """[rows (multiple of 128), <= 64 nkb] bf16 row-major -> the colour kernels' tile layout (include/spurfies_b200.h)."""
+    rows = t.shape[0]
+    full = torch.zeros(rows, nkb * 64, dtype=t.dtype, device=t.device)
+    full[:, :t.shape[1]] = t
+    x = full.view(rows // 128, 128, nkb, 8, 8)                       # tile, r, kb, chunk, elem
+    r = torch.arange(128, device=t.device)
+    c = torch.arange(8, device=t.device)
+    src = (c[None, :] ^ (r[:, None] & 7))                              # position c holds chunk c ^ (r & 7)
+    x = torch.gather(x, 3, src[None, :, None, :, None].expand(rows // 128, 128, nkb, 8, 8))
+    return x.permute(0, 2, 1, 3, 4).contiguous().view(-1)              # tile, kb, r, pos, elem
+
+
+@pytest.mark.parametrize("layout", [0, 3])
 @pytest.mark.parametrize("n_units,rpu,N,lda", [(1000, 8, 256, 256), (37, 8, 112, 112), (5000, 1, 256, 256), (300, 1, 16, 64)])
-def test_wgrad_tc(n_units, rpu, N, lda):
+def test_wgrad_tc(n_units, rpu, N, lda, layout):
     """split-K tcgen05 weight-gradient kernel (MN-major operands, device-side row count) vs torch."""
     from spurfies_b200 import _lib
     g = torch.Generator().manual_seed(n_units)
@@ -183,8 +197,12 @@ def test_wgrad_tc(n_units, rpu, N, lda):
     count = torch.tensor([n_units], dtype=torch.int32, device="cuda")
     dW = torch.zeros(256, N, device="cuda")
     db = torch.zeros(256, device="cuda")
-    _lib.call("spf_wgrad_tc", _lib.ptr(dz), _lib.ptr(act), lda, N, _lib.ptr(count), rpu, n_units + 50, _lib.ptr(dW), _lib.ptr(db),
-              _lib.stream())
+    dz_in, act_in, lda_in = dz, act, lda
+    if layout == 3:
+        nkb = (lda + 63) // 64
+        dz_in, act_in, lda_in = _to_tile_layout(dz[:rows + 128], 4), _to_tile_layout(act[:rows + 128], nkb), nkb * 64
+    _lib.call("spf_wgrad_tc", _lib.ptr(dz_in), _lib.ptr(act_in), lda_in, N, _lib.ptr(count), rpu, n_units + 50, layout,
+              _lib.ptr(dW), _lib.ptr(db), _lib.stream())
     torch.cuda.synchronize()
     ref = dz[:rows].float().t() @ act[:rows, :N].float()
     refb = dz[:rows].float().sum(0)
