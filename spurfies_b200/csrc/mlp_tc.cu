@@ -467,6 +467,112 @@ k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Same product for operands in the tile layout (layout == 3): a 64-row x 64-column panel is one contiguous, already
+// swizzled 8 KB run, so the stages are filled by the TMA engine (8 KB bulk copies on a "full" mbarrier) instead of 4096
+// cp.async per tile, and all 256 threads are free for the bias-gradient column sums.  Warp 0 issues the MMAs (one
+// elected lane), thread 32 refills a stage once its MMAs have retired and all 8 warps have read it ("empty" mbarrier).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, int act_nkb, int N,
+              const int* __restrict__ count, int rows_per_unit, float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + WG_STAGES;
+  uint64_t* bar_done = bar_empty + WG_STAGES;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long rows = ((long long)(*count) * rows_per_unit + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+  const int ntiles = (int)(rows / 64);
+  if ((int)blockIdx.x >= ntiles) return;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 9); }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t sbase = smem_u32(smem);
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int act_panels = (N + 63) >> 6;
+  const uint32_t idesc = idesc_bf16_mn(128, N);
+  float bsum = 0.0f;
+
+  auto load_tile = [&](int it) {   // one thread
+    const int st = it % WG_STAGES;
+    const long long j = (long long)blockIdx.x + (long long)it * gridDim.x;   // 64-row tile
+    uint8_t* sdz = smem + st * WG_STAGE_BYTES;
+    uint8_t* sact = sdz + 32768;
+    mbar_expect_tx(bar_full + st, (uint32_t)(4 + act_panels) * 8192u);
+    const uint8_t* gdz = dz + (j >> 1) * (4ll * 16384) + (j & 1) * 8192;
+    const uint8_t* gact = act + (j >> 1) * ((long long)act_nkb * 16384) + (j & 1) * 8192;
+    for (int kb = 0; kb < 4; ++kb) bulk_g2s(sdz + kb * 8192, gdz + kb * 16384, 8192, bar_full + st);
+    for (int kb = 0; kb < act_panels; ++kb) bulk_g2s(sact + kb * 8192, gact + kb * 16384, 8192, bar_full + st);
+  };
+
+  if (tid == 32)
+    for (int it = 0; it < WG_STAGES && it < my_tiles; ++it) load_tile(it);
+  for (int it = 0; it < my_tiles; ++it) {
+    const int st = it % WG_STAGES;
+    const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+    mbar_wait(bar_full + st, ph);
+    const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = smem_desc_mn_sw128(sact + ks * 2048, 8192);
+          mma_bf16(tmem, smem_desc_mn_sw128(sdz + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+          mma_bf16(tmem + 256, smem_desc_mn_sw128(sdz + 16384 + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+        }
+        mma_commit(bar_empty + st);
+      }
+      __syncwarp();
+    }
+    // bias gradient: thread = output column, column sum over this tile's 64 rows (read from the swizzled tile)
+    {
+      const uint8_t* pdz = smem + st * WG_STAGE_BYTES + (tid >> 6) * 8192;
+      const int c = (tid & 63) >> 3, e = tid & 7;
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(pdz + k * 128 + ((c ^ (k & 7)) << 4) + e * 2);
+        bsum += __bfloat162float(v);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(bar_empty + st);
+    if (tid == 32 && it + WG_STAGES < my_tiles) {
+      mbar_wait(bar_empty + st, ph);   // MMAs of tile `it` retired and every warp has read the stage
+      load_tile(it + WG_STAGES);
+    }
+  }
+  if (warp == 0) {
+    if (elect_one()) mma_commit(bar_done);
+    __syncwarp();
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  if (db) atomicAdd(db + tid, bsum);
+  {
+    const int out_row = 128 * (warp >> 2) + 32 * (warp & 3) + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 256;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(t_lane + c0, v);
+      tmem_ld_wait();
+      float* dst = dW + (size_t)out_row * N + c0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        if (c0 + 4 * j4 < N) atomicAdd(reinterpret_cast<float4*>(dst) + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count,
                             int32_t rows_per_unit, int64_t n_max, int32_t layout, float* dW, float* db, void* stream_) {
   if (!dz || !act || !count || !dW) return SPF_ERR_INVALID;
@@ -474,9 +580,15 @@ extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_
   if (n_max <= 0) return SPF_OK;
   int64_t tiles = (n_max * rows_per_unit + 63) / 64;
   int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  SPF_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
-  k_wgrad_tc<<<grid, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)act, lda,
-                                                                  N, count, rows_per_unit, layout, dW, db);
+  if (layout == 3) {
+    SPF_CUDA(cudaFuncSetAttribute(k_wgrad_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
+    k_wgrad_tiled<<<grid, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>((const uint8_t*)dz, (const uint8_t*)act, (lda + 63) >> 6, N,
+                                                                        count, rows_per_unit, dW, db);
+  } else {
+    SPF_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
+    k_wgrad_tc<<<grid, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)act, lda,
+                                                                    N, count, rows_per_unit, layout, dW, db);
+  }
   SPF_CHECK_LAUNCH("k_wgrad_tc");
   return SPF_OK;
 }
