@@ -25,7 +25,8 @@ lib = _load()
 class SpfGrid(C.Structure):
     _fields_ = [("shift", C.c_float * 3), ("vsize", C.c_float * 3), ("dim", C.c_int32 * 3), ("ks", C.c_int32 * 3),
                 ("n_points", C.c_int32), ("n_cells", C.c_int32), ("cell_start", C.c_void_p), ("sorted", C.c_void_p),
-                ("hit", C.c_void_p)]
+                ("hit", C.c_void_p), ("search_cell", C.c_float), ("search_dim", C.c_int32 * 3),
+                ("search_cell_start", C.c_void_p), ("search_sorted", C.c_void_p)]
 
 
 class GeoWeightsF32(C.Structure):
@@ -74,6 +75,7 @@ lib.spf_compact_workspace_bytes.argtypes = [C.c_int64]
 _P, _I, _L, _F, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _SIGS = {
     "spf_grid_build": [_P, _P, _P, _P, _P, _P, _P, _Z, _P],
+    "spf_grid_build_search": [_P, _P, _P, _P, _P, _Z, _P],
     "spf_mask_slots": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "spf_knn_slots": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "spf_knn_points": [_P, _P, _L, _I, _F, _P, _P],

@@ -74,6 +74,12 @@ struct GridDev {
   const int* __restrict__ cell_start;
   const float4* __restrict__ sorted;
   const uint8_t* __restrict__ hit;
+  // search grid (optional): cubic cells of edge fcell >= query radius
+  float fcell;
+  int fdx, fdy, fdz;
+  const int* __restrict__ fcell_start;
+  const float4* __restrict__ fsorted;
+  int use_search;       // set per launch: search grid present and radius <= fcell
 };
 static inline GridDev to_dev(const spf_grid* g) {
   GridDev d;
@@ -84,6 +90,11 @@ static inline GridDev to_dev(const spf_grid* g) {
   d.cell_start = g->cell_start;
   d.sorted = reinterpret_cast<const float4*>(g->sorted);
   d.hit = g->hit;
+  d.fcell = g->search_cell;
+  d.fdx = g->search_dim[0]; d.fdy = g->search_dim[1]; d.fdz = g->search_dim[2];
+  d.fcell_start = g->search_cell_start;
+  d.fsorted = reinterpret_cast<const float4*>(g->search_sorted);
+  d.use_search = 0;
   return d;
 }
 

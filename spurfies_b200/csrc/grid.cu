@@ -103,6 +103,24 @@ __global__ void k_grid_dilate(GridDev g, int G, uint8_t* __restrict__ hit) {
   hit[v] = (uint8_t)h;
 }
 
+// search-grid cell of a point: only points inside the reference grid are inserted (the reference ignores the others)
+__global__ void k_search_count(GridDev g, const float* __restrict__ pts, int n, int* __restrict__ cell_of,
+                               int* __restrict__ counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  int cx, cy, cz;
+  int c = voxel_of(g, x, y, z, cx, cy, cz);
+  if (c >= 0) {
+    int fx = (int)floorf(__fdiv_rn(__fsub_rn(x, g.sx), g.fcell));
+    int fy = (int)floorf(__fdiv_rn(__fsub_rn(y, g.sy), g.fcell));
+    int fz = (int)floorf(__fdiv_rn(__fsub_rn(z, g.sz), g.fcell));
+    c = (fx < 0 || fx >= g.fdx || fy < 0 || fy >= g.fdy || fz < 0 || fz >= g.fdz) ? -1 : fx * (g.fdy * g.fdz) + fy * g.fdz + fz;
+  }
+  cell_of[i] = c;
+  if (c >= 0) atomicAdd(&counts[c], 1);
+}
+
 extern "C" size_t spf_grid_workspace_bytes(int32_t n_points, int32_t n_cells) {
   return sizeof(int) * ((size_t)n_points + 2 * (size_t)n_cells + 64);
 }
@@ -137,6 +155,33 @@ extern "C" int spf_grid_build(const spf_grid* g, const float* points, int32_t* c
   return SPF_OK;
 }
 
+extern "C" int spf_grid_build_search(const spf_grid* g, const float* points, int32_t* search_cell_start, float* search_sorted,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!g || !points || !search_cell_start || !search_sorted || !workspace) return SPF_ERR_INVALID;
+  const int n = g->n_points;
+  const long long G = (long long)g->search_dim[0] * g->search_dim[1] * g->search_dim[2];
+  if (G <= 0 || G >= (1ll << 31) || !(g->search_cell > 0.0f)) return SPF_ERR_INVALID;
+  if (workspace_bytes < spf_grid_workspace_bytes(n, (int)G)) return SPF_ERR_WORKSPACE;
+  int* cell_of = (int*)workspace;
+  int* counts = cell_of + n;
+  int* cursor = counts + G;
+  int* stats = cursor + G;   // 64 spare ints at the end of the workspace
+  GridDev d = to_dev(g);
+  SPF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)G, st), "grid_build_search memset");
+  if (n > 0) {
+    k_search_count<<<(n + 255) / 256, 256, 0, st>>>(d, points, n, cell_of, counts);
+    SPF_CHECK_LAUNCH("k_search_count");
+  }
+  k_grid_scan<<<1, 1024, 0, st>>>(counts, (int)G, search_cell_start, cursor, stats);
+  SPF_CHECK_LAUNCH("k_grid_scan");
+  if (n > 0) {
+    k_grid_fill<<<(n + 255) / 256, 256, 0, st>>>(points, n, cell_of, cursor, reinterpret_cast<float4*>(search_sorted));
+    SPF_CHECK_LAUNCH("k_grid_fill");
+  }
+  return SPF_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // warp-cooperative kNN of one query against the cells within Chebyshev distance L of its voxel
 // (knnquery.cu:263-303).  Returns this lane's key (lanes 0..K-1 hold the sorted result).
@@ -156,23 +201,30 @@ __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v) 
 
 __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float qx, float qy, float qz, int K,
                                                        float r2, int lane) {
-  int fx = (int)floorf(__fdiv_rn(__fsub_rn(qx, g.sx), g.vx));
-  int fy = (int)floorf(__fdiv_rn(__fsub_rn(qy, g.sy), g.vy));
-  int fz = (int)floorf(__fdiv_rn(__fsub_rn(qz, g.sz), g.vz));
-  const int L = (g.kx + 1) / 2 - 1;  // the reference uses kernel_size[0] on all axes (knnquery.cu:263)
+  // candidate cells: the 27 reference voxels around the query (knnquery.cu:263-277), or -- same result, ~3.4x fewer
+  // candidates -- the 27 search cells (edge >= radius) that cover the radius ball
+  const bool fine = g.use_search != 0;
+  const float vx = fine ? g.fcell : g.vx, vy = fine ? g.fcell : g.vy, vz = fine ? g.fcell : g.vz;
+  const int dx = fine ? g.fdx : g.dx, dy = fine ? g.fdy : g.dy, dz = fine ? g.fdz : g.dz;
+  const int* __restrict__ cstart = fine ? g.fcell_start : g.cell_start;
+  const float4* __restrict__ cand = fine ? g.fsorted : g.sorted;
+  int fx = (int)floorf(__fdiv_rn(__fsub_rn(qx, g.sx), vx));
+  int fy = (int)floorf(__fdiv_rn(__fsub_rn(qy, g.sy), vy));
+  int fz = (int)floorf(__fdiv_rn(__fsub_rn(qz, g.sz), vz));
+  const int L = fine ? 1 : (g.kx + 1) / 2 - 1;  // the reference uses kernel_size[0] on all axes (knnquery.cu:263)
   unsigned long long key = KEY_NONE, thr = KEY_NONE;
-  const int z0 = max(0, fz - L), z1 = min(g.dz - 1, fz + L);
+  const int z0 = max(0, fz - L), z1 = min(dz - 1, fz + L);
   if (z0 > z1) return key;
-  for (int cx = max(0, fx - L); cx <= min(g.dx - 1, fx + L); ++cx)
-    for (int cy = max(0, fy - L); cy <= min(g.dy - 1, fy + L); ++cy) {
-      const int base = cx * (g.dy * g.dz) + cy * g.dz;
-      const int beg = g.cell_start[base + z0], end = g.cell_start[base + z1 + 1];
+  for (int cx = max(0, fx - L); cx <= min(dx - 1, fx + L); ++cx)
+    for (int cy = max(0, fy - L); cy <= min(dy - 1, fy + L); ++cy) {
+      const int base = cx * (dy * dz) + cy * dz;
+      const int beg = cstart[base + z0], end = cstart[base + z1 + 1];
       for (int j0 = beg; j0 < end; j0 += 32) {
         int j = j0 + lane;
         bool pass = false;
         unsigned long long ck = KEY_NONE;
         if (j < end) {
-          float4 c = g.sorted[j];
+          float4 c = cand[j];
           float xv = __fsub_rn(c.x, qx), yv = __fsub_rn(c.y, qy), zv = __fsub_rn(c.z, qz);
           // knnquery.cu:281 as nvcc contracts it: FMUL y*y ; FFMA x,x ; FFMA z,z
           float d2 = __fmaf_rn(zv, zv, __fmaf_rn(xv, xv, __fmul_rn(yv, yv)));
@@ -194,6 +246,17 @@ __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float q
       }
     }
   return key;
+}
+
+// the search grid may replace the reference voxels only when its 27 cells cover the radius ball AND the ball lies inside
+// the 27 reference voxels (radius <= every voxel edge): then both candidate sets contain exactly the same in-radius points
+static inline GridDev to_dev_query(const spf_grid* g, float radius2) {
+  GridDev d = to_dev(g);
+  if (g->search_sorted && g->search_cell_start && radius2 > 0.0f) {
+    const float r = sqrtf(radius2);
+    if (r * 1.0005f <= g->search_cell && r <= g->vsize[0] && r <= g->vsize[1] && r <= g->vsize[2]) d.use_search = 1;
+  }
+  return d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,7 +370,7 @@ extern "C" int spf_knn_slots(const spf_grid* g, const float* sample_loc, const i
   SPF_CUDA(cudaMemsetAsync(ray_nvalid, 0, sizeof(int) * (size_t)R, st), "knn_slots memset");
   const int wpb = 8;
   long long warps = (long long)R * Smax;
-  k_knn_slots<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(to_dev(g), sample_loc, n_slots, R, Smax, K,
+  k_knn_slots<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(to_dev_query(g, radius2), sample_loc, n_slots, R, Smax, K,
                                                                         radius2, pidx, ray_nvalid);
   SPF_CHECK_LAUNCH("k_knn_slots");
   return SPF_OK;
@@ -320,7 +383,7 @@ extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int3
   if (!g || !q || !pidx) return SPF_ERR_INVALID;
   const int wpb = 8;
   long long warps = (Q + 31) / 32;
-  k_knn_points<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream_>>>(to_dev(g), q, Q, K,
+  k_knn_points<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream_>>>(to_dev_query(g, radius2), q, Q, K,
                                                                                             radius2, pidx);
   SPF_CHECK_LAUNCH("k_knn_points");
   return SPF_OK;

@@ -17,6 +17,7 @@ Same constructor, ``set_pointset`` and ``query`` signatures and the same ragged 
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -43,6 +44,8 @@ class VoxelGrid(torch.nn.Module):
         self._key = None
         self._grid: Optional[SpfGrid] = None
         self._stats = None
+        self._search_radius = None
+        self.use_search_grid = True   # False: always scan the 27 reference voxels (same results, more candidates)
 
     # ------------------------------------------------------------------ set_pointset (knnquery.py:52-164)
     def set_pointset(self, points: torch.Tensor, actual_num_points_per_example: torch.Tensor) -> None:
@@ -95,7 +98,7 @@ class VoxelGrid(torch.nn.Module):
         g.cell_start, g.sorted, g.hit = self._cell_start.data_ptr(), self._sorted.data_ptr(), self._hit.data_ptr()
         call("spf_grid_build", C.byref(g), ptr(points), ptr(self._cell_start), ptr(self._sorted), ptr(self._hit),
              ptr(self._stats_dev), ptr(ws), ws.numel(), stream())
-        self._grid, self._key, self._stats = g, key, None
+        self._grid, self._key, self._stats, self._search_radius = g, key, None, None
         self.grid_dim = tuple(dim)
         self.d_coord_shift = self.ranges[:3]
 
@@ -112,7 +115,32 @@ class VoxelGrid(torch.nn.Module):
 
     def radius2(self, radius_limit_scale: float) -> float:
         radius_limit = radius_limit_scale * max(self.vsize_tup[0], self.vsize_tup[1])  # knnquery.py:247
+        self._ensure_search_grid(radius_limit)
         return radius_limit ** 2
+
+    def _ensure_search_grid(self, radius: float) -> None:
+        """Build (once per point set and radius) the SEARCH grid: cubic cells a hair larger than the query radius, so a
+        query scans the 27 cells covering its radius ball instead of the 27 (2.25x wider) reference voxels.  Used by the
+        kernels only when it cannot change the result (radius <= reference voxel edge, see spf_grid in the header)."""
+        g = self._grid
+        if g is None or not self.use_search_grid or radius <= 0.0 or radius > min(g.vsize) or self._search_radius == radius:
+            return
+        cell = float(radius) * 1.001
+        dims = [max(1, int(math.ceil(g.dim[a] * g.vsize[a] / cell))) for a in range(3)]
+        G = dims[0] * dims[1] * dims[2]
+        if G >= 2 ** 31:
+            return
+        dev = self.points.device
+        self._search_cell_start = torch.empty(G + 1, dtype=torch.int32, device=dev)
+        self._search_sorted = torch.empty(max(g.n_points, 1), 4, dtype=torch.float32, device=dev)
+        g.search_cell = cell
+        for a in range(3):
+            g.search_dim[a] = dims[a]
+        ws = torch.empty(_lib.lib.spf_grid_workspace_bytes(g.n_points, G), dtype=torch.uint8, device=dev)
+        call("spf_grid_build_search", C.byref(g), ptr(self.points), ptr(self._search_cell_start), ptr(self._search_sorted),
+             ptr(ws), ws.numel(), stream())
+        g.search_cell_start, g.search_sorted = self._search_cell_start.data_ptr(), self._search_sorted.data_ptr()
+        self._search_radius = radius
 
     @property
     def handle(self) -> SpfGrid:

@@ -132,6 +132,23 @@ def test_full_size_properties():
     assert st["points_in_grid"] == 1_000_000
 
 
+def test_search_grid_equals_reference_voxel_scan():
+    """The radius-sized search grid is an access-path optimisation only: identical indices (same order) as scanning the
+    27 reference voxels, for ray queries and point queries; and it switches itself off when radius > voxel edge."""
+    sc = scenes.dtu_like(60000, seed=5)
+    q = (sc["pts"][:40000] + 0.02 * torch.randn(40000, 3, generator=torch.Generator().manual_seed(1))).cuda().contiguous()
+    rays = q[:32768].view(512, 64, 3).contiguous()
+    out = {}
+    for use in (True, False):
+        vg = make_grid(sc["pts"], sc["ranges"], P=128, max_o=32768)
+        vg.use_search_grid = use
+        out[use] = (vg.query_points(q, 8, 2.0), vg.query_dense(rays, 8, 2.0, 48)[0], vg.query_points(q, 8, 4.0))
+        assert (vg.handle.search_sorted is not None and vg.handle.search_sorted != 0) == use
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+    assert int((out[True][0] >= 0).sum()) > 100000
+
+
 def _load_reference_ext():
     so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "knnquery_cuda*.so"))
     if not so:
