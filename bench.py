@@ -206,9 +206,20 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
+
+    def shutdown():
+        # Leave without interpreter / NCCL teardown: destroying a process group whose collectives live inside a captured
+        # CUDA graph can block forever at exit.  Every rank stays alive until rank 0 has printed its line.
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
     pk = peaks()
     total_rays = RAYS * world * args.steps
@@ -253,8 +264,7 @@ def run_ours(args):
     if args.cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=1)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def cpu_baseline(sample_rays=128, repeats=1, threads=None):
@@ -337,8 +347,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or int(os.environ.get("RANK", "0")) > 0:
-            args.cpu_baseline = False if int(os.environ.get("RANK", "0")) != 0 else args.cpu_baseline
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            args.cpu_baseline = False   # the CPU baseline is reported at N = 1 only
         run_ours(args)
 
 
