@@ -203,6 +203,22 @@ int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, cons
                     int32_t R, float* ray_dirs /*[R,3]*/, float* cam_loc /*[3]*/, float* depth_scale /*[R]*/,
                     void* stream);
 
+/* ---- f1: the optimiser step after the hot path (spurfies/train.py:355-363 clip_grad_norm_ + on_after_backward
+ * 
+ * :548-564 NaN/Inf guard + Adam.step (train.py:168-189) + zero_grad) over flat fp32 buffers (16-byte aligned) -------------- */
+size_t spf_optim_workspace_bytes(void);
+/* norm_sq[0] = grad_scale^2 * sum(grad^2); deterministic (fixed grid, fixed summation order) */
+int spf_grad_sumsq(const float* grad, int64_t n, float grad_scale, float* norm_sq /*[1]*/, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* One Adam step (the reference optimiser's defaults: betas as given, no amsgrad, no weight decay) on g * grad_scale * min(max_norm / (norm + 1e-6), 1)
+ * (max_norm <= 0: no clipping).  state[0] = steps taken so far (float), state[1] = learning rate of this step; state[0]
+ * is advanced on the device.  If norm_sq is not finite the update is skipped entirely (parameters, moments and step
+ * count untouched), as the reference does by dropping the gradients.  zero_grad != 0 clears grad in the same pass.
+ * info (optional) [2]: total norm, 1.0 if the step was skipped. */
+int spf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* norm_sq,
+                  float* state /*[2]*/, float grad_scale, float max_norm, double beta1, double beta2, float eps,
+                  int32_t zero_grad, float* info, void* stream);
+
 /* ---- bf16 tensor-core mode (tcgen05.mma + TMEM) ------------------------------------------------
  * Packed weight images: see spurfies_b200/packing.py (k-block major, 128B-swizzled, bf16). */
 typedef struct {

@@ -71,8 +71,10 @@ lib.spf_grid_workspace_bytes.restype = C.c_size_t
 lib.spf_grid_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
 lib.spf_compact_workspace_bytes.restype = C.c_size_t
 lib.spf_compact_workspace_bytes.argtypes = [C.c_int64]
+lib.spf_optim_workspace_bytes.restype = C.c_size_t
+lib.spf_optim_workspace_bytes.argtypes = []
 
-_P, _I, _L, _F, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+_P, _I, _L, _F, _Z, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_double
 _SIGS = {
     "spf_grid_build": [_P, _P, _P, _P, _P, _P, _P, _Z, _P],
     "spf_grid_build_search": [_P, _P, _P, _P, _P, _Z, _P],
@@ -96,6 +98,8 @@ _SIGS = {
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "spf_grad_sumsq": [_P, _L, _F, _P, _P, _Z, _P],
+    "spf_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _D, _D, _F, _I, _P, _P],
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
     "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
     "spf_wgrad_tc": [_P, _P, _I, _I, _P, _I, _L, _I, _P, _P, _P],
@@ -110,7 +114,8 @@ for _n, _a in _SIGS.items():
     _f.restype = C.c_int
     _f.argtypes = _a
 
-EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes", *_SIGS]
+EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes",
+            "spf_optim_workspace_bytes", *_SIGS]
 
 
 class SpfError(RuntimeError):

@@ -16,6 +16,7 @@ SOURCES = {
     "mlp_f32.cu": [],
     "mlp_tc.cu": [],
     "mlp_tc2.cu": [],
+    "optim.cu": [],
 }
 
 

@@ -36,15 +36,26 @@ def shard_rays(batch: dict, rank: int, world: int, ray_keys=("uv",), dim: int = 
     return out
 
 
+def flat_offsets(params: Iterable[torch.Tensor], align: int = 1) -> Tuple[List[int], int]:
+    """Element offsets of each tensor inside a flat buffer whose segments start on multiples of `align` elements
+    (align = 4: 16-byte boundaries for the fused optimiser's 128-bit accesses) and the padded total."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
 class FlatGradReducer:
     """Flatten -> one all-reduce(sum) -> scale by 1/world -> write back.  The flat buffer is persistent (its address
     is stable, so the reduction can be captured in a CUDA graph together with the rest of the step)."""
 
-    def __init__(self, params: Iterable[torch.Tensor], world_size: int, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, params: Iterable[torch.Tensor], world_size: int, group: Optional[dist.ProcessGroup] = None,
+                 align: int = 1):
         self.params: List[torch.Tensor] = list(params)
         self.world_size = int(world_size)
         self.group = group
-        self.numel = sum(p.numel() for p in self.params)
+        self.offsets, self.numel = flat_offsets(self.params, align)   # padding (if any) stays zero
         self._flat: Optional[torch.Tensor] = None
 
     @property
@@ -62,54 +73,49 @@ class FlatGradReducer:
         the all-reduce, the global-norm clip and the NaN guard are single passes over one tensor with no packing.
         The owner must clear gradients with `zero()` (not `zero_grad(set_to_none=True)`, which would drop the views)."""
         flat = self.flat()
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            p.grad = flat[off:off + k].view_as(p)
-            off += k
+        for p, off in zip(self.params, self.offsets):
+            p.grad = flat[off:off + p.numel()].view_as(p)
         return flat
 
     def attached(self) -> bool:
         if self._flat is None:
             return False
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self._flat.data_ptr() + 4 * off or not p.grad.is_contiguous():
                 return False
-            off += p.numel()
         return True
 
     def zero(self) -> None:
         self.flat().zero_()
 
-    def reduce(self) -> None:
-        """Average `p.grad` over the ranks in place (a missing grad counts as zero).  No-op for world_size 1."""
+    def reduce(self, average: bool = True) -> None:
+        """Sum `p.grad` over the ranks in place and (average=True) divide by the world size; a missing grad counts as
+        zero.  average=False leaves the sum: the fused optimiser folds 1/world into its clip coefficient.
+        No-op for world_size 1."""
         if self.world_size <= 1:
             return
         flat = self.flat()
         if self.attached():
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.mul_(1.0 / self.world_size)
+            if average:
+                flat.mul_(1.0 / self.world_size)
             return
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             k = p.numel()
             if p.grad is None:
                 flat[off:off + k].zero_()
             else:
                 flat[off:off + k].copy_(p.grad.reshape(-1))
-            off += k
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.mul_(1.0 / self.world_size)
-        off = 0
-        for p in self.params:
+        if average:
+            flat.mul_(1.0 / self.world_size)
+        for p, off in zip(self.params, self.offsets):
             k = p.numel()
             g = flat[off:off + k].view_as(p)
             if p.grad is None:
                 p.grad = g.clone()
             else:
                 p.grad.copy_(g)
-            off += k
 
 
 def max_over_ranks(values: List[float], device) -> List[float]:

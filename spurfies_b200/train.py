@@ -1,5 +1,7 @@
 """One optimisation step of the reference trainer around the hot path (spurfies/train.py:330-397): forward,
-VolSDFLoss, backward, clip_grad_norm_(1.0), NaN guard, Adam (lr 5e-4 on every trainable tensor, train.py:168-189).
+VolSDFLoss, backward, clip_grad_norm_(1.0), NaN guard, Adam (lr 5e-4 on every trainable tensor, train.py:168-189),
+cosine learning-rate schedule (train.py:191-193).  Clip + guard + Adam + zero_grad are the two kernels of
+`spurfies_b200/optim.py::FusedAdam` over flat parameter / gradient / moment buffers.
 
 Data parallel (new functionality): one process per GPU, the step's rays are sharded across
 ranks, the neural points / grid / latents / MLPs are replicated, and ONE NCCL all-reduce per step carries the
@@ -15,27 +17,35 @@ import torch.distributed as dist
 
 from .dist import FlatGradReducer
 from .model import PointVolSDF, VolSDFLoss
+from .optim import FusedAdam, cosine_lr
 
 
 class TrainStep:
     def __init__(self, model: PointVolSDF, lr: float = 5.0e-4, grad_clip: float = 1.0, loss: Optional[VolSDFLoss] = None,
-                 world_size: int = 1):
+                 world_size: int = 1, lr_schedule: bool = True):
         self.model = model
         self.loss = loss or VolSDFLoss()
         for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
             prm.requires_grad_(False)  # the local-prior SDF field is frozen (train.py:151-154)
         self.params = [p for p in model.parameters() if p.requires_grad]
-        cuda = self.params[0].is_cuda
-        self.opt = torch.optim.Adam(self.params, lr=lr, fused=cuda, capturable=cuda)
         self.grad_clip = grad_clip
         self.world_size = world_size
-        self._reducer = FlatGradReducer(self.params, world_size)
+        self.base_lr, self.lr_schedule, self.iter_step = lr, lr_schedule, 0
+        self._reducer = FlatGradReducer(self.params, world_size, align=4)
+        # every p.data / p.grad becomes a view of a flat buffer; the gradient buffer is the one NCCL reduces
+        self.opt = FusedAdam(self.params, lr=lr, max_norm=grad_clip if grad_clip else 0.0, grad_flat=self._reducer.flat())
         self._graph = None
         self._static = None
         self.graph_error = None
 
     def _allreduce_grads(self):
-        self._reducer.reduce()
+        self._reducer.reduce(average=False)   # 1/world is folded into the optimiser's clip coefficient
+
+    def _tick_lr(self):
+        """scheduler.step() (train.py:363): host-side closed form, one 4-byte H2D copy; outside the captured graph."""
+        if self.lr_schedule:
+            self.opt.set_lr(cosine_lr(self.iter_step, self.base_lr))
+        self.iter_step += 1
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def capture(self, batch, gt, rng) -> bool:
@@ -81,12 +91,14 @@ class TrainStep:
             sg[k].copy_(v, non_blocking=True)
         for k, v in rng.items():
             sr[k].copy_(v, non_blocking=True)
+        self._tick_lr()
         self._graph.replay()
         return self._static_out
 
     def __call__(self, batch, gt, rng=None) -> Dict[str, torch.Tensor]:
         if self._graph is not None:
             return self.replay(batch, gt, rng)
+        self._tick_lr()
         return self._eager(batch, gt, rng)
 
     def _eager(self, batch: Dict[str, torch.Tensor], gt: Dict[str, torch.Tensor], rng=None) -> Dict[str, torch.Tensor]:
@@ -95,17 +107,12 @@ class TrainStep:
         losses = self.loss(out, gt)
         if not self._reducer.attached():
             self._reducer.attach()
-        flat = self._reducer.flat()
-        flat.zero_()                      # every p.grad is a view of `flat`: autograd accumulates into it in place
+            self._reducer.flat().zero_()
+        # every p.grad is a view of the flat buffer: autograd accumulates into it in place.  It is all-zero here: the
+        # optimiser kernel clears it in the same pass that consumes it (zero_grad, train.py:355).
         losses["loss"].backward()
-        self._allreduce_grads()           # N > 1: one NCCL all-reduce of `flat`, no packing
-        # clip_grad_norm_(1.0) (train.py:360-361) and the NaN / Inf guard (train.py:548-564) share ONE reduction: the
-        # global norm is finite iff every gradient entry is.  When it is not, the gradients are zeroed (the reference
-        # drops them and skips the update; here Adam still decays its moments on such a step).  No host sync.
-        total = torch.linalg.vector_norm(flat, 2.0)
-        coef = torch.clamp(self.grad_clip / (total + 1e-6), max=1.0) if self.grad_clip > 0 else torch.ones_like(total)
-        coef = torch.where(torch.isfinite(total), coef, torch.zeros_like(coef))
-        flat.mul_(coef)
-        torch.nan_to_num_(flat, nan=0.0, posinf=0.0, neginf=0.0)
-        self.opt.step()
+        self._allreduce_grads()           # N > 1: one NCCL all-reduce (sum) of the flat buffer, no packing
+        # clip_grad_norm_(1.0) (train.py:360-361), the NaN / Inf guard (train.py:548-564: a non-finite global norm skips
+        # the whole update, exactly like the reference's dropped gradients), Adam and zero_grad: two kernels, no host sync.
+        self.opt.step(grad_scale=1.0 / self.world_size, zero_grad=True)
         return losses

@@ -1,0 +1,106 @@
+"""GPU: SURVEY 8(f1) -- FusedAdam (spf_grad_sumsq + spf_adam_step) against the reference's optimiser step,
+torch.nn.utils.clip_grad_norm_(1.0) -> NaN/Inf guard -> torch.optim.Adam.step (spurfies/train.py:355-363, 548-564),
+run with plain torch ops on the same seeded tensors.  fp32: 1e-6 relative after 5 steps."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1000, 64), (1000, 32), (256, 103), (256,), (3, 256), (3,), ()]  # odd sizes: segments get padded to 16 B
+
+
+def _make(seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(s, generator=g).cuda() for s in SHAPES]
+
+
+def _grads(step, scale):
+    g = torch.Generator().manual_seed(100 + step)
+    return [(torch.randn(s, generator=g) * scale).cuda() for s in SHAPES]
+
+
+def _reference_step(params, opt, grads, max_norm=1.0):
+    for p, g in zip(params, grads):
+        p.grad = g.clone()
+    torch.nn.utils.clip_grad_norm_(params, max_norm)
+    ok = all(bool(torch.isfinite(p.grad).all()) for p in params)   # on_after_backward (train.py:548-564)
+    if not ok:
+        opt.zero_grad()
+    opt.step()
+
+
+@pytest.mark.parametrize("scale", [1e-3, 10.0])   # below / above the clip threshold
+def test_fused_adam_matches_torch_adam(scale):
+    from spurfies_b200.optim import FusedAdam
+    ref_p = [torch.nn.Parameter(t.clone()) for t in _make(0)]
+    our_p = [torch.nn.Parameter(t.clone()) for t in _make(0)]
+    ref_opt = torch.optim.Adam(ref_p, lr=5e-4)
+    ours = FusedAdam(our_p, lr=5e-4, max_norm=1.0)
+    for step in range(5):
+        grads = _grads(step, scale)
+        if step == 2:
+            grads[3][7] = float("nan")   # a poisoned step must be skipped entirely
+        _reference_step(ref_p, ref_opt, grads)
+        for p, g in zip(our_p, grads):
+            p.grad.copy_(g)
+        ours.step()
+        assert bool(ours.skipped()) == (step == 2)
+        assert float(ours.flat_g.abs().sum()) == 0.0   # zero_grad fused into the step
+    for a, b in zip(our_p, ref_p):
+        err = float((a.detach() - b.detach()).abs().max() / b.detach().abs().max().clamp(min=1e-12))
+        assert err < 1e-6, err
+    assert float(ours.state[0]) == 4.0   # 5 calls, one skipped
+    # checkpoint layout of torch.optim.Adam: moments round-trip and match the reference optimiser's
+    sd = ours.state_dict()
+    rs = ref_opt.state_dict()["state"]
+    for i in range(len(SHAPES)):
+        for k in ("exp_avg", "exp_avg_sq"):
+            want = rs[i][k]
+            err = float((sd["state"][i][k] - want).abs().max() / want.abs().max().clamp(min=1e-20))
+            assert err < 1e-5, (i, k, err)
+    fresh = FusedAdam([torch.nn.Parameter(t.clone()) for t in _make(0)], lr=5e-4)
+    fresh.load_state_dict(ref_opt.state_dict())
+    assert float(fresh.state[0]) == 4.0
+    assert torch.equal(fresh.view_of(fresh.exp_avg, 0), rs[0]["exp_avg"])
+
+
+def test_grad_scale_is_the_data_parallel_average():
+    """step(grad_scale = 1/W) on summed gradients == step on averaged gradients (norm and clip included)."""
+    from spurfies_b200.optim import FusedAdam
+    a = FusedAdam([torch.nn.Parameter(t.clone()) for t in _make(1)], lr=1e-3)
+    b = FusedAdam([torch.nn.Parameter(t.clone()) for t in _make(1)], lr=1e-3)
+    grads = _grads(0, 3.0)
+    for p, g in zip(a.params, grads):
+        p.grad.copy_(g * 4.0)
+    for p, g in zip(b.params, grads):
+        p.grad.copy_(g)
+    a.step(grad_scale=0.25)
+    b.step()
+    assert abs(float(a.total_norm()) - float(b.total_norm())) < 1e-5 * float(b.total_norm())
+    for x, y in zip(a.params, b.params):
+        assert float((x.detach() - y.detach()).abs().max()) < 1e-7
+
+
+def test_train_step_uses_fused_optimizer_and_learns():
+    """TrainStep end to end (small scene): parameters are views of the flat buffer, the loss goes down."""
+    from spurfies_b200 import scenes
+    from spurfies_b200.model import PointVolSDF, default_conf
+    from spurfies_b200.train import TrainStep
+    sc = scenes.dtu_like(8000, seed=1, radii=(0.35, 0.5))
+    torch.manual_seed(0)
+    model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], precision="bf16")
+    with torch.no_grad():
+        model.neural_feats_geometry.mul_(8.0)
+    step = TrainStep(model)
+    base = step.opt.flat_p.data_ptr()
+    assert all(base <= p.data_ptr() < base + 4 * step.opt.numel for p in step.params)
+    R = 256
+    cam = scenes.camera(0, sc["cam_radius"])
+    batch = {"uv": scenes.pixel_batch(R, 3).cuda(), "pose": cam["pose"].cuda(), "intrinsics": cam["intrinsics"].cuda(),
+             "local_data": None}
+    gt = {k: v.cuda() for k, v in scenes.synthetic_gt(R, 3).items()}
+    rng = {k: v.cuda() for k, v in scenes.rng_inputs(R, 3).items()}
+    losses = [float(step(batch, gt, rng)["rgb_loss"]) for _ in range(30)]
+    assert all(l == l for l in losses)
+    assert float(step.opt.state[0]) == 30.0
+    assert sum(losses[-5:]) < sum(losses[:5])
