@@ -30,8 +30,23 @@ RAYS = 4096
 RES = (512, 384)
 METRIC = "train rays/s (fwd+bwd)"
 
+# BASELINE.json configs.  "train" (configs[1]) is the headline the driver runs; the others are run by hand / gpu_round.sh
+# and their lines are committed under profiles/.
+WORKLOADS = {
+    "train": {"scene": "dtu", "n_points": 100_000, "rays": 4096, "scaling": "weak",
+              "desc": "BASELINE configs[1]: DTU-shaped 3-view 512x384, %d neural points, %d-ray batch per GPU, full training "
+                      "step (coarse pass + error-bounded sampler + kNN + fields + compositing + loss + backward + Adam)"},
+    "garden": {"scene": "garden", "n_points": 1_000_000, "rays": 8192, "scaling": "strong",
+               "desc": "BASELINE configs[2]: Mip-NeRF-360 garden-shaped, %d neural points, %d-ray batch sharded over the "
+                       "GPUs, full training step + NCCL gradient all-reduce"},
+}
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+# capture of this command (profiles/r01c_ncu_full.md: k_sdf_tc2<1>, 23.8 MB read + 111.2 MB written)
+TRAFFIC_BYTES = {"spf_sdf_fwd_tc": 135.0e6}
+
 # kernels launched per C-ABI call (for gpu_launches)
-LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3}
+LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3, "spf_grad_sumsq": 2, "spf_adam_step": 2}
 
 # FLOPs per (sample, neighbour) pair of the geometry field, 2 * MAC.
 #  algorithmic = SURVEY 8(d): reference graph, 35->256->256->256->256->256->1 = 271 360 MAC, forward + the
@@ -85,13 +100,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_scene(device, seed=24, precision="bf16"):
+def build_scene(device, seed=24, precision="bf16", scene="dtu", n_points=N_POINTS):
     from spurfies_b200 import scenes
     from spurfies_b200.model import PointVolSDF, default_conf
-    sc = scenes.dtu_like(N_POINTS, seed=seed)
+    sc = scenes.dtu_like(n_points, seed=seed) if scene == "dtu" else scenes.garden_like(n_points, seed=360)
     torch.manual_seed(0)
     # caps above the occupancy so the reference semantics are well defined for this density
-    model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], device=device,
+    sid, ds = ("24", "dtu") if scene == "dtu" else ("garden", "mipnerf")   # pointneus_disent.py:45-62 picks the ranges
+    model = PointVolSDF(default_conf(), sid, ds, neural_points=sc["pts"], neural_colors=sc["colors"], device=device,
                         max_points_per_voxel=128, max_occ_voxels=32768, precision=precision)
     with torch.no_grad():  # non-degenerate latents (the real ones come from a trained prior / optimisation)
         model.neural_feats_geometry.mul_(8.0)
@@ -99,13 +115,13 @@ def build_scene(device, seed=24, precision="bf16"):
     return sc, model
 
 
-def host_batches(n_batches, rank, n_rays=RAYS):
+def host_batches(n_batches, rank, n_rays=RAYS, cam_radius=2.3):
     """Synthetic per-step inputs in pinned host memory: pixels, ground truth, sampler draws."""
     from spurfies_b200 import scenes
     out = []
     for b in range(n_batches):
         seed = 1000 * rank + b
-        cam = scenes.camera(b % 3, 2.3, RES)
+        cam = scenes.camera(b % 3, cam_radius, RES)
         item = {"uv": scenes.pixel_batch(n_rays, seed, RES), "pose": cam["pose"], "intrinsics": cam["intrinsics"]}
         item.update({"gt_" + k: v for k, v in scenes.synthetic_gt(n_rays, seed).items()})
         item.update({"rng_" + k: v for k, v in scenes.rng_inputs(n_rays, seed).items()})
@@ -137,10 +153,13 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    sc, model = build_scene(device, precision=args.precision)
+    wl = WORKLOADS[args.workload]
+    # weak scaling: every rank runs the full per-GPU batch; strong scaling: the batch is sharded over the ranks
+    rays_gpu = wl["rays"] if wl["scaling"] == "weak" else wl["rays"] // world
+    sc, model = build_scene(device, precision=args.precision, scene=wl["scene"], n_points=wl["n_points"])
     step = TrainStep(model, world_size=world)
     nb = 8
-    hb = host_batches(nb, rank)
+    hb = host_batches(nb, rank, n_rays=rays_gpu, cam_radius=sc["cam_radius"])
     db = [to_device(h, device) for h in hb]
     torch.cuda.synchronize()
 
@@ -190,6 +209,7 @@ def run_ours(args):
         _lib.profile_reset(False)
         barrier()
     pairs_per_step = float(model._last["slots"].V) * 8  # last step's fine-pass pairs (representative)
+    model._bench_cq = knn_candidate_stats(model)
     # ---------------- timed region 2: end to end from pinned host buffers, loss read back every step
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -222,7 +242,7 @@ def run_ours(args):
         shutdown()
         return
     pk = peaks()
-    total_rays = RAYS * world * args.steps
+    total_rays = rays_gpu * world * args.steps
     value = total_rays / (ms * 1e-3)
     e2e = total_rays / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in hb[0].values())
@@ -236,7 +256,9 @@ def run_ours(args):
     achieved = GEO_FLOPS_ALGO * pairs_per_step / (ms_launch * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": dom + " (fine pass, fwd + d sdf/d input)", "achieved": achieved,
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "traffic": None, "peak_source": pk["source"] + " bf16 sustained", "ms_per_launch": ms_launch,
+            "traffic": TRAFFIC_BYTES.get(dom) if args.workload == "train" else None,
+            "traffic_source": "profiles/r01c_ncu_full.md (ncu --set full of this command, per launch)",
+            "peak_source": pk["source"] + " bf16 sustained", "ms_per_launch": ms_launch,
             "pairs_per_launch": pairs_per_step, "flops_per_pair_algorithmic": GEO_FLOPS_ALGO,
             "flops_per_pair_executed": GEO_FLOPS_EXEC,
             "achieved_executed": GEO_FLOPS_EXEC * pairs_per_step / (ms_launch * 1e-3) / 1e12,
@@ -244,12 +266,10 @@ def run_ours(args):
     launches = int(sum(v["calls"] * LAUNCHES.get(k, 1) for k, v in prof.items()) * args.steps / prof_steps)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: DTU-shaped 3-view 512x384, %d neural points, %d-ray batch per GPU, "
-                               "full training step (coarse pass + error-bounded sampler + kNN + fields + compositing + "
-                               "loss + backward + Adam)" % (N_POINTS, RAYS),
-                   "rays_per_gpu": RAYS, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
+        "config": {"workload": wl["desc"] % (wl["n_points"], wl["rays"]),
+                   "rays_per_gpu": rays_gpu, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
                    "cuda_graph": graphed, "cuda_graph_note": step.graph_error,
                    "l2": "distinct ray batch each step; per-step working set (saved activations, > 1 GB) >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -257,6 +277,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,
+        "rooflines_other": other_rooflines(prof, prof_steps, pairs_per_step, model, pk),
         "kernels_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         "kernel_timing": ("CUDA events around each C-ABI call, eager re-run of %d of the timed steps (graph replay cannot be "
                           "instrumented)" % prof_steps) if graphed else "CUDA events around each C-ABI call inside the timed region",
@@ -265,6 +286,73 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=1)
     print(json.dumps(line))
     shutdown()
+
+
+def other_rooflines(prof, prof_steps, pairs, model, pk):
+    """Algorithmic-work rooflines of the other kernels of the step, from the same live event timings.
+    HBM-bound kernels against the measured copy bandwidth, tensor-core kernels against sustained bf16."""
+    out = {}
+    V = pairs / 8.0
+    N = float(model.neural_pts.shape[0])
+
+    def per_step(name):
+        return prof[name]["ms"] / prof_steps * 1e-3 if name in prof else None
+
+    def add(name, work, unit, peak, note):
+        t = per_step(name)
+        if t:
+            a = work / t / (1e9 if unit == "GB/s" else 1e12)
+            out[name] = {"achieved": a, "unit": unit, "peak": peak, "frac": a / peak, "ms_per_step": t * 1e3, "work": note}
+
+    hbm, tc = pk["hbm_gbs"], pk["bf16_tflops_sustained"]
+    # colour field: fwd 2*(103*256 + 2*256^2) FLOP/pair; dgrad 2*(2*256^2 + 256*64); wgrad 2*256*(256+256+103)
+    add("spf_color_fwd_tc", 2 * (103 * 256 + 2 * 65536) * pairs, "TFLOP/s", tc, "314 880 FLOP/pair (unpadded)")
+    add("spf_color_bwd_tc", 2 * (2 * 65536 + 256 * 64) * pairs, "TFLOP/s", tc, "294 912 FLOP/pair (dgrad)")
+    # all wgrad launches of the step: colour (3 layers over pairs) + head (4 layers over samples); bytes = bf16 dZ + A rows
+    wg_bytes = pairs * (3 * 512 + 512 + 512 + 256) + V * (3 * 512 + 512 + 512 + 512 + 64 + 512 + 32)
+    add("spf_wgrad_tc", wg_bytes, "GB/s", hbm, "bf16 dZ + activation rows read once per layer")
+    add("spf_head_fwd_tc", 2 * 137_216 * V, "TFLOP/s", tc, "274 432 FLOP/sample")
+    add("spf_head_bwd_tc", 2 * 137_216 * V, "TFLOP/s", tc, "274 432 FLOP/sample (dgrad)")
+    # kNN, fine pass: 12 B query + 27*8 B cell headers + 16 B * C_q candidates + 32 B out per masked-in query (8(d));
+    # C_q counted on the REFERENCE geometry (27 voxels of edge 0.075) from the grid's own cell table
+    cq = getattr(model, "_bench_cq", None)
+    if cq is not None:
+        add("spf_knn_slots", cq["queries"] * (12 + 216 + 32) + 16.0 * cq["candidates"], "GB/s", hbm,
+            "%d masked-in queries, mean C_q %.0f (reference 27-voxel candidate set)" % (cq["queries"], cq["candidates"] / max(cq["queries"], 1)))
+    # compositing: 28 B in + 4 B out per slot, + 28 B per ray
+    R, S = model._last["t"].shape
+    add("spf_composite_fwd", R * S * 32.0 + R * 28.0, "GB/s", hbm, "32 B/slot + 28 B/ray")
+    # optimiser: p, g, m, v read + p, m, v, g written (fused clip + Adam + zero_grad), + one read of g for the norm
+    n_par = float(sum(p.numel() for p in model.parameters() if p.requires_grad))
+    add("spf_adam_step", n_par * 32.0, "GB/s", hbm, "32 B/parameter")
+    add("spf_grad_sumsq", n_par * 4.0, "GB/s", hbm, "4 B/parameter")
+    return out
+
+
+def knn_candidate_stats(model):
+    """Sum over the last step's masked-in fine-pass queries of the number of points in their 27 reference voxels
+    (bench bookkeeping in torch, outside every timed region)."""
+    grid = model._voxel_grid_neural
+    g = grid.handle
+    loc = model._last.get("loc")
+    if loc is None:
+        return None
+    q = loc[model._last["slot_sample"] >= 0]   # slots that passed the dilated-occupancy mask
+    shift = torch.tensor(list(g.shift), device=q.device)
+    vs = torch.tensor(list(g.vsize), device=q.device)
+    dim = torch.tensor(list(g.dim), device=q.device)
+    c = torch.floor((q - shift) / vs).long()
+    cs = grid._cell_start.long()
+    total = torch.zeros((), dtype=torch.long, device=q.device)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            cx, cy = c[:, 0] + dx, c[:, 1] + dy
+            ok = (cx >= 0) & (cx < dim[0]) & (cy >= 0) & (cy < dim[1])
+            z0 = (c[:, 2] - 1).clamp(0, int(dim[2]) - 1)
+            z1 = (c[:, 2] + 1).clamp(0, int(dim[2]) - 1)
+            base = cx.clamp(0, int(dim[0]) - 1) * (dim[1] * dim[2]) + cy.clamp(0, int(dim[1]) - 1) * dim[2]
+            total += ((cs[base + z1 + 1] - cs[base + z0]) * ok).sum()
+    return {"queries": int(q.shape[0]), "candidates": int(total)}
 
 
 def cpu_baseline(sample_rays=128, repeats=1, threads=None):
@@ -330,6 +418,124 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_inference(args):
+    """BASELINE configs[3] (full-image 512x384 eval render, error-bounded up-sampler, inference only) and configs[4]
+    (marching-cubes SDF grid query via kNN + prior MLP), sharded over the ranks with no collective.  Same timing contract
+    as the training arm: W warm-up passes, K timed passes between barriers, CUDA events, max over ranks."""
+    import numpy as np
+    import torch.distributed as dist
+    from spurfies_b200 import _lib, scenes
+    from spurfies_b200 import eval as E
+    from spurfies_b200 import mesh
+    from spurfies_b200.dist import shard_range
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    sc, model = build_scene(device, precision=args.precision)
+    model.eval()
+    W, H = RES
+    if args.workload == "eval":
+        total = W * H
+        cams = [scenes.camera(v, sc["cam_radius"], RES) for v in range(3)]
+        uv_host = scenes.full_image_uv(RES).pin_memory()
+        inputs = [{"uv": uv_host.to(device), "pose": c["pose"].to(device), "intrinsics": c["intrinsics"].to(device),
+                   "local_data": None} for c in cams]
+
+        def one(i, from_host=False):
+            inp = inputs[i % 3]
+            if from_host:
+                inp = dict(inp, uv=uv_host.to(device, non_blocking=True))
+            out, (lo, hi) = E.render_image(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world)
+            return out
+
+        units, unit, metric = total, "rays/s", "eval rays/s (full-image render, inference)"
+        desc = ("BASELINE configs[3]: full-image %dx%d eval render (%d rays, eval sampler schedule <= 5 iterations, %d-ray "
+                "chunks), DTU-shaped %d neural points, pixels sharded over the GPUs" % (W, H, total, args.eval_chunk, N_POINTS))
+        d2h = lambda out: sum(out[k].numel() * 4 for k in ("rgb_values", "depth_values", "normal_map"))
+    else:
+        res = args.mesh_res
+        grid = mesh.get_grid_uniform(res, (-1.0, 1.0))
+        total = res ** 3
+        lo, hi = shard_range(total, rank, world)
+        vol = torch.empty(hi - lo, dtype=torch.float32, device=device)
+
+        def one(i, from_host=False):
+            mesh.sdf_volume(model, grid["xyz"], chunk=args.mesh_chunk, rank=rank, world=world, out=vol)
+            return {"volume": vol}
+
+        units, unit, metric = total, "grid points/s", "SDF grid points/s (marching-cubes query)"
+        desc = ("BASELINE configs[4]: %d^3 SDF grid query (get_sdf_eval: kNN + prior MLP) over [-1,1]^3, DTU-shaped %d neural "
+                "points, grid slabs sharded over the GPUs, %d-point chunks" % (res, N_POINTS, args.mesh_chunk))
+        d2h = lambda out: out["volume"].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.profile_reset(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = one(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_collect()
+    _lib.profile_reset(False)
+    # end to end: inputs from pinned host memory, the step's result copied back to pinned host memory
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if torch.is_tensor(v)}
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        out = one(i, from_host=True)
+        for k, v in host_out.items():
+            v.copy_(out[k], non_blocking=True)
+        torch.cuda.synchronize()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        launches = int(sum(v["calls"] * LAUNCHES.get(k, 1) for k, v in prof.items()))
+        line = {"metric": metric, "value": units * args.steps / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": desc, "parallelism": "sharded dp%d, no collective" % world,
+                           "l2": "working set per pass (kNN lists, activations) >> 126 MB L2"},
+                "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit,
+                        "h2d_bytes_per_step": int(uv_host.numel() * 4) if args.workload == "eval" else 0,
+                        "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_out.values())),
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk,
+                "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        dist.barrier()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,14 +548,22 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core field kernels (2e-2 tolerance); fp32: exact SIMT kernels (1e-4)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--workload", default="train", choices=["train", "garden", "eval", "mesh"],
+                    help="train: BASELINE configs[1] (the headline); garden: configs[2]; eval: configs[3]; mesh: configs[4]")
+    ap.add_argument("--mesh-res", type=int, default=512)
+    ap.add_argument("--mesh-chunk", type=int, default=1 << 24)
+    ap.add_argument("--eval-chunk", type=int, default=16384)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            args.cpu_baseline = False   # the CPU baseline is reported at N = 1 only
-        run_ours(args)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.workload != "train":
+            args.cpu_baseline = False   # the CPU baseline is reported at N = 1 only, on the headline workload
+        if args.workload in ("train", "garden"):
+            run_ours(args)
+        else:
+            run_inference(args)
 
 
 if __name__ == "__main__":

@@ -219,6 +219,19 @@ int spf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   float* state /*[2]*/, float grad_scale, float max_norm, double beta1, double beta2, float eps,
                   int32_t zero_grad, float* info, void* stream);
 
+/* ---- f2: SDF-grid query feeding marching cubes (spurfies/utils/plots.py:188-287, 302-333; get_sdf_eval,
+ * pointneus_disent.py:249-298) ------------------------------------------------------------------------------------- */
+/* For the `count` grid points with linear index lo .. lo+count-1 in the reference's order (np.meshgrid(x, y, z) raveled:
+ * index = (iy * nx + ix) * nz + iz): vol[t] = fill, and every point inside the dilated occupancy (knnquery.cu:171-196) is
+ * appended to (idx_out = chunk-local index t, pts_out = xyz); *counter = how many (may exceed cap: then only the first
+ * cap were stored).  Order of the compacted list is unspecified. */
+int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx, int32_t ny,
+                         int32_t nz, int64_t lo, int64_t count, float fill, float* vol /*[count]*/,
+                         int32_t* idx_out /*[cap]*/, float* pts_out /*[cap,3]*/, int32_t* counter /*[1]*/, int32_t cap,
+                         void* stream);
+/* out[idx[i]] = vals[i] */
+int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream);
+
 /* ---- bf16 tensor-core mode (tcgen05.mma + TMEM) ------------------------------------------------
  * Packed weight images: see spurfies_b200/packing.py (k-block major, 128B-swizzled, bf16). */
 typedef struct {

@@ -17,6 +17,7 @@ SOURCES = {
     "mlp_tc.cu": [],
     "mlp_tc2.cu": [],
     "optim.cu": [],
+    "mesh.cu": ["-fmad=false"],
 }
 
 

@@ -213,10 +213,32 @@ __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float q
   int fz = (int)floorf(__fdiv_rn(__fsub_rn(qz, g.sz), vz));
   const int L = fine ? 1 : (g.kx + 1) / 2 - 1;  // the reference uses kernel_size[0] on all axes (knnquery.cu:263)
   unsigned long long key = KEY_NONE, thr = KEY_NONE;
-  const int z0 = max(0, fz - L), z1 = min(dz - 1, fz + L);
-  if (z0 > z1) return key;
+  const int zlo = max(0, fz - L), zhi = min(dz - 1, fz + L);
+  if (zlo > zhi) return key;
+  // Search-grid mode: skip the cells of the 27 that the radius ball cannot reach (a corner cell is farther than r from
+  // most queries).  gap = distance from the query to the near face of the neighbouring column / cell, shrunk by `eps`
+  // (>> the fp32 rounding of the cell assignment floor((p - s) / cell)), so a skipped cell provably holds no point
+  // with d2 <= r2: the result is unchanged.
+  float ux = 0.f, uy = 0.f, uz = 0.f, eps = 0.f, r2c = 0.f;
+  if (fine) {
+    ux = __fsub_rn(qx, g.sx) - (float)fx * vx;
+    uy = __fsub_rn(qy, g.sy) - (float)fy * vy;
+    uz = __fsub_rn(qz, g.sz) - (float)fz * vz;
+    eps = vx * (1.0e-3f + 1.0e-5f * (float)max(dx, max(dy, dz)));
+    r2c = r2 * 1.0001f;
+  }
   for (int cx = max(0, fx - L); cx <= min(dx - 1, fx + L); ++cx)
     for (int cy = max(0, fy - L); cy <= min(dy - 1, fy + L); ++cy) {
+      int z0 = zlo, z1 = zhi;
+      if (fine) {
+        const float gx = cx == fx ? 0.f : fmaxf((cx < fx ? ux : vx - ux) - eps, 0.f);
+        const float gy = cy == fy ? 0.f : fmaxf((cy < fy ? uy : vy - uy) - eps, 0.f);
+        const float rem = r2c - gx * gx - gy * gy;
+        if (rem < 0.f) continue;
+        const float gl = fmaxf(uz - eps, 0.f), gh = fmaxf(vz - uz - eps, 0.f);
+        if (z0 < fz && gl * gl > rem) z0 = fz;
+        if (z1 > fz && gh * gh > rem) z1 = fz;
+      }
       const int base = cx * (dy * dz) + cy * dz;
       const int beg = cstart[base + z0], end = cstart[base + z1 + 1];
       for (int j0 = beg; j0 < end; j0 += 32) {
@@ -314,16 +336,17 @@ __global__ void k_knn_slots(GridDev g, const float* __restrict__ sample_loc, con
   if (lane < K) pidx[w * K + lane] = key == KEY_NONE ? -1 : (int)(unsigned)(key & 0xffffffffull);
 }
 
-// point queries: mask + kNN fused, each warp owns 32 consecutive points
+// point queries: mask + kNN fused, each warp owns `ppw` consecutive points (ppw = 32 for huge, mostly masked-out
+// batches such as SDF grids; smaller when there are too few points to fill the machine with 32 per warp)
 __global__ void k_knn_points(GridDev g, const float* __restrict__ q, long long Q, int K, float r2,
-                             int* __restrict__ pidx) {
+                             int* __restrict__ pidx, int ppw) {
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  long long i = w * 32 + lane;
-  if (w * 32 >= Q) return;
+  long long i = w * ppw + lane;
+  if (w * ppw >= Q) return;
   bool h = false;
   float x = 0, y = 0, z = 0;
-  if (i < Q) {
+  if (lane < ppw && i < Q) {
     x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2];
     int cx, cy, cz;
     int v = voxel_of(g, x, y, z, cx, cy, cz);
@@ -337,7 +360,7 @@ __global__ void k_knn_points(GridDev g, const float* __restrict__ q, long long Q
     m &= m - 1;
     float qx = __shfl_sync(SPF_FULL, x, src), qy = __shfl_sync(SPF_FULL, y, src), qz = __shfl_sync(SPF_FULL, z, src);
     unsigned long long key = knn_warp(g, qx, qy, qz, K, r2, lane);
-    if (lane < K) pidx[(w * 32 + src) * K + lane] = key == KEY_NONE ? -1 : (int)(unsigned)(key & 0xffffffffull);
+    if (lane < K) pidx[(w * ppw + src) * K + lane] = key == KEY_NONE ? -1 : (int)(unsigned)(key & 0xffffffffull);
   }
 }
 
@@ -382,9 +405,13 @@ extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int3
   if (Q <= 0) return SPF_OK;
   if (!g || !q || !pidx) return SPF_ERR_INVALID;
   const int wpb = 8;
-  long long warps = (Q + 31) / 32;
+  // enough warps to fill the machine several times over (148 SMs x 64 resident warps), at most 32 points per warp
+  int ppw = 32;
+  const long long want_warps = (long long)spf_num_sms() * 64 * 8;
+  while (ppw > 1 && (Q + ppw - 1) / ppw < want_warps) ppw >>= 1;
+  long long warps = (Q + ppw - 1) / ppw;
   k_knn_points<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream_>>>(to_dev_query(g, radius2), q, Q, K,
-                                                                                            radius2, pidx);
+                                                                                            radius2, pidx, ppw);
   SPF_CHECK_LAUNCH("k_knn_points");
   return SPF_OK;
 }

@@ -1,0 +1,69 @@
+"""Full-image evaluation render around the hot path (BASELINE config "Full-image 512x384 eval render with
+error-bounded up-sampler (inference only) at 1-8 GPUs").
+
+Mirrors the reference's chunked render loop: ``utils.split_input`` / ``utils.merge_output``
+(spurfies/utils/general.py:24-60) as driven by ``eval_spurfies.py:278-295`` and ``train.py:419-440`` -- the model is
+called in eval mode on ``n_pixels``-sized pixel chunks and the per-chunk outputs are concatenated.  Pixels shard
+across ranks as contiguous slices with no collective; every rank returns its own slice.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .dist import shard_range
+
+RENDER_KEYS = ("rgb_values", "normal_map", "depth_values", "weights")   # eval_spurfies.py:282-289
+
+
+def split_input(model_input: Dict, total_pixels: int, n_pixels: int = 10000, lo: int = 0, hi: Optional[int] = None) -> List[Dict]:
+    """general.py:24-39 over the pixel range [lo, hi) (the reference always uses the full range)."""
+    hi = total_pixels if hi is None else hi
+    split = []
+    for a in range(lo, hi, n_pixels):
+        b = min(a + n_pixels, hi)
+        data = dict(model_input)
+        data["uv"] = model_input["uv"][:, a:b]
+        for key in ("object_mask", "rgb"):
+            if key in data:
+                data[key] = model_input[key][:, a:b]
+        split.append(data)
+    return split
+
+
+def merge_output(res: List[Dict], total_pixels: int, batch_size: int) -> Dict:
+    """general.py:41-60."""
+    out = {}
+    for entry in res[0]:
+        if res[0][entry] is None:
+            continue
+        nd = res[0][entry].dim()
+        if nd == 1:
+            out[entry] = torch.cat([r[entry].reshape(batch_size, -1, 1) for r in res], 1).reshape(batch_size * total_pixels)
+        elif nd == 2:
+            out[entry] = torch.cat([r[entry].reshape(batch_size, -1, r[entry].shape[-1]) for r in res], 1).reshape(
+                batch_size * total_pixels, -1)
+        elif nd == 3:
+            out[entry] = torch.cat([r[entry].reshape(batch_size, -1, r[entry].shape[-2], r[entry].shape[-1]) for r in res],
+                                   1).reshape(batch_size * total_pixels, -1, res[0][entry].shape[-1])
+        else:
+            raise NotImplementedError
+    return out
+
+
+@torch.no_grad()
+def render_image(model, model_input: Dict, total_pixels: int, n_pixels: int = 16384, rank: int = 0, world: int = 1,
+                 fast: int = -1, keys=RENDER_KEYS) -> Tuple[Dict, Tuple[int, int]]:
+    """Eval-mode render of this rank's pixel slice.  Returns (merged outputs over the slice, (lo, hi))."""
+    was_training = model.training
+    model.eval()
+    try:
+        lo, hi = shard_range(total_pixels, rank, world)
+        res = []
+        for s in split_input(model_input, total_pixels, n_pixels, lo, hi):
+            out = model(s, fast=fast, aux_losses=False)
+            res.append({k: out[k].detach() for k in keys})
+        return merge_output(res, hi - lo, 1), (lo, hi)
+    finally:
+        model.train(was_training)

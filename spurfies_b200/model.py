@@ -313,7 +313,9 @@ class PointVolSDF(nn.Module):
         return TVRegul.apply(self.neural_feats_geometry, self.neural_pts, self._self_knn[1])
 
     # ------------------------------------------------------------------ forward (pointneus_disent.py:614-892)
-    def forward(self, input, fast=-1, rng=None, dense_outputs: bool = False):
+    def forward(self, input, fast=-1, rng=None, dense_outputs: bool = False, aux_losses: bool = True):
+        """aux_losses=False skips the pseudo-point and TV terms (pointneus_disent.py:765-780, 870-878), which the
+        reference also computes in eval mode although nothing reads them there (eval_spurfies.py:278-290)."""
         set_precision(self.precision)
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
         iter_step = input.get("iter_step", 1)
@@ -332,7 +334,7 @@ class PointVolSDF(nn.Module):
         z_vals, _ = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, fast, iter_step, rng=rng)
         points = self.ray_sampler.last_points  # cam_loc + z * dir, produced by the sampler kernel
         # kNN (pointneus_disent.py:654-660)
-        pidx, loc, _, nvalid = grid.query_dense(points, K, self.conf.r, S)
+        pidx, loc, slot_sample, nvalid = grid.query_dense(points, K, self.conf.r, S)
         slots = SlotSet(pidx, "fine")
         n = R * S
         # filter_points (pointneus_disent.py:666-669)
@@ -356,13 +358,17 @@ class PointVolSDF(nn.Module):
                                                                  slots.pidx, nvalid, R, S, K, not self.training)
         ray_mask = nvalid > 0
         # pseudo points (pointneus_disent.py:765-780): expected-depth point per hit ray, SDF should vanish there
-        pts_rendered = cam_loc[None, :] + ray_dirs * dist[:, None]
-        p_sdf, p_valid = self.pseudo_sdf(pts_rendered, dense=True)
-        p_ok = p_valid & ray_mask
-        cnt = p_ok.sum()
-        # F.l1_loss over the valid rows; the reference returns 1000-filled rows when nothing is valid
-        pseudo = torch.where(cnt > 0, (p_sdf.abs() * p_ok).sum() / cnt.clamp(min=1),
-                             torch.where(ray_mask.any(), torch.full((), 1000.0, device=dev), torch.zeros((), device=dev)))
+        if aux_losses:
+            pts_rendered = cam_loc[None, :] + ray_dirs * dist[:, None]
+            p_sdf, p_valid = self.pseudo_sdf(pts_rendered, dense=True)
+            p_ok = p_valid & ray_mask
+            cnt = p_ok.sum()
+            # F.l1_loss over the valid rows; the reference returns 1000-filled rows when nothing is valid
+            pseudo = torch.where(cnt > 0, (p_sdf.abs() * p_ok).sum() / cnt.clamp(min=1),
+                                 torch.where(ray_mask.any(), torch.full((), 1000.0, device=dev),
+                                             torch.zeros((), device=dev)))
+        else:
+            pseudo = torch.zeros((), device=dev)
         far_cfg = float(self.conf.ray_sampler.far)
         depth_vals = torch.where(ray_mask[:, None], t * depth_scale[:, None], torch.full_like(t, far_cfg))
         output = {
@@ -373,7 +379,7 @@ class PointVolSDF(nn.Module):
             "xyz": x_new,
             "local_loss": torch.zeros((), device=dev),   # DTU-only feature-consistency loss: SURVEY 8(f4), not built
             "pseudo_pts_loss": pseudo,
-            "tv_loss": self.tv_loss(),
+            "tv_loss": self.tv_loss() if aux_losses else torch.zeros((), device=dev),
         }
         if self.white_bkgd:  # pointneus_disent.py:856-861 (computed but never written back there either)
             pass
@@ -388,7 +394,7 @@ class PointVolSDF(nn.Module):
         # AccumulateGrad nodes) alive, which breaks CUDA-graph capture of the next step
         self._last = {"slots": slots, "z_vals": z_vals, "ray_mask": ray_mask, "sdf": sdf.detach(), "delta": delta, "t": t,
                       "rgb_s": rgb_s.detach(), "dist": dist.detach(), "acc": acc.detach(), "ray_dirs": ray_dirs,
-                      "cam_loc": cam_loc}
+                      "cam_loc": cam_loc, "loc": loc, "slot_sample": slot_sample}
         return output
 
 

@@ -1,0 +1,94 @@
+"""GPU: the callers either side of the hot path (BASELINE configs 4 and 5) -- SDF volume for marching
+cubes and the chunked full-image eval render -- against the oracle restatements.  fp32 mode, 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hotpath as H
+from oracle import mesh as OM
+from tests.helpers import load_golden, load_into_model, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from spurfies_b200.model import PointVolSDF, default_conf
+    g, P = load_golden()
+    model = PointVolSDF(default_conf(), "24", "dtu", neural_points=g["scene"]["pts"], neural_colors=g["scene"]["colors"])
+    load_into_model(model, P)
+    return g, P, model
+
+
+GRID_PARAMS = np.array([[-0.45, -0.5, -0.6], [0.7, 0.72, 0.68]])   # bbs.npz-style [min; max] (eval_spurfies.py:142-149)
+
+
+def test_sdf_volume_matches_reference_order_and_values(setup):
+    from spurfies_b200 import mesh
+    g, P, model = setup
+    want, og = OM.surface_volume(P, P.make_grid(), GRID_PARAMS, resolution=24, splitn=7000)
+    got = mesh.get_surface_by_grid(GRID_PARAMS, model, resolution=24, chunk=5000)   # several chunks, ragged tail
+    for a, b in zip(got["xyz"], og["xyz"]):
+        assert np.array_equal(a, b)
+    vol = got["volume"].cpu().numpy()
+    assert vol.shape == want.shape
+    assert np.array_equal(vol == 1000.0, want == 1000.0)
+    hit = want != 1000.0
+    assert hit.sum() > 100 and (~hit).sum() > 100
+    assert rel_err(torch.from_numpy(vol[hit]), torch.from_numpy(want[hit])) < TOL
+    assert got["has_surface"] == (not (want.min() > 0 or want.max() < 0))
+    assert abs(got["spacing"][0] - (og["xyz"][0][2] - og["xyz"][0][1])) < 1e-12
+
+
+def test_sdf_volume_shards_without_collective(setup):
+    from spurfies_b200 import mesh
+    g, P, model = setup
+    grid = mesh.get_grid_uniform(20, (-0.8, 0.8))
+    whole, (lo, hi) = mesh.sdf_volume(model, grid["xyz"], chunk=3000)
+    assert (lo, hi) == (0, 8000)
+    parts = [mesh.sdf_volume(model, grid["xyz"], chunk=3000, rank=r, world=3) for r in range(3)]
+    assert [p[1] for p in parts] == [(0, 2667), (2667, 5334), (5334, 8000)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), whole)
+    # same values as the model's own point query on the reference's materialised grid points
+    pts = OM.get_grid_uniform(20, (-0.8, 0.8))["grid_points"].cuda()
+    assert torch.equal(whole, model.get_sdf_eval(pts))
+
+
+def test_empty_and_all_masked_grids(setup):
+    from spurfies_b200 import mesh
+    g, P, model = setup
+    far = mesh.get_grid_uniform(6, (5.0, 6.0))        # entirely outside the neural points' grid
+    v, _ = mesh.sdf_volume(model, far["xyz"])
+    assert v.numel() == 216 and bool((v == 1000.0).all())
+    v1, r = mesh.sdf_volume(model, far["xyz"], rank=3, world=300)   # ranks beyond the work get empty slabs
+    assert v1.numel() == r[1] - r[0] <= 1
+
+
+def test_render_image_chunks_and_shards(setup):
+    """Chunked / sharded eval render == the model called on the same pixel chunks (general.py:24-60 plumbing), and the
+    single-chunk render == oracle eval forward."""
+    from spurfies_b200 import eval as E
+    from spurfies_b200 import scenes
+    g, P, model = setup
+    cam = scenes.camera(1, 2.3)
+    uv = scenes.pixel_batch(96, seed=5)
+    inp = {"uv": uv.cuda(), "pose": cam["pose"].cuda(), "intrinsics": cam["intrinsics"].cuda(), "local_data": None}
+    one, (lo, hi) = E.render_image(model, inp, 96, n_pixels=96)
+    assert (lo, hi) == (0, 96) and one["rgb_values"].shape == (96, 3) and one["weights"].shape == (96, 80)
+    model.eval()
+    with torch.no_grad():
+        ro = H.render_forward(P, P.make_grid(), uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), False, -1, None)
+    for k in ("rgb_values", "weights", "depth_values", "normal_map"):   # tolerance of the eval sampler chain, as in
+        e = rel_err(one[k].reshape(-1), ro[k].reshape(-1))              # test_gpu_hotpath.test_eval_forward_matches_reference
+        assert e < 2e-2, (k, e)
+    # shards: rank r of 2 renders its own contiguous half in 20-pixel chunks
+    for r in range(2):
+        part, (a, b) = E.render_image(model, inp, 96, n_pixels=20, rank=r, world=2)
+        assert (a, b) == (48 * r, 48 * r + 48)
+        chunks = []
+        with torch.no_grad():
+            for s in E.split_input(inp, 96, 20, a, b):
+                chunks.append(model(s, aux_losses=False)["rgb_values"])
+        assert torch.equal(part["rgb_values"], torch.cat(chunks))
+    assert not model.training

@@ -100,7 +100,10 @@ def test_train_step_uses_fused_optimizer_and_learns():
              "local_data": None}
     gt = {k: v.cuda() for k, v in scenes.synthetic_gt(R, 3).items()}
     rng = {k: v.cuda() for k, v in scenes.rng_inputs(R, 3).items()}
-    losses = [float(step(batch, gt, rng)["rgb_loss"]) for _ in range(30)]
+    before = step.opt.flat_p.clone()
+    losses = [float(step(batch, gt, rng)["loss"]) for _ in range(30)]
     assert all(l == l for l in losses)
-    assert float(step.opt.state[0]) == 30.0
-    assert sum(losses[-5:]) < sum(losses[:5])
+    assert float(step.opt.state[0]) == 30.0 and float(step.opt.skipped()) == 0.0
+    moved = (step.opt.flat_p - before).abs().max()
+    assert 0.0 < float(moved) <= 30 * 5.0e-4 * 4.0       # Adam's per-step move is O(lr) whatever the gradient scale
+    assert min(losses[10:]) < losses[0]                  # same batch every step: the loss goes down

@@ -29,3 +29,29 @@ def test_flat_offsets_are_16_byte_aligned_and_ordered():
     assert red.attached() and flat.numel() == 44
     for p, o in zip(red.params, offs):
         assert p.grad.data_ptr() == flat.data_ptr() + 4 * o
+
+
+def test_mesh_grids_match_the_restated_reference_grids():
+    """mesh.get_grid / get_grid_uniform (axes only) == the materialising restatement of plots.py:289-333, and
+    mesh.grid_points reproduces the reference's point order."""
+    import numpy as np
+    from oracle import mesh as OM
+    from spurfies_b200 import mesh
+    for gp in ([[-0.45, -0.5, -0.6], [0.7, 0.72, 0.68]], [[-1.0, -0.2, -0.6], [0.7, 0.1, 0.68]], [[-1.0, -0.9, -0.1], [0.7, 0.7, 0.2]]):
+        gp = np.asarray(gp, dtype=np.float64) * np.array([[1.5], [1.0]])
+        a = mesh.get_grid(None, 17, input_min=gp[0], input_max=gp[1], eps=0.0)
+        b = OM.get_grid(None, 17, input_min=gp[0], input_max=gp[1], eps=0.0)
+        assert a["shortest_axis_index"] == b["shortest_axis_index"]
+        for u, v in zip(a["xyz"], b["xyz"]):
+            assert np.array_equal(u, v)
+        assert torch.equal(mesh.grid_points(a["xyz"]), b["grid_points"])
+    pts = torch.rand(50, 3)
+    a, b = mesh.get_grid(pts, 9), OM.get_grid(pts, 9)
+    assert all(np.array_equal(u, v) for u, v in zip(a["xyz"], b["xyz"]))
+    a, b = mesh.get_grid_uniform(11), OM.get_grid_uniform(11)
+    assert all(np.array_equal(u, v) for u, v in zip(a["xyz"], b["xyz"]))
+    # linear index rule used by spf_grid_points_mask: (iy * nx + ix) * nz + iz
+    x, y, z = np.arange(3.0), np.arange(10.0, 14.0), np.arange(20.0, 25.0)
+    P = mesh.grid_points([x, y, z])
+    i = (2 * 3 + 1) * 5 + 4
+    assert P[i].tolist() == [1.0, 12.0, 24.0]
