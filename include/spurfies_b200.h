@@ -232,6 +232,18 @@ int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, co
 /* out[idx[i]] = vals[i] */
 int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream);
 
+/* ---- f3: neural-point ingestion (spurfies/model/utils.py:6-37 construct_vox_points_closest) --------------------------- */
+size_t spf_voxelize_workspace_bytes(int32_t cells_per_axis);
+/* Voxel-downsample: voxel of a point = floor((p - space_min) / vox_size) per axis (fp32, as the reference computes it);
+ * for every occupied voxel, in sorted (x, y, z) voxel order (the order of unique(dim=0)): min_idx = index of the input
+ * point closest to the voxel centroid (ties: smallest index), centroid (optional) = mean of its points, grid_idx
+ * (optional) = the voxel's integer coordinates.  n_out[0] = number of occupied voxels (may exceed cap: then only the
+ * first cap rows were written), n_out[1] = points that fell outside the cells_per_axis^3 table (must be 0). */
+int spf_voxelize_closest(const float* points /*[n,3]*/, int32_t n, float min_x, float min_y, float min_z, float vox_size,
+                         int32_t cells_per_axis, int64_t* min_idx /*[cap]*/, float* centroid /*[cap,3] or NULL*/,
+                         int32_t* grid_idx /*[cap,3] or NULL*/, int32_t cap, int32_t* n_out /*[2]*/, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- bf16 tensor-core mode (tcgen05.mma + TMEM) ------------------------------------------------
  * Packed weight images: see spurfies_b200/packing.py (k-block major, 128B-swizzled, bf16). */
 typedef struct {

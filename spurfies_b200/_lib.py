@@ -13,6 +13,9 @@ _here = os.path.dirname(os.path.abspath(__file__))
 
 
 def _load():
+    path = os.environ.get("SPF_LIBRARY")   # development only: an instrumented build of the same sources
+    if path:
+        return C.CDLL(path)
     path = LIB
     if not os.path.exists(path):
         path = build_library()
@@ -73,6 +76,8 @@ lib.spf_compact_workspace_bytes.restype = C.c_size_t
 lib.spf_compact_workspace_bytes.argtypes = [C.c_int64]
 lib.spf_optim_workspace_bytes.restype = C.c_size_t
 lib.spf_optim_workspace_bytes.argtypes = []
+lib.spf_voxelize_workspace_bytes.restype = C.c_size_t
+lib.spf_voxelize_workspace_bytes.argtypes = [C.c_int32]
 
 _P, _I, _L, _F, _Z, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_double
 _SIGS = {
@@ -102,6 +107,7 @@ _SIGS = {
     "spf_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _D, _D, _F, _I, _P, _P],
     "spf_grid_points_mask": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _F, _P, _P, _P, _P, _I, _P],
     "spf_scatter_f32": [_P, _P, _I, _P, _P],
+    "spf_voxelize_closest": [_P, _I, _F, _F, _F, _F, _I, _P, _P, _P, _I, _P, _P, _Z, _P],
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
     "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
     "spf_wgrad_tc": [_P, _P, _I, _I, _P, _I, _L, _I, _P, _P, _P],
@@ -117,7 +123,7 @@ for _n, _a in _SIGS.items():
     _f.argtypes = _a
 
 EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes",
-            "spf_optim_workspace_bytes", *_SIGS]
+            "spf_optim_workspace_bytes", "spf_voxelize_workspace_bytes", *_SIGS]
 
 
 class SpfError(RuntimeError):

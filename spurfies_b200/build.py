@@ -18,6 +18,7 @@ SOURCES = {
     "mlp_tc2.cu": [],
     "optim.cu": [],
     "mesh.cu": ["-fmad=false"],
+    "ingest.cu": ["-fmad=false"],
 }
 
 

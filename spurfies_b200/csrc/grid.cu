@@ -213,32 +213,13 @@ __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float q
   int fz = (int)floorf(__fdiv_rn(__fsub_rn(qz, g.sz), vz));
   const int L = fine ? 1 : (g.kx + 1) / 2 - 1;  // the reference uses kernel_size[0] on all axes (knnquery.cu:263)
   unsigned long long key = KEY_NONE, thr = KEY_NONE;
-  const int zlo = max(0, fz - L), zhi = min(dz - 1, fz + L);
-  if (zlo > zhi) return key;
-  // Search-grid mode: skip the cells of the 27 that the radius ball cannot reach (a corner cell is farther than r from
-  // most queries).  gap = distance from the query to the near face of the neighbouring column / cell, shrunk by `eps`
-  // (>> the fp32 rounding of the cell assignment floor((p - s) / cell)), so a skipped cell provably holds no point
-  // with d2 <= r2: the result is unchanged.
-  float ux = 0.f, uy = 0.f, uz = 0.f, eps = 0.f, r2c = 0.f;
-  if (fine) {
-    ux = __fsub_rn(qx, g.sx) - (float)fx * vx;
-    uy = __fsub_rn(qy, g.sy) - (float)fy * vy;
-    uz = __fsub_rn(qz, g.sz) - (float)fz * vz;
-    eps = vx * (1.0e-3f + 1.0e-5f * (float)max(dx, max(dy, dz)));
-    r2c = r2 * 1.0001f;
-  }
+  const int z0 = max(0, fz - L), z1 = min(dz - 1, fz + L);
+  if (z0 > z1) return key;
+  // (Skipping the cells of the 27 that the radius ball cannot reach was measured and rejected: with cell edge ~ radius
+  // only ~20 % of the corner columns can be skipped, and the per-column distance test costs more instructions than the
+  // shorter scan saves: k_knn_slots 0.27 -> 0.32 ms.)
   for (int cx = max(0, fx - L); cx <= min(dx - 1, fx + L); ++cx)
     for (int cy = max(0, fy - L); cy <= min(dy - 1, fy + L); ++cy) {
-      int z0 = zlo, z1 = zhi;
-      if (fine) {
-        const float gx = cx == fx ? 0.f : fmaxf((cx < fx ? ux : vx - ux) - eps, 0.f);
-        const float gy = cy == fy ? 0.f : fmaxf((cy < fy ? uy : vy - uy) - eps, 0.f);
-        const float rem = r2c - gx * gx - gy * gy;
-        if (rem < 0.f) continue;
-        const float gl = fmaxf(uz - eps, 0.f), gh = fmaxf(vz - uz - eps, 0.f);
-        if (z0 < fz && gl * gl > rem) z0 = fz;
-        if (z1 > fz && gh * gh > rem) z1 = fz;
-      }
       const int base = cx * (dy * dz) + cy * dz;
       const int beg = cstart[base + z0], end = cstart[base + z1 + 1];
       for (int j0 = beg; j0 < end; j0 += 32) {

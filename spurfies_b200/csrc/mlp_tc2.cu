@@ -404,6 +404,7 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
         const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 256 + half * 128);
         __nv_bfloat16* hdst = (l == 0 ? h1 : h2);
         wait_acc(B, t, acc_par);
+        if ((tid & 255) == 0) TL(6, t, l);
         drain_store(t);
         if ((tid & 255) == 0) TL(0, t, l);
         float v[2][16];
@@ -574,7 +575,9 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = u1;
         }
       }
+      if ((tid & 255) == 0) TL(3, t, it);
       signal_a_ready(B, t, rank, tile < ntiles ? dz3 + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      if ((tid & 255) == 0) TL(4, t, it);
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         // dz2 = (dz3 @ W3) * lrelu'(z2) ; dz1 = (dz2 @ W2) * lrelu'(z1)
@@ -583,7 +586,9 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
         const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
         __nv_bfloat16* dzo = (l == 0 ? dz2 : dz1);
         wait_acc(B, t, acc_par);
+        if ((tid & 255) == 0) TL(6, t, l);
         drain_store(t);
+        if ((tid & 255) == 0) TL(0, t, l);
         float v[2][16];
         tmem_ld16(t_acc, v[0]);
 #pragma unroll
@@ -599,11 +604,15 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = u0;
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = u1;
         }
+        if ((tid & 255) == 0) TL(1, t, l);
         signal_a_ready(B, t, rank, tile < ntiles ? dzo + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+        if ((tid & 255) == 0) TL(2, t, l);
       }
       // d latent = dz1 @ W1[:, latent columns]  -> scatter-add (vector atomics, 16 B each)
       wait_acc(B, t, acc_par);
+      if ((tid & 255) == 0) TL(6, t, 2);
       drain_store(t);   // the next iteration's prologue overwrites the A tile
+      if ((tid & 255) == 0) TL(0, t, 2);
       if (half == 0) {
         const int p = sl >= 0 ? pidx[(size_t)sl * 8 + (row & 7)] : -1;
 #pragma unroll
@@ -620,6 +629,7 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
       }
       tc_fence_before();
       epi_bar(t);
+      if ((tid & 255) == 0) TL(5, t, it);
     }
   }
   teardown(tmem);

@@ -222,8 +222,21 @@ class PointVolSDF(nn.Module):
         self._voxel_grid_neural = VoxelGrid((0.025, 0.025, 0.025), (3, 3, 3), (3, 3, 3), max_points_per_voxel,
                                             max_occ_voxels, ranges)
         if neural_points is None:
-            raise RuntimeError("PointVolSDF: pass the neural points as `neural_points` (reading "
-                               "./data/<dataset>/<scan>.ply, pointneus_disent.py:131-205, is outside the hot path)")
+            # pointneus_disent.py:131-146: the scene's DUSt3R cloud, voxel-downsampled at conf.vox_res
+            import os
+            from .ingest import load_neural_points
+            path = conf.get_string("pointcloud_path", default=None)
+            if path is None:
+                if dataset == "dtu":
+                    path = f"./data/{dataset}/scan{scan_id}/{scan_id}.ply"
+                elif dataset in ("mipnerf", "own_data"):
+                    path = f"./data/{dataset}/{scan_id}/{scan_id}.ply"
+                else:
+                    raise NotImplementedError(dataset)
+            if not os.path.exists(path):
+                raise RuntimeError(f"The pointcloud_path must be specified ({path} not found); or pass `neural_points`")
+            data = load_neural_points(path, vox_res=conf.get_int("vox_res", default=None))
+            neural_points, neural_colors = data["pts"].float(), (data["colors"].float() if "colors" in data else None)
         self._init_neural_info(neural_points, neural_colors, device)
         C = conf.feature_vector_size
         self.F_color = nn.Sequential(nn.Linear(C + 39, 256), nn.LeakyReLU(inplace=True), nn.Linear(256, 256),
@@ -251,7 +264,7 @@ class PointVolSDF(nn.Module):
         norms = fg.norm(dim=-1, keepdim=True)
         fg = fg * (torch.clamp(norms, max=1) / (norms + 1e-7))
         if colors is not None and self.conf.get_bool("initialize_colors", default=True):
-            fc[:, :3] = colors.float() * 2.0 / 255.0 - 1.0
+            fc[:, :3] = colors.float().to(fc.device) * 2.0 / 255.0 - 1.0
         self.neural_feats_color = nn.Parameter(fc)
         self.neural_feats_geometry = nn.Parameter(fg)
 

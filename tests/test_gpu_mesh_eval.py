@@ -77,8 +77,8 @@ def test_render_image_chunks_and_shards(setup):
     one, (lo, hi) = E.render_image(model, inp, 96, n_pixels=96)
     assert (lo, hi) == (0, 96) and one["rgb_values"].shape == (96, 3) and one["weights"].shape == (96, 80)
     model.eval()
-    with torch.no_grad():
-        ro = H.render_forward(P, P.make_grid(), uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), False, -1, None)
+    # (not under no_grad: the oracle takes d sdf / d x with autograd.grad, pointneus_disent.py:315-323)
+    ro = H.render_forward(P, P.make_grid(), uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), False, -1, None)
     for k in ("rgb_values", "weights", "depth_values", "normal_map"):   # tolerance of the eval sampler chain, as in
         e = rel_err(one[k].reshape(-1), ro[k].reshape(-1))              # test_gpu_hotpath.test_eval_forward_matches_reference
         assert e < 2e-2, (k, e)
