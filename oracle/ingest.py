@@ -14,7 +14,9 @@ def construct_vox_points_closest(xyz_val, vox_res):  # utils.py:6-37 (bounds-fro
     space_edge = torch.max(xyz_max - xyz_min) * 1.05
     xyz_mid = (xyz_max + xyz_min) / 2
     space_min = xyz_mid - space_edge / 2
-    construct_vox_sz = space_edge / vox_res
+    # The reference evaluates this on CUDA tensors (utils.py:49-55 moves the cloud to the GPU first), where torch divides a
+    # tensor by a Python scalar as `a * (1 / b)` in fp32 (ATen div_true_kernel_cuda), not as an IEEE division: restate that.
+    construct_vox_sz = space_edge * (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(float(vox_res), dtype=torch.float32))
     xyz_shift = xyz - space_min[None, ...]
     sparse_grid_idx, inv_idx = torch.unique(torch.floor(xyz_shift / construct_vox_sz[None, ...]).to(torch.int32), dim=0,
                                             return_inverse=True)

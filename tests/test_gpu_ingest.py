@@ -46,8 +46,14 @@ def test_ply_roundtrip_and_model_from_ply(tmp_path):
     data = ingest.load_neural_points(path, vox_res=60)
     want_pts, want_idx = OI.voxelize(pts, 60)
     assert data["pts"].shape == want_pts.shape and data["colors"].shape == want_pts.shape
-    match = (data["pts"].cpu() == want_pts).all(dim=1).float().mean()
-    assert float(match) > 0.999
+    same = (data["pts"].cpu() == want_pts).all(dim=1)
+    assert float(same.float().mean()) > 0.99
+    # a different kept point is a numerical tie (see the module docstring): its distance to the voxel centroid is
+    # within fp32 rounding of the minimum the restatement found
+    _, _, rm, res, inv = OI.construct_vox_points_closest(pts, 60)
+    d = (~same).nonzero().flatten()
+    got = (pts[None, :, :] == data["pts"].cpu()[d][:, None, :]).all(dim=2).float().argmax(dim=1)
+    assert torch.equal(inv[got], d) and float((res[got] - res[rm[d]]).abs().max() if len(d) else 0.0) < 1e-6
     # ascii PLY without colours
     apath = str(tmp_path / "a.ply")
     with open(apath, "w") as f:
