@@ -149,8 +149,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "WAIT_DONE_C:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Arrivals use the default .release.cta semantics (what CUTLASS's ClusterBarrier::arrive emits): a cluster-scope release
+// compiles to MEMBAR.ALL.GPU + CCTL on the epilogue -> MMA critical path.  The data these barriers order is shared memory
+// written by the arriving CTA's own threads and already made visible to the async proxy by fence.proxy.async + bar.sync.
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // arrive on the barrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
@@ -158,7 +161,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {  // warp 0 of BOTH CTAs
