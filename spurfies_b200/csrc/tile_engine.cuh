@@ -32,18 +32,51 @@ using namespace tc;
 
 // ---- optional timeline instrumentation (development only: build with SPF_TIMELINE=1) --------------------
 #ifdef SPF_TIMELINE
+// Events are appended to a small ring in the CTA's spare shared memory (a shared-memory atomic + clock read: tens of
+// cycles, so the instrumented kernel keeps its shape) and copied out by CTA 0 in teardown().
 __device__ unsigned long long g_tl[4 * 8192];
 __device__ unsigned int g_tl_n;
+constexpr int TL_OFF = 220672;        // == SMEM_BYTES of the normal build (checked below)
+constexpr int TL_MAX = 700;           // 16 B per event
 __device__ __forceinline__ void tl(int ev, int t, int l) {
+  extern __shared__ __align__(1024) uint8_t tl_smem[];
   if (blockIdx.x != 0 || (ev >= 10 && (threadIdx.x & 31) != 0)) return;
-  unsigned i = atomicAdd(&g_tl_n, 1u);
-  if (i < 8192) { g_tl[4 * i] = ev; g_tl[4 * i + 1] = t; g_tl[4 * i + 2] = l; g_tl[4 * i + 3] = clock64(); }
+  unsigned* cnt = reinterpret_cast<unsigned*>(tl_smem + TL_OFF);
+  const unsigned i = atomicAdd(cnt, 1u);
+  if (i < TL_MAX) {
+    unsigned long long* e = reinterpret_cast<unsigned long long*>(tl_smem + TL_OFF + 16 + 16 * i);
+    e[0] = (unsigned long long)ev | ((unsigned long long)t << 8) | ((unsigned long long)l << 16);
+    e[1] = clock64();
+  }
+}
+__device__ __forceinline__ void tl_init() {
+  extern __shared__ __align__(1024) uint8_t tl_smem[];
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(tl_smem + TL_OFF) = 0u;
+}
+__device__ __forceinline__ void tl_dump() {
+  extern __shared__ __align__(1024) uint8_t tl_smem[];
+  if (blockIdx.x != 0) return;
+  unsigned n = *reinterpret_cast<unsigned*>(tl_smem + TL_OFF);
+  if (n > TL_MAX) n = TL_MAX;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long* e = reinterpret_cast<const unsigned long long*>(tl_smem + TL_OFF + 16 + 16 * i);
+    g_tl[4 * i] = e[0] & 0xff; g_tl[4 * i + 1] = (e[0] >> 8) & 0xff; g_tl[4 * i + 2] = (e[0] >> 16) & 0xff; g_tl[4 * i + 3] = e[1];
+  }
+  if (threadIdx.x == 0) g_tl_n = n;
 }
 #define TL(ev, t, l) tl(ev, t, l)
+#define TL_INIT() tl_init()
+#define TL_DUMP() tl_dump()
 __device__ int g_dbg_mode;   // 0 normal, 1 epilogue skips TMEM loads, 2 epilogue loads but skips math + smem stores
+#ifdef SPF_DBGMODE
 #define DBG_MODE g_dbg_mode
 #else
+#define DBG_MODE 0
+#endif
+#else
 #define TL(ev, t, l)
+#define TL_INIT()
+#define TL_DUMP()
 #define DBG_MODE 0
 #endif
 
@@ -60,7 +93,12 @@ constexpr int OFF_PART = OFF_W + NSLOT * SLOT_BYTES; // 2 tiles x 256 floats
 constexpr int OFF_BIAS = OFF_PART + 2048;            // 5 x 256 floats (per-kernel use)
 constexpr int OFF_CHAIN = OFF_BIAS + 5120;           // the layer table (struct Chain)
 constexpr int OFF_BAR = OFF_CHAIN + 256;
-constexpr int SMEM_BYTES = OFF_BAR + 256;            // 220 928 <= 232 448
+#ifdef SPF_TIMELINE
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 16 + 16 * 700;   // + the event ring
+static_assert(TL_OFF == OFF_BAR + 256 && SMEM_BYTES <= 232448, "timeline ring placement");
+#else
+constexpr int SMEM_BYTES = OFF_BAR + 256;            // 220 672 <= 232 448
+#endif
 constexpr int MAX_LAYERS = 8;
 
 struct Layer {
@@ -95,6 +133,7 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem) {
 
 // common prologue: barrier init, TMEM allocation (512 columns, both CTAs), cluster-wide visibility. Returns TMEM base.
 __device__ __forceinline__ uint32_t setup(uint8_t* smem, const Bars& b) {
+  TL_INIT();
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(b.w_full + s, 1); mbar_init(b.w_empty + s, 1); mbar_init(b.w_peer + s, 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(b.acc_full + t, 1); mbar_init(b.a_ready + t, 2); }
@@ -110,6 +149,7 @@ __device__ __forceinline__ uint32_t setup(uint8_t* smem, const Bars& b) {
 __device__ __forceinline__ void teardown(uint32_t tmem) {
   tc_fence_before();
   __syncthreads();
+  TL_DUMP();
   cluster_sync_all();   // the peer may still be signalling our barriers / the leader's MMAs still read our smem
   if ((threadIdx.x >> 5) == 0) tmem_dealloc2(tmem, 512);
 }
@@ -200,6 +240,7 @@ __device__ __forceinline__ void signal_a_ready(const Bars& b, int t, uint32_t ra
   fence_proxy_async();
   epi_bar(t);
   if ((threadIdx.x & (EPI_THREADS - 1)) == 0) {
+    TL(4, t, 0);
     if (gdst) { bulk_s2g(gdst, ssrc, bytes); bulk_commit(); }
     if (rank == 0) mbar_arrive_local(b.a_ready + t);
     else mbar_arrive_remote(b.a_ready + t, 0);

@@ -137,13 +137,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
-// wait on a barrier other CTAs of the cluster arrive on (acquire at cluster scope)
+// wait on a barrier other CTAs of the cluster arrive on.  Default (cta-scope) acquire, as CUTLASS's ClusterBarrier::wait:
+// a cluster-scope acquire makes ptxas emit CCTL.IVALL (whole-L1 invalidate) after every wait, and the waiter (the MMA
+// issuer) consumes the guarded shared memory through the async proxy only.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP_C:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra WAIT_DONE_C;\n\t"
       "bra WAIT_LOOP_C;\n\t"
       "WAIT_DONE_C:\n\t"

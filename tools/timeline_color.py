@@ -20,7 +20,7 @@ fields.set_precision("bf16")
 fc = [m for m in model.F_color if isinstance(m, torch.nn.Linear)]
 buf = (C.c_ulonglong * (4 * 8192))()
 _lib.lib.spf_debug_mode(mode)
-NAMES = {0: "E.ready(acc+drain)", 1: "E.compute_done", 2: "E.signalled", 3: "E.gather_done", 4: "E.gather_signalled",
+NAMES = {0: "E.ready(acc+drain)", 1: "E.compute_done", 2: "E.signalled", 3: "E.gather_done", 4: "E.bar_passed", 4: "E.gather_signalled",
          5: "E.iter_end", 6: "E.acc_seen", 10: "M.a_ready_seen", 11: "M.issued"}
 
 

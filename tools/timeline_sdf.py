@@ -37,7 +37,7 @@ for mode in (1, 2, 0):
 nev = _lib.lib.spf_debug_timeline(buf, 8192)
 ev = sorted([(buf[4*i+3], buf[4*i], buf[4*i+1], buf[4*i+2]) for i in range(nev)])
 t0 = ev[0][0]
-names = {0: "E.acc_seen", 1: "E.compute_done", 2: "E.signalled", 3: "E.gather_done", 10: "M.a_ready_seen", 11: "M.issued"}
+names = {0: "E.acc_seen", 1: "E.compute_done", 2: "E.signalled", 3: "E.gather_done", 4: "E.bar_passed", 10: "M.a_ready_seen", 11: "M.issued"}
 print("events", nev)
 for c, e, t, l in ev[:260]:
     print(f"{c - t0:9d} cyc  {'  ' if t == 0 else '                          '}tile{t} L{l} {names.get(e, e)}")
