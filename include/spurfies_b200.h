@@ -232,6 +232,27 @@ int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, co
 /* out[idx[i]] = vals[i] */
 int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream);
 
+/* ---- f4: feature-consistency ("local") loss on the hot path's per-ray SDF (spurfies/model/pointneus_disent.py:586-612
+ * find_surface_points + :727-763; spurfies/feat_utils.py:377-451 get_local_loss with uncerts = None, :43-77 projection /
+ * grid normalisation) -------------------------------------------------------------------------------------------------- */
+/* Per ray r: cross[r] = first slot i with sdf[i] * sdf[i+1] < 0 and sdf[i+1] < sdf[i] (slots equal to 1000 = "no
+ * neighbour" never cross), -1 if none; d_surface[r] = interpolated depth of the crossing (0 if none).  With m > 0 source
+ * views: num[r] = sum over the m views of |1 - cos(feat_ref(x), feat_src_v(x))| where both projections are inside the image
+ * and the term is < 0.5, x = cam_loc + d_surface * dir; g0 / g1 [R] = d num / d sdf at slots cross and cross + 1.  The loss
+ * is sum(num) / (m * #crossing rays) (the reference's .mean() over [m, n]).  feat_ref [C,H,W] and feat_src [m][C,H,W] are
+ * addressed as base + c * chan_stride + (y * W + x) * pix_stride (+ v * src_stride): NCHW = (H*W, 1), channels-last =
+ * (1, C).  C must be 32 (SPF_ERR_UNSUPPORTED otherwise).  cam_ref [2,4,4], cam_src [m,2,4,4]: [0] world->camera,
+ * [1][:3,:3] intrinsics at twice the feature resolution.  m == 0: surface search only (feature / camera pointers unused). */
+int spf_local_loss_fwd(const float* sdf /*[R,Smax]*/, const float* t /*[R,Smax]*/, const float* cam_loc /*[3]*/,
+                       const float* ray_dirs /*[R,3]*/, int32_t R, int32_t Smax, const float* feat_ref,
+                       const float* feat_src, int64_t src_stride, int64_t chan_stride, int64_t pix_stride, int32_t channels,
+                       const float* cam_ref, const float* cam_src, int32_t m, int32_t H, int32_t W,
+                       const float* size /*[1] device*/, const float* center /*[3] device*/, float* num /*[R]*/,
+                       int32_t* cross /*[R]*/, float* d_surface /*[R]*/, float* g0 /*[R]*/, float* g1 /*[R]*/, void* stream);
+/* d_sdf [R,Smax] (every element written) = scale[0] * (g0 at slot cross, g1 at slot cross + 1, 0 elsewhere) */
+int spf_local_loss_bwd(const int32_t* cross, const float* g0, const float* g1, const float* scale /*[1] device*/, int32_t R,
+                       int32_t Smax, float* d_sdf, void* stream);
+
 /* ---- f3: neural-point ingestion (spurfies/model/utils.py:6-37 construct_vox_points_closest) --------------------------- */
 size_t spf_voxelize_workspace_bytes(int32_t cells_per_axis);
 /* Voxel-downsample: voxel of a point = floor((p - space_min) / vox_size) per axis (fp32, as the reference computes it);

@@ -383,8 +383,8 @@ def tv_regul(p: Params, grid: OracleGrid):
 
 # ----------------------------------------------------------------------------- full forward
 def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: SamplerCfg, training: bool,
-                   fast: int = -1, rng=None, far_cfg: float = 4.5, with_tv: bool = True, z_vals=None):
-    """PointVolSDF.forward (pointneus_disent.py:614-892) without the DTU-only local loss."""
+                   fast: int = -1, rng=None, far_cfg: float = 4.5, with_tv: bool = True, z_vals=None, local_data=None):
+    """PointVolSDF.forward (pointneus_disent.py:614-892); the DTU-only local loss (:727-763) when `local_data` is given."""
     ray_dirs, cam_loc = camera_rays(uv, pose, intrinsics)
     ray_dirs_tmp, _ = camera_rays(uv, torch.eye(4)[None], intrinsics)
     depth_scale = ray_dirs_tmp[0, :, 2:]
@@ -399,6 +399,7 @@ def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: Sampl
     vm = mask[ray_mask]                                            # valid_neural_pts_mask [Rv,S]
     out = {"z_vals": z_vals, "ray_mask": ray_mask, "mask": mask}
     pseudo_loss = torch.tensor(0.0)
+    local_loss = torch.tensor(0.0)
     Rv = int(ray_mask.sum())
     have = shading_pts.shape[0] > 0
     if have:
@@ -437,6 +438,9 @@ def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: Sampl
         density_filler = torch.zeros(Rv, S, 1)
         density_filler[vm] = laplace_density(agg_sdf, get_beta(p))
         weights_values = volume_rendering(deltas[..., 0], density_filler[..., 0])
+        if local_data is not None and training:                                       # pointneus_disent.py:727-763
+            from .local_loss import local_loss_from_rays
+            local_loss = local_loss_from_rays(sdf_filler[..., 0], z_values[..., 0], o, dd, local_data)
         dist_map = torch.sum(weights_values / (weights_values.sum(-1, keepdim=True) + 1e-10) * z_values.squeeze(-1), -1)
         pts_rendered = o + dd * dist_map[:, None]
         sdf_rendered = point_sdf(p, grid, pts_rendered, compact=True)
@@ -471,7 +475,7 @@ def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: Sampl
         weights[ray_mask] = weights_values
         depth_vals[ray_mask] = z_values.squeeze(-1) * depth_scale[ray_mask]
     out.update(rgb_values=rgb, depth_values=depth, depth_vals=depth_vals, weights=weights, xyz=xyz,
-               accumulation=acc, local_loss=torch.tensor(0.0), pseudo_pts_loss=pseudo_loss)
+               accumulation=acc, local_loss=local_loss, pseudo_pts_loss=pseudo_loss)
     out["tv_loss"] = tv_regul(p, grid) if with_tv else torch.tensor(0.0)
     if not training:
         if have:

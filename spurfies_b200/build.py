@@ -19,6 +19,7 @@ SOURCES = {
     "optim.cu": [],
     "mesh.cu": ["-fmad=false"],
     "ingest.cu": ["-fmad=false"],
+    "local_loss.cu": [],
 }
 
 

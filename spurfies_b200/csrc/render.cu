@@ -499,10 +499,14 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   __syncwarp();
   for (int i = lane; i < cols; i += 32) {
     float v = ssort[i];
+    const bool vnan = v != v;
     int rank = 0;
     for (int j = 0; j < cols; ++j) {
+      // torch.sort order: NaN sorts last (a miss ray's samples are NaN, as in the reference); ties by position, so
+      // the ranks are a permutation and every output element is written
       float o = ssort[j];
-      rank += (o < v) || (o == v && j < i);
+      const bool onan = o != o;
+      rank += (!onan && (vnan || o < v)) || ((o == v || (onan && vnan)) && j < i);
     }
     out_z[(size_t)r * cols + rank] = v;
 #pragma unroll
@@ -547,16 +551,19 @@ __global__ void k_sampler_merge(const float* __restrict__ z, const float* __rest
   const float* b = zs + (size_t)r * N;
   float* zo = z_out + (size_t)r * (M + N);
   float* so = sdf_out + (size_t)r * (M + N);
+  // torch.sort order with NaN last (the samples of a miss ray are NaN): the two rank maps stay a permutation
   for (int i = lane; i < M; i += 32) {
     float v = a[i];
-    int lo = 0, hi = N;  // count of b < v
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (b[mid] < v) lo = mid + 1; else hi = mid; }
+    const bool vnan = v != v;
+    int lo = 0, hi = N;  // count of b sorting strictly before v
+    while (lo < hi) { int mid = (lo + hi) >> 1; float x = b[mid]; if ((x == x) && (vnan || x < v)) lo = mid + 1; else hi = mid; }
     zo[i + lo] = v; so[i + lo] = sdf[(size_t)r * M + i];
   }
   for (int j = lane; j < N; j += 32) {
     float v = b[j];
-    int lo = 0, hi = M;  // count of a <= v
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    const bool vnan = v != v;
+    int lo = 0, hi = M;  // count of a sorting before or equal to v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (vnan || a[mid] <= v) lo = mid + 1; else hi = mid; }
     zo[j + lo] = v; so[j + lo] = sdf_s[(size_t)r * N + j];
   }
 }

@@ -462,3 +462,87 @@ class TVRegul(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return (ctx.grad * g if ctx.grad is not None else None), None, None
+
+
+# ------------------------------------------------------------------------------------------------ f4: local loss
+def surface_search(sdf, t, cam_loc, ray_dirs, R, Smax, feats=None):
+    """spf_local_loss_fwd: first back-facing zero crossing per ray (pointneus_disent.py:586-612) and, with ``feats``
+    (see ``local_feature_args``), the per-ray numerator of the feature-consistency loss and its SDF partials."""
+    dev = sdf.device
+    num = torch.empty(R, dtype=torch.float32, device=dev)
+    cross = torch.empty(R, dtype=torch.int32, device=dev)
+    d_surface = torch.empty(R, dtype=torch.float32, device=dev)
+    g0 = torch.empty(R, dtype=torch.float32, device=dev)
+    g1 = torch.empty(R, dtype=torch.float32, device=dev)
+    sdf, t, cam_loc, ray_dirs = (v.detach().float().contiguous() for v in (sdf, t, cam_loc, ray_dirs))
+    if feats is None:
+        fa = (None, None, 0, 0, 0, 32, None, None, 0, 0, 0, None, None)
+    else:
+        fa = feats["args"]
+    call("spf_local_loss_fwd", ptr(sdf), ptr(t), ptr(cam_loc), ptr(ray_dirs), R, Smax, *fa, ptr(num), ptr(cross),
+         ptr(d_surface), ptr(g0), ptr(g1), stream())
+    return num, cross, d_surface, g0, g1
+
+
+def local_feature_args(local_data: dict, device) -> dict:
+    """Device-side view of the reference's ``local_data`` dict (spurfies/datasets/dtu.py:277-291) for the kernel:
+    feat [C,H,W], feat_src [m,C,H,W] (NCHW as the reference holds them, or channels-last storage -- whatever the strides
+    say), cam [2,4,4], src_cams [m,2,4,4], size (scalar), center [3].  No copies when the tensors already live on the
+    device as fp32; the returned dict keeps them alive."""
+    f32 = lambda v: v.to(device=device, dtype=torch.float32)
+    feat, src = f32(local_data["feat"]), f32(local_data["feat_src"])
+    if src.dim() == 3:
+        src = src.unsqueeze(0)
+    Cn, H, W = feat.shape
+    m = src.shape[0]
+
+    def strides_ok(a, b):
+        # both addressed as c * cs + (y * W + x) * ps: NCHW-contiguous or channels-last storage
+        return a.stride()[-3:] == b.stride()[-3:] and a.stride(-2) == W * a.stride(-1)
+    if not strides_ok(feat, src) or (m > 1 and src.stride(0) <= 0):
+        feat, src = feat.contiguous(), src.contiguous()
+    dptr = lambda v: v.data_ptr() if v.is_cuda else ptr(v)   # strided (channels-last) views are addressed by stride
+    cam = f32(local_data["cam"]).contiguous()
+    src_cams = f32(local_data["src_cams"]).reshape(m, 2, 4, 4).contiguous()
+    size = f32(torch.as_tensor(local_data["size"])).reshape(-1)[:1].contiguous()
+    center = f32(torch.as_tensor(local_data["center"])).reshape(-1)[:3].contiguous()
+    keep = (feat, src, cam, src_cams, size, center)
+    args = (dptr(feat), dptr(src), int(src.stride(0)) if m > 0 else 0, int(feat.stride(0)), int(feat.stride(2)), int(Cn),
+            ptr(cam), ptr(src_cams), int(m), int(H), int(W), ptr(size), ptr(center))
+    return {"args": args, "keep": keep, "m": m}
+
+
+def channels_last_features(local_data: dict, device="cuda") -> dict:
+    """Optional one-off re-layout of a view's feature maps to channels-last storage (one 128-byte line per bilinear
+    corner instead of 32 sectors); shapes stay [C,H,W] / [m,C,H,W], so the dict is used exactly like the original."""
+    out = dict(local_data)
+    feat = local_data["feat"].to(device=device, dtype=torch.float32)
+    src = local_data["feat_src"].to(device=device, dtype=torch.float32)
+    out["feat"] = feat.permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    out["feat_src"] = src.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return out
+
+
+class LocalLoss(torch.autograd.Function):
+    """Feature-consistency loss of the rendered surface (pointneus_disent.py:727-763 + feat_utils.py:377-451):
+    mean over (source view, crossing ray) of |1 - cos| gated by in-image and < 0.5; gradient to the dense SDF only."""
+
+    @staticmethod
+    def forward(ctx, sdf, t, cam_loc, ray_dirs, feats, R, Smax):
+        sdf_c = sdf.detach().contiguous()
+        num, cross, d_surface, g0, g1 = surface_search(sdf_c, t, cam_loc, ray_dirs, R, Smax, feats)
+        hits = (cross >= 0).sum()
+        inv = 1.0 / (feats["m"] * hits.clamp(min=1)).to(torch.float32)
+        ctx.saved_t = (cross, g0, g1, inv)
+        ctx.dims = (R, Smax)
+        ctx.mark_non_differentiable(d_surface, cross)
+        return num.sum() * inv, d_surface, cross
+
+    @staticmethod
+    def backward(ctx, g, _d, _c):
+        cross, g0, g1, inv = ctx.saved_t
+        R, Smax = ctx.dims
+        d_sdf = torch.empty(R * Smax, dtype=torch.float32, device=cross.device)
+        scale = (g * inv).reshape(1).contiguous()
+        call("spf_local_loss_bwd", ptr(cross), ptr(g0), ptr(g1), ptr(scale), R, Smax, ptr(d_sdf), stream())
+        return d_sdf, None, None, None, None, None, None

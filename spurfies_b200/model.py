@@ -25,7 +25,8 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import call, ptr, stream
-from .fields import ColorField, Composite, GeoPack, GeoSDF, RadianceHead, SlotSet, TVRegul, geo_sdf_raw, set_precision
+from .fields import (ColorField, Composite, GeoPack, GeoSDF, LocalLoss, RadianceHead, SlotSet, TVRegul, geo_sdf_raw,
+                     local_feature_args, set_precision, surface_search)
 from .knnquery import VoxelGrid
 
 
@@ -311,6 +312,19 @@ class PointVolSDF(nn.Module):
             return torch.ones(x.shape[0], device=x.device) * 1000
         return sdf[slots.list[:slots.V].long()].unsqueeze(-1)
 
+    def find_surface_points(self, sdf, d_all, device="cuda"):
+        """pointneus_disent.py:586-612: sdf, d_all [..., Rv, S] (1000 = slot without neighbours) -> (d_surface, mask)
+        [..., Rv]: depth of the first back-facing zero crossing per ray.  (The reference also overwrites the 1000s of
+        its argument with NaN in place; nothing downstream reads that.)"""
+        shape = sdf.shape[:-1]
+        S = sdf.shape[-1]
+        sd = sdf.detach().reshape(-1, S).float().contiguous()
+        dd = d_all.detach().reshape(-1, S).float().contiguous()
+        Rv = sd.shape[0]
+        zero3 = torch.zeros(3, device=sd.device)
+        _, cross, d_surface, _, _ = surface_search(sd, dd, zero3, torch.zeros(max(Rv, 1), 3, device=sd.device), Rv, S)
+        return d_surface.reshape(shape), (cross >= 0).reshape(shape)
+
     def volume_rendering(self, deltas, density):
         """pointneus_disent.py:894-908 (API compatibility; the hot path uses the fused compositing kernel)."""
         free_energy = deltas * density
@@ -370,6 +384,13 @@ class PointVolSDF(nn.Module):
         weights, rgb, depth, acc, dist, normal = Composite.apply(sdf, rgb_s, beta, delta.view(-1), t.view(-1), grad,
                                                                  slots.pidx, nvalid, R, S, K, not self.training)
         ray_mask = nvalid > 0
+        # feature-consistency loss at the first back-facing zero crossing (pointneus_disent.py:727-763, DTU 3-view only)
+        local_data = input.get("local_data", None)
+        local_loss = torch.zeros((), device=dev)
+        if local_data is not None and self.training:
+            feats = local_feature_args(local_data, dev)
+            local_loss, d_surface, cross = LocalLoss.apply(sdf, t, cam_loc, ray_dirs, feats, R, S)
+            self._last_surface = (d_surface, cross)
         # pseudo points (pointneus_disent.py:765-780): expected-depth point per hit ray, SDF should vanish there
         if aux_losses:
             pts_rendered = cam_loc[None, :] + ray_dirs * dist[:, None]
@@ -390,7 +411,7 @@ class PointVolSDF(nn.Module):
             "depth_vals": depth_vals,
             "weights": weights,
             "xyz": x_new,
-            "local_loss": torch.zeros((), device=dev),   # DTU-only feature-consistency loss: SURVEY 8(f4), not built
+            "local_loss": local_loss,
             "pseudo_pts_loss": pseudo,
             "tv_loss": self.tv_loss() if aux_losses else torch.zeros((), device=dev),
         }

@@ -110,3 +110,34 @@ def rng_inputs(n_rays: int, step: int, n_coarse: int = 128, n_fine: int = 64, n_
 def synthetic_gt(n_rays: int, seed: int):
     g = torch.Generator().manual_seed(seed + 99)
     return {"rgb": torch.rand(1, n_rays, 3, generator=g), "mask": (torch.rand(1, n_rays, 3, generator=g) > 0.3).float()}
+
+
+def local_data(view: int, radius: float, n_views: int = 3, feat_res: Tuple[int, int] = (512, 384), channels: int = 32,
+               size: float = 2.6, center=(0.05, -0.1, 0.15), seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic stand-in for the Vis-MVSNet feature data of one DTU training view (spurfies/datasets/dtu.py:205-240,
+    277-291): `feat` [C,H,W] of the view, `feat_src` [m,C,H,W] of the other views, `cam` [2,4,4] / `src_cams` [m,2,4,4]
+    (row 0 = world->camera of the UN-normalised scene, row 1[:3,:3] = intrinsics at twice the feature resolution),
+    `size`, `center` of the normalisation (world = p / 2 * size + center).  Features are smooth positive functions of
+    the pixel so that neighbouring views correlate (no network / checkpoint is available)."""
+    W, H = feat_res
+    g = torch.Generator().manual_seed(seed + 4242)
+    freq = torch.rand(channels, 2, generator=g) * 5.0 + 0.5
+    phase = torch.rand(channels, generator=g) * 6.2831853
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) / H, torch.arange(W, dtype=torch.float32) / W,
+                            indexing="ij")
+    c = torch.tensor(center, dtype=torch.float32)
+    to_norm = torch.eye(4)
+    to_norm[:3, :3] *= 2.0 / size
+    to_norm[:3, 3] = -2.0 * c / size
+
+    def one(v):
+        cam = camera(v, radius, res=(2 * W, 2 * H), focal=600.0 * (2 * W) / 512.0, n_views=n_views)
+        ext = torch.linalg.inv(cam["pose"][0]) @ to_norm                     # world (un-normalised) -> camera
+        f = 1.0 + 0.6 * torch.sin(freq[:, 0, None, None] * xs[None] * 6.2831853 + freq[:, 1, None, None] * ys[None] * 6.2831853
+                                  + phase[:, None, None] + 0.35 * v)
+        return f.contiguous(), torch.stack([ext, cam["intrinsics"][0]], 0)
+    src = [v for v in range(n_views) if v != view]
+    f0, c0 = one(view)
+    fs, cs = zip(*[one(v) for v in src])
+    return {"feat": f0, "feat_src": torch.stack(fs, 0), "cam": c0, "src_cams": torch.stack(cs, 0),
+            "size": torch.tensor(size), "center": c}

@@ -82,6 +82,12 @@ def test_render_image_chunks_and_shards(setup):
     for k in ("rgb_values", "weights", "depth_values", "normal_map"):   # tolerance of the eval sampler chain, as in
         e = rel_err(one[k].reshape(-1), ro[k].reshape(-1))              # test_gpu_hotpath.test_eval_forward_matches_reference
         assert e < 2e-2, (k, e)
+    # rays that miss the cloud: their up-sampler rows are NaN in the reference as well, torch.sort puts NaN last
+    # (ray_sampler.py:533, 559) -- same pattern here, every element written (this once depended on stale memory)
+    z = model._last["z_vals"].cpu()
+    assert int(torch.isnan(ro["z_vals"]).sum()) > 0
+    assert torch.equal(torch.isnan(z), torch.isnan(ro["z_vals"]))
+    assert rel_err(torch.nan_to_num(z), torch.nan_to_num(ro["z_vals"])) < 2e-2
     # shards: rank r of 2 renders its own contiguous half in 20-pixel chunks
     for r in range(2):
         part, (a, b) = E.render_image(model, inp, 96, n_pixels=20, rank=r, world=2)
