@@ -300,17 +300,18 @@ typedef struct {
   const uint8_t* w4p;    /* pack(F_color.6.weight) */
   const uint8_t* r1fp;   /* pack(R.0.weight[:, 21:277])  (the PE3(dir) columns enter through zpe) */
   const uint8_t* r2p;    /* pack(R.2.weight) */
-  const uint8_t* r3p;    /* pack(R.4.weight padded to [16][256]) */
+  const uint8_t* r3p;    /* pack(R.4.weight padded to [32][256]) */
   const uint8_t* r3tp;   /* pack(R.4.weight^T padded to [256][16 -> 64]) */
   const uint8_t* r2tp; const uint8_t* r1ftp; const uint8_t* w4tp;  /* pack(weight^T) for dgrad */
   const float* b4; const float* rb2; const float* rb3;
 } spf_head_weights_tc;
 /* zpe [R,256] = PE3(dir) @ R.0.weight[:, :21]^T + R.0.bias (fp32, per ray).  Saved bf16 [rows,256] by compact sample
- * row: hb (= hbar), f, a1, a2. */
+ * row, in the TILE layout (see spf_wgrad_tc): hb (= hbar), f, a1, a2; rows = ceil(count / 128) * 128. */
 int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* hbar, const float* zpe, const float* ray_dirs, int32_t Smax, float* rgb, void* hb, void* f,
                     void* a1, void* a2, void* pe /*[rows,32] bf16: PE3(dir) per sample*/, void* stream);
-/* dz3 is bf16 [rows,16] (3 used); drb3 [3] (fp32) is accumulated in-kernel */
+/* a1, a2 in and dzf, dz1, dz2 out: bf16 [rows,256] in the TILE layout; dz3 is bf16 [rows,16] row-major (3 used);
+ * drb3 [3] (fp32) is accumulated in-kernel */
 int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
                     void* dz1, void* dz2, void* dz3, float* drb3, void* stream);

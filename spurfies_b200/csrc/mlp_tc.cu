@@ -1,18 +1,6 @@
-// mlp_tc.cu -- bf16 tensor-core mode, single-CTA kernels: the radiance head (per SAMPLE, 8x fewer rows than the per-pair
-// fields, which live in mlp_tc2.cu on the CTA-pair tile engine), the split-K weight-gradient kernel, weight packing and
-// the tcgen05 building-block self test.  The description below is the single-CTA tile scheme the head kernels use.
-//
-// One persistent CTA per SM walks tiles of 128 pair rows (16 slots x 8 neighbours).  Per tile the whole MLP chain
-// runs on-chip:
-//   gather (coalesced vector loads of latent rows) -> A operand tile in shared memory (bf16, 128B-swizzled K-major)
-//   per layer: weights arrive by bulk copy (TMA engine, UBLKCP) into shared memory, ONE elected thread issues
-//              tcgen05.mma (M=128, N=256, K=16) accumulating fp32 in TMEM, tcgen05.commit -> mbarrier;
-//              8 warps read the accumulator back with tcgen05.ld (thread = pair row), apply bias + LeakyReLU
-//              (or the LeakyReLU derivative mask on the dgrad chain), convert to bf16 and write the NEXT layer's A tile;
-//              the next layer's weight copy is issued as soon as the MMAs retire, so it overlaps the epilogue;
-//   LeakyReLU sign bits stay in registers (each thread owns a row), so the d sdf / d input chain needs no extra memory;
-//   the K=8 neighbour interpolation is an 8-lane shuffle reduction (rows of a slot are consecutive lanes).
-// Activations never touch HBM in the geometry kernel; the colour kernel writes bf16 h1/h2 once for the backward.
+// mlp_tc.cu -- bf16 tensor-core mode, single-CTA kernels: the split-K weight-gradient kernels (row-major operands via a
+// cp.async ring; tile-layout operands via TMA bulk copies), weight packing and the tcgen05 building-block self test.
+// The per-pair fields and the per-sample radiance head live in mlp_tc2.cu on the CTA-pair tile engine.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -20,328 +8,6 @@ using namespace tc;
 
 #define TC_THREADS 256
 #define TC_ROWS 128
-#define TC_SLOTS 16
-#define LEAKY 0.01f
-// shared memory map (bytes)
-#define OFF_A 0
-#define OFF_W 65536
-#define OFF_BIAS (65536 + 131072)            // 4 x 256 floats
-#define OFF_V5 (OFF_BIAS + 4096)             // 256 floats
-#define OFF_PART (OFF_V5 + 1024)             // 2 x 128 floats
-#define OFF_SLOT (OFF_PART + 1024)           // 16 ints
-#define OFF_BAR (OFF_SLOT + 64)              // 2 mbarriers + tmem ptr
-#define OFF_BITS (OFF_BAR + 64)              // LeakyReLU sign bits: [4 layers][4 chunks][256 threads] words
-#define TC_SMEM (OFF_BITS + 16384)
-
-__device__ __forceinline__ float rbf_w(float dx, float dy, float dz, float rbf) {
-  float dist = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-  float tq = dist * rbf;
-  return __expf(-(tq * tq));
-}
-
-// one weight image of the per-tile stream
-struct WImg { const uint8_t* ptr; uint32_t bytes; };
-
-// issue all MMAs of one layer (called by one thread) and commit to bar_m
-__device__ __forceinline__ void issue_layer(uint32_t sA, uint32_t sW, int ksteps, int N, uint32_t tmem_d, uint64_t* bar_m) {
-  const uint32_t idesc = idesc_bf16(128, N);
-  const uint32_t wkb = (uint32_t)N * 128u;
-  for (int s = 0; s < ksteps; ++s) {
-    const int kb = s >> 2, ks = s & 3;
-    mma_bf16(tmem_d, smem_desc_sw128(sA + kb * 16384 + ks * 32), smem_desc_sw128(sW + kb * wkb + ks * 32), idesc, s != 0);
-  }
-  mma_commit(bar_m);
-}
-
-__device__ __forceinline__ void load_weights(uint8_t* sW, WImg w, uint64_t* bar_w) {
-  mbar_expect_tx(bar_w, w.bytes);
-  for (uint32_t o = 0; o < w.bytes; o += 32768) bulk_g2s(sW + o, w.ptr + o, min(32768u, w.bytes - o), bar_w);
-}
-
-// write 32 consecutive columns [c0, c0+32) of this thread's row as bf16 into the A tile
-__device__ __forceinline__ void store_a32(uint8_t* sA, int row, int c0, const float* v) {
-  const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-    *reinterpret_cast<uint4*>(sA + kb * 16384 + sw128_off(row, ch0 + q)) = u;
-  }
-}
-// same values as plain row-major bf16 to global (dst points at this row's column c0)
-__device__ __forceinline__ void store_g32(__nv_bfloat16* dst, const float* v) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-    reinterpret_cast<uint4*>(dst)[q] = u;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// radiance head (per SAMPLE, tile = 128 valid samples), bf16 tensor-core mode:
-//   f = F_color.6(hbar) ; a1 = lrelu(R.0_f f + zpe[ray]) ; a2 = lrelu(R.2 a1) ; rgb = sigmoid(R.4 a2)
-// zpe[ray] = R.0[:, :21] PE3(dir_ray) + R.0.bias is per-ray constant and enters as an fp32 per-row bias.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_head_fwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
-              const float* __restrict__ hbar, const float* __restrict__ zpe, const float* __restrict__ dirs, int Smax,
-              float* __restrict__ rgb, __nv_bfloat16* __restrict__ hb_s, __nv_bfloat16* __restrict__ f_s,
-              __nv_bfloat16* __restrict__ a1_s, __nv_bfloat16* __restrict__ a2_s, __nv_bfloat16* __restrict__ pe_s) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + OFF_A;
-  uint8_t* sW = smem + OFF_W;
-  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_m + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  const int V = *count;
-  const int ntiles = (V + TC_ROWS - 1) / TC_ROWS;
-  if ((int)blockIdx.x >= ntiles) return;
-  const WImg imgs[4] = {{W.w4p, 131072u}, {W.r1fp, 131072u}, {W.r2p, 131072u}, {W.r3p, 4u * 16u * 128u}};
-  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(s_tmem, 256);
-  for (int i = tid; i < 256; i += TC_THREADS) { s_bias[i] = W.b4[i]; s_bias[256 + i] = W.rb2[i]; }
-  if (tid < 3) s_bias[512 + tid] = W.rb3[tid];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  uint32_t wpar = 0, mpar = 0;
-  if (tid == 0) load_weights(sW, imgs[0], bar_w);
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  int tile_i = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
-    const size_t grow = (size_t)tile * TC_ROWS + row;  // compact sample row
-    const int slot = (tile * TC_ROWS + row < V) ? list[tile * TC_ROWS + row] : -1;
-    const float* zrow = zpe + (size_t)(slot >= 0 ? slot / Smax : 0) * 256;
-    if (pe_s && half == 1) {  // PE3(dir) (21 values, embedder.py:10-36) padded to 32: operand of the R.0 weight gradient
-      float pe[32];
-      float d[3] = {0.f, 0.f, 0.f};
-      if (slot >= 0) { const int ray = slot / Smax; d[0] = dirs[3 * ray]; d[1] = dirs[3 * ray + 1]; d[2] = dirs[3 * ray + 2]; }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) pe[a] = d[a];
-      float fr = 1.0f;
-#pragma unroll
-      for (int l = 0; l < 3; ++l) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          float sv, cv;
-          sincosf(d[a] * fr, &sv, &cv);
-          pe[3 + 6 * l + a] = slot >= 0 ? sv : 0.0f;
-          pe[6 + 6 * l + a] = slot >= 0 ? cv : 0.0f;
-        }
-        fr *= 2.0f;
-      }
-#pragma unroll
-      for (int j = 21; j < 32; ++j) pe[j] = 0.0f;
-      store_g32(pe_s + grow * 32, pe);
-    }
-    // A0 = hbar[slot] (bf16)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c0 = half * 128 + q * 32;
-      float v[32];
-      const float4* src = reinterpret_cast<const float4*>(hbar + (size_t)(slot >= 0 ? slot : 0) * 256 + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float4 d = slot >= 0 ? src[j4] : make_float4(0, 0, 0, 0);
-        v[4 * j4] = d.x; v[4 * j4 + 1] = d.y; v[4 * j4 + 2] = d.z; v[4 * j4 + 3] = d.w;
-      }
-      store_a32(sA, row, c0, v);
-      if (hb_s) store_g32(hb_s + grow * 256 + c0, v);
-    }
-#pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, 16, l == 3 ? 16 : 256, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0 && !(l == 3 && tile_i == my_tiles - 1)) load_weights(sW, imgs[(l + 1) % 4], bar_w);
-      if (l < 3) {
-        __nv_bfloat16* dst = l == 0 ? f_s : (l == 1 ? a1_s : a2_s);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = half * 128 + q * 32;
-          float v[32];
-          tmem_ld32(t_lane + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = v[j];
-            if (l == 0) t += s_bias[c0 + j];
-            else if (l == 1) { t += zrow[c0 + j]; t = t > 0.0f ? t : LEAKY * t; }
-            else { t += s_bias[256 + c0 + j]; t = t > 0.0f ? t : LEAKY * t; }
-            v[j] = t;
-          }
-          store_a32(sA, row, c0, v);
-          if (dst) store_g32(dst + grow * 256 + c0, v);
-        }
-      } else if (half == 0) {
-        float v[32];
-        tmem_ld32(t_lane, v);
-        tmem_ld_wait();
-        if (slot >= 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) rgb[3 * (size_t)slot + c] = 1.0f / (1.0f + __expf(-(v[c] + s_bias[512 + c])));
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-extern "C" int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                               const float* hbar, const float* zpe, const float* dirs, int32_t Smax, float* rgb, void* hb,
-                               void* f, void* a1, void* a2, void* pe, void* stream_) {
-  if (!W || !list || !count || !hbar || !zpe || !dirs || !rgb || Smax < 1) return SPF_ERR_INVALID;
-  if (n_max <= 0) return SPF_OK;
-  int64_t tiles = (n_max + TC_ROWS - 1) / TC_ROWS;
-  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  SPF_CUDA(cudaFuncSetAttribute(k_head_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "head_tc attr");
-  k_head_fwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(*W, list, count, hbar, zpe, dirs, Smax, rgb,
-                                                                     (__nv_bfloat16*)hb, (__nv_bfloat16*)f,
-                                                                     (__nv_bfloat16*)a1, (__nv_bfloat16*)a2,
-                                                                     (__nv_bfloat16*)pe);
-  SPF_CHECK_LAUNCH("k_head_fwd_tc");
-  return SPF_OK;
-}
-
-// backward: dz3 = d_rgb * rgb (1 - rgb); dz2 = (dz3 @ R.4) * lrelu'(a2); dz1 = (dz2 @ R.2) * lrelu'(a1);
-//           dzf = dz1 @ R.0[:, 21:]; d_hbar = dzf @ F_color.6
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_head_bwd_tc(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
-              const float* __restrict__ d_rgb, const float* __restrict__ rgb, const __nv_bfloat16* __restrict__ a1_s,
-              const __nv_bfloat16* __restrict__ a2_s, float* __restrict__ d_hbar, __nv_bfloat16* __restrict__ dzf,
-              __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
-              float* __restrict__ drb3) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + OFF_A;
-  uint8_t* sW = smem + OFF_W;
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_m + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  const int V = *count;
-  const int ntiles = (V + TC_ROWS - 1) / TC_ROWS;
-  if ((int)blockIdx.x >= ntiles) return;
-  const WImg imgs[4] = {{W.r3tp, 32768u}, {W.r2tp, 131072u}, {W.r1ftp, 131072u}, {W.w4tp, 131072u}};
-  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(s_tmem, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  uint32_t wpar = 0, mpar = 0;
-  if (tid == 0) load_weights(sW, imgs[0], bar_w);
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  int tile_i = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
-    const size_t grow = (size_t)tile * TC_ROWS + row;
-    const int slot = (tile * TC_ROWS + row < V) ? list[tile * TC_ROWS + row] : -1;
-    if (half == 0) {
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
-      if (slot >= 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { float y = rgb[3 * (size_t)slot + c]; g[c] = d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
-      }
-      const uint4 gz = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
-      reinterpret_cast<uint4*>(dz3 + grow * 16)[0] = gz;                     // [rows,16] bf16, operand of the R.4 wgrad
-      reinterpret_cast<uint4*>(dz3 + grow * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
-      if (drb3) {                                                             // bias gradient of R.4
-        float s0 = warp_sum(g[0]), s1 = warp_sum(g[1]), s2 = warp_sum(g[2]);
-        if (lane == 0) { atomicAdd(drb3, s0); atomicAdd(drb3 + 1, s1); atomicAdd(drb3 + 2, s2); }
-      }
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 0)) = gz;
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_w, wpar);
-        tc_fence_after();
-        issue_layer(aA, aW, l == 0 ? 1 : 16, 256, tmem, bar_m);
-      }
-      wpar ^= 1;
-      mbar_wait(bar_m, mpar);
-      mpar ^= 1;
-      tc_fence_after();
-      if (tid == 0 && !(l == 3 && tile_i == my_tiles - 1)) load_weights(sW, imgs[(l + 1) % 4], bar_w);
-      const __nv_bfloat16* act = (l == 0 ? a2_s : a1_s) + grow * 256;
-      __nv_bfloat16* dzo = (l == 0 ? dz2 : (l == 1 ? dz1 : dzf)) + grow * 256;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c0 = half * 128 + q * 32;
-        float v[32];
-        tmem_ld32(t_lane + c0, v);
-        uint4 a[4];
-        if (l < 2) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = reinterpret_cast<const uint4*>(act + c0)[u];
-        }
-        tmem_ld_wait();
-        if (l < 2) {
-          const uint16_t* ah = reinterpret_cast<const uint16_t*>(a);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint16_t hb = ah[j];
-            const bool pos = ((hb & 0x8000u) == 0) && ((hb & 0x7fffu) != 0);
-            v[j] *= pos ? 1.0f : LEAKY;
-          }
-        }
-        if (l < 3) {
-          store_a32(sA, row, c0, v);
-          store_g32(dzo + c0, v);
-        } else if (slot >= 0) {
-          float4* dst = reinterpret_cast<float4*>(d_hbar + (size_t)slot * 256 + c0);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
-                               const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar,
-                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* stream_) {
-  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || !d_hbar || !dzf || !dz1 || !dz2 || !dz3)
-    return SPF_ERR_INVALID;
-  if (n_max <= 0) return SPF_OK;
-  int64_t tiles = (n_max + TC_ROWS - 1) / TC_ROWS;
-  int grid = (int)(tiles < spf_num_sms() ? tiles : spf_num_sms());
-  SPF_CUDA(cudaFuncSetAttribute(k_head_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM), "headb_tc attr");
-  k_head_bwd_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(
-      *W, list, count, d_rgb, rgb, (const __nv_bfloat16*)a1, (const __nv_bfloat16*)a2, d_hbar, (__nv_bfloat16*)dzf,
-      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3);
-  SPF_CHECK_LAUNCH("k_head_bwd_tc");
-  return SPF_OK;
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dW[256][N] += dZ^T @ A, db[256] += column sums of dZ, over the rows written by the dgrad kernels

@@ -649,6 +649,322 @@ extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* li
   return SPF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// radiance head on the tile engine (rows are valid SAMPLES: tile = 128 samples, super-tile = 512):
+//   f = F_color.6(hbar) ; a1 = lrelu(R.0_f f + zpe[ray]) ; a2 = lrelu(R.2 a1) ; rgb = sigmoid(R.4 a2)
+// zpe[ray] = R.0[:, :21] PE3(dir_ray) + R.0.bias is constant per ray and enters as an fp32 per-row bias.
+// Saved for the backward by compact sample row: hb (= bf16 hbar), f, a1, a2 [.,256] in the engine's TILE layout (one TMA
+// bulk store of the A tile each, see signal_a_ready), pe [.,32] row-major (PE3(dir), operand of the R.0 wgrad).
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
+               const float* __restrict__ hbar, const float* __restrict__ zpe, const float* __restrict__ dirs, int Smax,
+               float* __restrict__ rgb, __nv_bfloat16* __restrict__ hb_s, __nv_bfloat16* __restrict__ f_s,
+               __nv_bfloat16* __restrict__ a1_s, __nv_bfloat16* __restrict__ a2_s, __nv_bfloat16* __restrict__ pe_s) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Bars B = carve_bars(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int V = *count;
+  const int ntiles = (V + 127) / 128;
+  const int nsuper = (ntiles + 3) / 4;
+  const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
+  Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b4, rb2, rb3
+  if (tid == 0) {
+    ch.L[0] = {W.w4p, 4, 16, 256};
+    ch.L[1] = {W.r1fp, 4, 16, 256};
+    ch.L[2] = {W.r2p, 4, 16, 256};
+    ch.L[3] = {W.r3p, 4, 16, 32};
+    ch.n = 4;
+  }
+  for (int i = tid; i < 256; i += THREADS) { s_bias[i] = W.b4[i]; s_bias[256 + i] = W.rb2[i]; }
+  if (tid < 3) s_bias[512 + tid] = W.rb3[tid];
+  const uint32_t tmem = setup(smem, B);
+
+  if (warp == WARP_PRODUCER) {
+    if (lane == 0) producer_loop(ch, n_iter, rank, smem, B);
+  } else if (warp == WARP_MMA) {
+    if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);
+    else if (lane == 0) relay_loop(ch, n_iter, B);
+  } else {
+    const int t = warp >> 3;
+    const int row = 32 * (warp & 3) + lane;
+    const int half = (warp >> 2) & 1;
+    const uint32_t t_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256;
+    const uint32_t t_acc = t_row + half * 128;
+    uint8_t* sA = smem + OFF_A + t * A_BYTES;
+    uint32_t acc_par = 0;
+    int slot_n = -1;
+    {
+      const int li = (4 * cid + 2 * t + (int)rank) * 128 + row;
+      if (n_iter > 0 && li < V) slot_n = list[li];
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = 4 * (cid + it * ncl) + 2 * t + (int)rank;
+      const bool tile_ok = tile < ntiles;
+      const size_t grow = (size_t)tile * 128 + row;   // compact sample row
+      const int slot = slot_n;
+      const int ray = slot >= 0 ? slot / Smax : 0;
+      if (pe_s && half == 1 && tile_ok) {   // PE3(dir) (embedder.py:10-36): 21 values padded to 32
+        float pe[32];
+        float d[3] = {0.f, 0.f, 0.f};
+        if (slot >= 0) { d[0] = dirs[3 * ray]; d[1] = dirs[3 * ray + 1]; d[2] = dirs[3 * ray + 2]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pe[a] = d[a];
+        float fr = 1.0f;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            float sv, cv;
+            sincosf(d[a] * fr, &sv, &cv);
+            pe[3 + 6 * l + a] = slot >= 0 ? sv : 0.0f;
+            pe[6 + 6 * l + a] = slot >= 0 ? cv : 0.0f;
+          }
+          fr *= 2.0f;
+        }
+#pragma unroll
+        for (int j = 21; j < 32; ++j) pe[j] = 0.0f;
+        store_g32(pe_s + grow * 32, pe);
+      }
+      // A0 = hbar[slot] (bf16)
+      {
+        const float4* src = reinterpret_cast<const float4*>(hbar + (size_t)(slot >= 0 ? slot : 0) * 256 + half * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 dq = slot >= 0 ? src[c * 4 + q] : make_float4(0, 0, 0, 0);
+            v[4 * q] = dq.x; v[4 * q + 1] = dq.y; v[4 * q + 2] = dq.z; v[4 * q + 3] = dq.w;
+          }
+          store_a16(sA, row, half * 128 + c * 16, v);
+        }
+      }
+      signal_a_ready(B, t, rank, (hb_s && tile_ok) ? hb_s + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      slot_n = -1;
+      if (it + 1 < n_iter) {
+        const int li = (tile + 4 * ncl) * 128 + row;
+        if (li < V) slot_n = list[li];
+      }
+      const float4* zrow4 = reinterpret_cast<const float4*>(zpe + (size_t)ray * 256 + half * 128);
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        const float4* bias4 = l == 1 ? zrow4 : reinterpret_cast<const float4*>(s_bias + (l == 0 ? 0 : 256) + half * 128);
+        __nv_bfloat16* dst = l == 0 ? f_s : (l == 1 ? a1_s : a2_s);
+        const float slope = l == 0 ? 1.0f : LEAKY;   // F_color.6 has no activation
+        wait_acc(B, t, acc_par);
+        drain_store(t);
+        float v[2][16];
+        tmem_ld16(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 bq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bq[q] = bias4[c * 4 + q];
+          tmem_ld_wait();
+          if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          float* vv = v[c & 1];
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float z0 = vv[4 * q] + bq[q].x, z1 = vv[4 * q + 1] + bq[q].y, z2 = vv[4 * q + 2] + bq[q].z, z3 = vv[4 * q + 3] + bq[q].w;
+            z0 = fmaxf(z0, slope * z0); z1 = fmaxf(z1, slope * z1); z2 = fmaxf(z2, slope * z2); z3 = fmaxf(z3, slope * z3);
+            pk[2 * q] = pack_bf16(z0, z1);
+            pk[2 * q + 1] = pack_bf16(z2, z3);
+          }
+          const int c0 = half * 128 + c * 16;
+          uint8_t* dstA = sA + (c0 >> 6) * 16384;
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        signal_a_ready(B, t, rank, (dst && tile_ok) ? dst + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      }
+      // rgb = sigmoid(R.4 a2 + rb3): 3 of the 32 accumulator columns
+      wait_acc(B, t, acc_par);
+      drain_store(t);   // the next iteration's prologue overwrites the A tile
+      if (half == 0) {
+        float v[16];
+        tmem_ld16(t_row, v);
+        tmem_ld_wait();
+        if (slot >= 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rgb[3 * (size_t)slot + c] = 1.0f / (1.0f + __expf(-(v[c] + s_bias[512 + c])));
+        }
+      }
+      tc_fence_before();
+      epi_bar(t);
+    }
+  }
+  teardown(tmem);
+}
+
+static int sample_grid(int64_t n_max) {
+  const int64_t supers = (n_max + 511) / 512;             // 512 sample rows per cluster iteration
+  const int max_cl = spf_num_sms() / 2;
+  return 2 * (int)(supers < max_cl ? supers : max_cl);
+}
+
+extern "C" int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                               const float* hbar, const float* zpe, const float* dirs, int32_t Smax, float* rgb, void* hb,
+                               void* f, void* a1, void* a2, void* pe, void* stream_) {
+  if (!W || !list || !count || !hbar || !zpe || !dirs || !rgb || Smax < 1) return SPF_ERR_INVALID;
+  if (n_max <= 0) return SPF_OK;
+  SPF_CUDA(cudaFuncSetAttribute(k_head_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "head_tc2 attr");
+  k_head_fwd_tc2<<<sample_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
+      *W, list, count, hbar, zpe, dirs, Smax, rgb, (__nv_bfloat16*)hb, (__nv_bfloat16*)f, (__nv_bfloat16*)a1,
+      (__nv_bfloat16*)a2, (__nv_bfloat16*)pe);
+  SPF_CHECK_LAUNCH("k_head_fwd_tc2");
+  return SPF_OK;
+}
+
+// backward: dz3 = d_rgb * rgb (1 - rgb); dz2 = (dz3 @ R.4) * lrelu'(a2); dz1 = (dz2 @ R.2) * lrelu'(a1);
+//           dzf = dz1 @ R.0[:, 21:]; d_hbar = dzf @ F_color.6.   a1 / a2 are read back from the tile layout for their
+// signs (sign(a) == sign(z)); dz2, dz1, dzf leave in the tile layout for the wgrad kernel, dz3 [rows,16] row-major.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
+               const float* __restrict__ d_rgb, const float* __restrict__ rgb, const uint8_t* __restrict__ a1_s,
+               const uint8_t* __restrict__ a2_s, float* __restrict__ d_hbar, __nv_bfloat16* __restrict__ dzf,
+               __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
+               float* __restrict__ drb3) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Bars B = carve_bars(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int V = *count;
+  const int ntiles = (V + 127) / 128;
+  const int nsuper = (ntiles + 3) / 4;
+  const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
+  Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
+  if (tid == 0) {
+    ch.L[0] = {W.r3tp, 1, 1, 256};
+    ch.L[1] = {W.r2tp, 4, 16, 256};
+    ch.L[2] = {W.r1ftp, 4, 16, 256};
+    ch.L[3] = {W.w4tp, 4, 16, 256};
+    ch.n = 4;
+  }
+  const uint32_t tmem = setup(smem, B);
+
+  if (warp == WARP_PRODUCER) {
+    if (lane == 0) producer_loop(ch, n_iter, rank, smem, B);
+  } else if (warp == WARP_MMA) {
+    if (rank == 0) mma_loop(ch, n_iter, smem, B, tmem);
+    else if (lane == 0) relay_loop(ch, n_iter, B);
+  } else {
+    const int t = warp >> 3;
+    const int row = 32 * (warp & 3) + lane;
+    const int half = (warp >> 2) & 1;
+    const uint32_t t_acc = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256 + half * 128;
+    uint8_t* sA = smem + OFF_A + t * A_BYTES;
+    uint32_t acc_par = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = 4 * (cid + it * ncl) + 2 * t + (int)rank;
+      const bool tile_ok = tile < ntiles;
+      const size_t grow = (size_t)tile * 128 + row;
+      const int li = tile * 128 + row;
+      const int slot = li < V ? list[li] : -1;
+      if (half == 0) {
+        float g[3] = {0.f, 0.f, 0.f};
+        if (slot >= 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { const float y = rgb[3 * (size_t)slot + c]; g[c] = d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
+        }
+        const uint4 gz = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
+        if (tile_ok) {                                                             // [rows,16] bf16: operand of the R.4 wgrad
+          reinterpret_cast<uint4*>(dz3 + grow * 16)[0] = gz;
+          reinterpret_cast<uint4*>(dz3 + grow * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (drb3 && tile_ok) {                                                     // bias gradient of R.4
+          const float s0 = warp_sum(g[0]), s1 = warp_sum(g[1]), s2 = warp_sum(g[2]);
+          if (lane == 0) { atomicAdd(drb3, s0); atomicAdd(drb3 + 1, s1); atomicAdd(drb3 + 2, s2); }
+        }
+        *reinterpret_cast<uint4*>(sA + sw128_off(row, 0)) = gz;                    // K = 16: chunks 0, 1 of k-block 0
+        *reinterpret_cast<uint4*>(sA + sw128_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      signal_a_ready(B, t, rank);
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        const uint8_t* act = (l == 0 ? a2_s : a1_s) + (size_t)tile * (4 * 16384);
+        __nv_bfloat16* dzo = l == 0 ? dz2 : (l == 1 ? dz1 : dzf);
+        const bool masked = l < 2 && tile_ok;
+        wait_acc(B, t, acc_par);
+        drain_store(t);
+        float v[2][16];
+        tmem_ld16(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int c0 = half * 128 + c * 16;
+          const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+          uint4 aw[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (masked) {
+            aw[0] = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0));
+            aw[1] = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0 + 1));
+          }
+          tmem_ld_wait();
+          if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          float* vv = v[c & 1];
+          if (l < 2) {
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(aw);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {   // word i holds activations 2i (low half) and 2i + 1 (high half)
+              const uint32_t w = w32[i];
+              const bool p0 = ((w & 0x8000u) == 0u) && ((w & 0x7fffu) != 0u);
+              const bool p1 = ((w & 0x80000000u) == 0u) && ((w & 0x7fff0000u) != 0u);
+              vv[2 * i] *= p0 ? 1.0f : LEAKY;
+              vv[2 * i + 1] *= p1 ? 1.0f : LEAKY;
+            }
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(vv[2 * i], vv[2 * i + 1]);
+          uint8_t* dstA = sA + kb * 16384;
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, ch0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dstA + sw128_off(row, ch0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        signal_a_ready(B, t, rank, tile_ok ? dzo + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      }
+      // d_hbar[slot] = dzf @ F_color.6 (fp32, consumed by the colour-field backward at valid slots)
+      wait_acc(B, t, acc_par);
+      drain_store(t);   // the next iteration's prologue overwrites the A tile
+      {
+        float v[2][16];
+        tmem_ld16(t_acc, v[0]);
+        float4* dst = reinterpret_cast<float4*>(d_hbar + (size_t)(slot >= 0 ? slot : 0) * 256 + half * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_wait();
+          if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
+          const float* vv = v[c & 1];
+          if (slot >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[c * 4 + q] = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      epi_bar(t);
+    }
+  }
+  teardown(tmem);
+}
+
+extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
+                               const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar,
+                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* stream_) {
+  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || !d_hbar || !dzf || !dz1 || !dz2 || !dz3)
+    return SPF_ERR_INVALID;
+  if (n_max <= 0) return SPF_OK;
+  SPF_CUDA(cudaFuncSetAttribute(k_head_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "headb_tc2 attr");
+  k_head_bwd_tc2<<<sample_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
+      *W, list, count, d_rgb, rgb, (const uint8_t*)a1, (const uint8_t*)a2, d_hbar, (__nv_bfloat16*)dzf,
+      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3);
+  SPF_CHECK_LAUNCH("k_head_bwd_tc2");
+  return SPF_OK;
+}
+
 #ifdef SPF_TIMELINE
 extern "C" int spf_debug_timeline(unsigned long long* host_out, int max_events) {
   unsigned n = 0;

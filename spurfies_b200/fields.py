@@ -323,7 +323,7 @@ class RadianceHead(torch.autograd.Function):
         if tcm:
             imgs = []
             for nm, w, N_, K_, tr, npad, co in (("h.w4p", W[0], 256, 256, False, 256, 0), ("h.r1fp", W[1], 256, 256, False, 256, 21),
-                                               ("h.r2p", W[2], 256, 256, False, 256, 0), ("h.r3p", W[3], 3, 256, False, 16, 0),
+                                               ("h.r2p", W[2], 256, 256, False, 256, 0), ("h.r3p", W[3], 3, 256, False, 32, 0),
                                                ("h.r3tp", W[3], 256, 3, True, 256, 0), ("h.r2tp", W[2], 256, 256, True, 256, 0),
                                                ("h.r1ftp", W[1], 256, 256, True, 256, 21), ("h.w4tp", W[0], 256, 256, True, 256, 0)):
                 im = _img(nm, dev, image_bytes(npad, K_))
@@ -381,12 +381,13 @@ class RadianceHead(torch.autograd.Function):
             drb3 = torch.zeros(3, dtype=torch.float32, device=dev)
             call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
                  ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), ptr(drb3), stream())
-            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1)
-            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1)
-            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False)
+            # hb, f, a1, a2 and dzf, dz1, dz2 are in the tile layout (layout bits), pe and dz3 row-major
+            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1, layout=3)
+            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1, layout=3)
+            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False, layout=1)
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
-            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1)
-            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False)   # (a2^T @ dz3) = dR3^T, [256,16]
+            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1, layout=3)
+            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False, layout=1)   # (a2^T @ dz3) = dR3^T, [256,16]
             dR3 = dR3t[:, :3].t().contiguous()
             return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)

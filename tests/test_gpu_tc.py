@@ -172,6 +172,44 @@ def test_color_field_tc_vs_fp32():
     assert errs["hbar"] < 2e-2 and all(v < 6e-2 for k, v in errs.items() if k != "d latent") and errs["d latent"] < 0.5, errs
 
 
+def test_radiance_head_tc_vs_fp32():
+    """bf16 tcgen05 radiance head (F_color.6 + R: fwd, dgrad, and the wgrad operands it saves in the tile layout) vs the
+    fp32 SIMT kernels, on the same slots, upstream gradient and weights."""
+    from spurfies_b200 import fields
+    from spurfies_b200.fields import RadianceHead, SlotSet
+    sc, P, model = _scene_model()
+    g = torch.Generator().manual_seed(3)
+    R, S = 250, 80
+    q = (sc["pts"][torch.randperm(30000, generator=g)[:R * S]] + 0.015 * torch.randn(R * S, 3, generator=g)).cuda().contiguous()
+    slots = SlotSet(model._grid().query_points(q, 8, 2.0))
+    assert slots.V > 5000 and slots.V % 128 != 0
+    fc = [m for m in model.F_color if isinstance(m, torch.nn.Linear)]
+    rl = [m for m in model.R if isinstance(m, torch.nn.Linear)]
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda().contiguous()
+    hbar0 = (0.5 * torch.randn(R * S, 256, generator=g)).cuda()
+    up = torch.randn(R * S, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    prm = [fc[3].weight, fc[3].bias, rl[0].weight, rl[0].bias, rl[1].weight, rl[1].bias, rl[2].weight, rl[2].bias]
+    res = {}
+    valid = slots.valid_mask()
+    for mode in ("fp32", "bf16"):
+        fields.set_precision(mode)
+        model.zero_grad()
+        hbar = hbar0.clone().requires_grad_()
+        rgb = RadianceHead.apply(hbar, *prm, dirs, slots, S)
+        (rgb * up)[valid].sum().backward()
+        res[mode] = [rgb.detach().clone(), torch.where(valid[:, None], hbar.grad, torch.zeros(())).clone()] + [p.grad.clone() for p in prm]
+    fields.set_precision("fp32")
+    names = ["rgb", "d hbar", "dW4", "db4", "dR1", "drb1", "dR2", "drb2", "dR3", "drb3"]
+    errs = {n: float((a - b).abs().max() / b.abs().max()) for n, a, b in zip(names, res["bf16"], res["fp32"])}
+    print("head tc vs fp32:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert torch.equal(res["bf16"][0][~valid], res["fp32"][0][~valid])
+    # d hbar per row: LeakyReLU sign flips of near-zero pre-activations move a unit's whole contribution (random-sign
+    # upstream, like "d latent" of the colour test) -> bounded in rms, loose in max-norm
+    rms = float(((res["bf16"][1] - res["fp32"][1]) ** 2).mean().sqrt() / (res["fp32"][1] ** 2).mean().sqrt())
+    assert errs["rgb"] < 2e-2 and all(v < 6e-2 for k, v in errs.items() if k != "d hbar"), errs
+    assert errs["d hbar"] < 0.5 and rms < 5e-2, (errs, rms)
+
+
 def _to_tile_layout(t, nkb):
     """[rows (multiple of 128), <= 64 nkb] bf16 row-major -> the colour kernels' tile layout (include/spurfies_b200.h)."""
     rows = t.shape[0]
@@ -185,7 +223,7 @@ def _to_tile_layout(t, nkb):
     return x.permute(0, 2, 1, 3, 4).contiguous().view(-1)              # tile, kb, r, pos, elem
 
 
-@pytest.mark.parametrize("layout", [0, 3])
+@pytest.mark.parametrize("layout", [0, 1, 3])
 @pytest.mark.parametrize("n_units,rpu,N,lda", [(1000, 8, 256, 256), (37, 8, 112, 112), (5000, 1, 256, 256), (300, 1, 16, 64)])
 def test_wgrad_tc(n_units, rpu, N, lda, layout):
     """split-K tcgen05 weight-gradient kernel (MN-major operands, device-side row count) vs torch."""
@@ -201,6 +239,8 @@ def test_wgrad_tc(n_units, rpu, N, lda, layout):
     if layout == 3:
         nkb = (lda + 63) // 64
         dz_in, act_in, lda_in = _to_tile_layout(dz[:rows + 128], 4), _to_tile_layout(act[:rows + 128], nkb), nkb * 64
+    elif layout == 1:   # dZ in the tile layout, A row-major (the radiance head's PE3 / dz3 operands)
+        dz_in = _to_tile_layout(dz[:rows + 128], 4)
     _lib.call("spf_wgrad_tc", _lib.ptr(dz_in), _lib.ptr(act_in), lda_in, N, _lib.ptr(count), rpu, n_units + 50, layout,
               _lib.ptr(dW), _lib.ptr(db), _lib.stream())
     torch.cuda.synchronize()
