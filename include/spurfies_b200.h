@@ -198,6 +198,20 @@ int spf_tv_fwd_bwd(const float* pts, const float* feat_g /*[N,32]*/, const int32
                    int32_t N, int32_t K, float* value /*[1]*/, float* grad /*[N,32] or NULL (accumulated)*/,
                    float grad_scale, void* stream);
 
+/* ---- a14: VolSDFLoss (spurfies/model/loss.py:51-100), forward and gradients in two launches ----------------------
+ * terms[8] = {loss, rgb_loss, eikonal_loss, tv_loss, mask_loss, local_loss, pseudo_loss, #valid samples};
+ * loss = w_rgb rgb + w_eik eik + w_tv tv + w_local local + w_pseudo pseudo + mask.  rgb_loss = mean |rgb - rgb_gt|;
+ * eikonal = mean over valid[i] != 0 of (|grad_theta_i| - 1)^2 (grad_theta NULL -> 0); mask_loss = BCE(clip(sum_s
+ * weights[r,s], 1e-3, 1 - 1e-3), mask_gt[r * mask_stride]) (weights NULL -> 0).  tv / local / pseudo are device scalars
+ * (NULL -> 0).  d_rgb [R,3] and d_weights [R,S] (optional) receive d loss / d rgb and d loss / d weights. */
+size_t spf_loss_workspace_bytes(void);
+int spf_volsdf_loss(const float* rgb /*[R,3]*/, const float* rgb_gt /*[R,3]*/, const float* weights /*[R,S]*/,
+                    const float* mask_gt, int32_t mask_stride, const float* grad_theta /*[n,3]*/,
+                    const uint8_t* valid /*[n]*/, int64_t n, int32_t R, int32_t S, const float* tv, const float* local,
+                    const float* pseudo, float w_rgb, float w_eik, float w_tv, float w_local, float w_pseudo,
+                    float* terms /*[8]*/, float* d_rgb, float* d_weights, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* ---- a15: rays (rend_util.py:60-95, 143-156) ------------------------------------------------ */
 int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, const float* intrinsics /*[4,4]*/,
                     int32_t R, float* ray_dirs /*[R,3]*/, float* cam_loc /*[3]*/, float* depth_scale /*[R]*/,
@@ -290,7 +304,9 @@ typedef struct {
  * [rows,24]: the LeakyReLU sign words of z1, z2, z3 (8 words per layer), consumed by spf_color_bwd_tc */
 int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c, float rbf,
-                     float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn, void* stream);
+                     float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn,
+                     void* hb /* optional out: bf16 copy of hbar by COMPACT slot (position in list), tile layout */,
+                     void* stream);
 /* as spf_color_bwd_f32; dz1..3 are bf16 [rows,256] in the TILE layout; h1 / h2 are not read (the sign words in m3 are) */
 int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
@@ -306,7 +322,9 @@ typedef struct {
   const float* b4; const float* rb2; const float* rb3;
 } spf_head_weights_tc;
 /* zpe [R,256] = PE3(dir) @ R.0.weight[:, :21]^T + R.0.bias (fp32, per ray).  Saved bf16 [rows,256] by compact sample
- * row, in the TILE layout (see spf_wgrad_tc): hb (= hbar), f, a1, a2; rows = ceil(count / 128) * 128. */
+ * row, in the TILE layout (see spf_wgrad_tc): hb (= hbar), f, a1, a2; rows = ceil(count / 128) * 128.
+ * hbar may be NULL: hb is then an INPUT (the compact copy written by spf_color_fwd_tc) and is bulk-copied as the A operand;
+ * the rows of its last tile beyond count are zeroed in place. */
 int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* hbar, const float* zpe, const float* ray_dirs, int32_t Smax, float* rgb, void* hb, void* f,
                     void* a1, void* a2, void* pe /*[rows,32] bf16: PE3(dir) per sample*/, void* stream);

@@ -76,6 +76,8 @@ lib.spf_compact_workspace_bytes.restype = C.c_size_t
 lib.spf_compact_workspace_bytes.argtypes = [C.c_int64]
 lib.spf_optim_workspace_bytes.restype = C.c_size_t
 lib.spf_optim_workspace_bytes.argtypes = []
+lib.spf_loss_workspace_bytes.restype = C.c_size_t
+lib.spf_loss_workspace_bytes.argtypes = []
 lib.spf_voxelize_workspace_bytes.restype = C.c_size_t
 lib.spf_voxelize_workspace_bytes.argtypes = [C.c_int32]
 
@@ -103,6 +105,7 @@ _SIGS = {
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "spf_volsdf_loss": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P, _P, _Z, _P],
     "spf_grad_sumsq": [_P, _L, _F, _P, _P, _Z, _P],
     "spf_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _D, _D, _F, _I, _P, _P],
     "spf_grid_points_mask": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _F, _P, _P, _P, _P, _I, _P],
@@ -117,7 +120,7 @@ _SIGS = {
     "spf_head_fwd_tc": [_P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_pack_sw128": [_P, _I, _I, _I, _I, _I, _P, _P],
-    "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 for _n, _a in _SIGS.items():
@@ -126,7 +129,7 @@ for _n, _a in _SIGS.items():
     _f.argtypes = _a
 
 EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes",
-            "spf_optim_workspace_bytes", "spf_voxelize_workspace_bytes", *_SIGS]
+            "spf_optim_workspace_bytes", "spf_voxelize_workspace_bytes", "spf_loss_workspace_bytes", *_SIGS]
 
 
 class SpfError(RuntimeError):

@@ -303,7 +303,7 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
                 const float* __restrict__ x, const int* __restrict__ pidx, const float* __restrict__ pts,
                 const float* __restrict__ feat_c, float rbf, float* __restrict__ hbar, __nv_bfloat16* __restrict__ in0,
                 __nv_bfloat16* __restrict__ h1, __nv_bfloat16* __restrict__ h2, uint32_t* __restrict__ msign,
-                float* __restrict__ wn_out) {
+                float* __restrict__ wn_out, uint8_t* __restrict__ hb_c) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = carve_bars(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -461,6 +461,11 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
             if (sl >= 0) {
               const int off = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
               *reinterpret_cast<float2*>(hbar + (size_t)sl * 256 + c0 + off) = make_float2(a2[0], a2[1]);
+              if (hb_c) {   // bf16 copy by COMPACT slot in the tile layout: the radiance head's A operand, loaded by TMA
+                const int vs = tile * 16 + (row >> 3), col = c0 + off;
+                *reinterpret_cast<uint32_t*>(hb_c + (size_t)(vs >> 7) * (4 * 16384) + (col >> 6) * 16384 +
+                                             sw128_off(vs & 127, (col & 63) >> 3) + (col & 7) * 2) = pack_bf16(a2[0], a2[1]);
+              }
             }
           }
         }
@@ -485,14 +490,15 @@ static int pair_grid(int64_t n_max) {
 
 extern "C" int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                 const float* x, const int32_t* pidx, int32_t K, const float* pts, const float* feat_c,
-                                float rbf, float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn,
+                                float rbf, float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn, void* hb,
                                 void* stream_) {
   if (!W || !list || !count || !x || !pidx || !pts || !feat_c || !hbar) return SPF_ERR_INVALID;
   if (K != 8) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_color_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "color_tc2 attr");
   k_color_fwd_tc2<<<pair_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
-      *W, list, count, x, pidx, pts, feat_c, rbf, hbar, (__nv_bfloat16*)in0, (__nv_bfloat16*)h1, (__nv_bfloat16*)h2, m3, wn);
+      *W, list, count, x, pidx, pts, feat_c, rbf, hbar, (__nv_bfloat16*)in0, (__nv_bfloat16*)h1, (__nv_bfloat16*)h2, m3, wn,
+      (uint8_t*)hb);
   SPF_CHECK_LAUNCH("k_color_fwd_tc2");
   return SPF_OK;
 }
@@ -681,6 +687,8 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
   }
   for (int i = tid; i < 256; i += THREADS) { s_bias[i] = W.b4[i]; s_bias[256 + i] = W.rb2[i]; }
   if (tid < 3) s_bias[512 + tid] = W.rb3[tid];
+  uint64_t* a_load = reinterpret_cast<uint64_t*>(smem + OFF_BAR + 192);   // [2]: A0 of tile t landed (bulk-copy mode)
+  if (tid == 0) { mbar_init(a_load, 1); mbar_init(a_load + 1, 1); }       // fenced + synchronised inside setup()
   const uint32_t tmem = setup(smem, B);
 
   if (warp == WARP_PRODUCER) {
@@ -695,7 +703,7 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
     const uint32_t t_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + t * 256;
     const uint32_t t_acc = t_row + half * 128;
     uint8_t* sA = smem + OFF_A + t * A_BYTES;
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0, ld_par = 0;
     int slot_n = -1;
     {
       const int li = (4 * cid + 2 * t + (int)rank) * 128 + row;
@@ -729,8 +737,8 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         for (int j = 21; j < 32; ++j) pe[j] = 0.0f;
         store_g32(pe_s + grow * 32, pe);
       }
-      // A0 = hbar[slot] (bf16)
-      {
+      if (hbar) {
+        // A0 = hbar[slot] (bf16), gathered by row; saved as hb
         const float4* src = reinterpret_cast<const float4*>(hbar + (size_t)(slot >= 0 ? slot : 0) * 256 + half * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -742,12 +750,46 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           }
           store_a16(sA, row, half * 128 + c * 16, v);
         }
+        if ((tid & 255) == 0) TL(3, t, it);
+        signal_a_ready(B, t, rank, (hb_s && tile_ok) ? hb_s + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      } else {
+        // A0 = the colour field's compact bf16 copy of hbar, already in the tile layout: one 64 KB bulk copy per tile
+        if ((tid & 255) == 0 && tile_ok) {
+          mbar_expect_tx(a_load + t, 4 * 16384);
+          bulk_g2s(sA, reinterpret_cast<const uint8_t*>(hb_s) + (size_t)tile * (4 * 16384), 4 * 16384, a_load + t);
+        }
+        bool fix = false;
+        if (tile_ok) {
+          mbar_wait(a_load + t, ld_par);
+          ld_par ^= 1u;
+          // rows past the last valid sample of the last tile were never written by the colour kernel: zero them here
+          // (and in the global copy, which the F_color.6 weight gradient reads) so that no stale NaN meets a zero dZ
+          fix = tile == ntiles - 1 && (V & 127) != 0;
+          if (fix && slot < 0) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              *reinterpret_cast<uint4*>(sA + (half * 2 + (c >> 3)) * 16384 + sw128_off(row, c & 7)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            *reinterpret_cast<uint4*>(sA + (half * 2 + (c >> 3)) * 16384 + sw128_off(row, c & 7)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if ((tid & 255) == 0) TL(3, t, it);
+        signal_a_ready(B, t, rank, fix ? hb_s + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
       }
-      signal_a_ready(B, t, rank, (hb_s && tile_ok) ? hb_s + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+      if ((tid & 255) == 0) TL(4, t, it);
       slot_n = -1;
       if (it + 1 < n_iter) {
         const int li = (tile + 4 * ncl) * 128 + row;
-        if (li < V) slot_n = list[li];
+        if (li < V) {
+          slot_n = list[li];
+          if (hbar) {   // pull the next tile's hbar half-row (4 lines) towards L2 while this tile's layers run
+            const char* nx = reinterpret_cast<const char*>(hbar + (size_t)slot_n * 256 + half * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128 * q));
+          }
+        }
       }
       const float4* zrow4 = reinterpret_cast<const float4*>(zpe + (size_t)ray * 256 + half * 128);
 #pragma unroll 1
@@ -756,7 +798,9 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         __nv_bfloat16* dst = l == 0 ? f_s : (l == 1 ? a1_s : a2_s);
         const float slope = l == 0 ? 1.0f : LEAKY;   // F_color.6 has no activation
         wait_acc(B, t, acc_par);
+        if ((tid & 255) == 0) TL(6, t, l);
         drain_store(t);
+        if ((tid & 255) == 0) TL(0, t, l);
         float v[2][16];
         tmem_ld16(t_acc, v[0]);
 #pragma unroll
@@ -780,10 +824,13 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        if ((tid & 255) == 0) TL(1, t, l);
         signal_a_ready(B, t, rank, (dst && tile_ok) ? dst + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
+        if ((tid & 255) == 0) TL(2, t, l);
       }
       // rgb = sigmoid(R.4 a2 + rb3): 3 of the 32 accumulator columns
       wait_acc(B, t, acc_par);
+      if ((tid & 255) == 0) TL(6, t, 3);
       drain_store(t);   // the next iteration's prologue overwrites the A tile
       if (half == 0) {
         float v[16];
@@ -796,6 +843,7 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
       }
       tc_fence_before();
       epi_bar(t);
+      if ((tid & 255) == 0) TL(5, t, it);
     }
   }
   teardown(tmem);
@@ -810,7 +858,7 @@ static int sample_grid(int64_t n_max) {
 extern "C" int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                const float* hbar, const float* zpe, const float* dirs, int32_t Smax, float* rgb, void* hb,
                                void* f, void* a1, void* a2, void* pe, void* stream_) {
-  if (!W || !list || !count || !hbar || !zpe || !dirs || !rgb || Smax < 1) return SPF_ERR_INVALID;
+  if (!W || !list || !count || (!hbar && !hb) || !zpe || !dirs || !rgb || Smax < 1) return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_head_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "head_tc2 attr");
   k_head_fwd_tc2<<<sample_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
@@ -889,7 +937,30 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
       for (int l = 0; l < 3; ++l) {
         const uint8_t* act = (l == 0 ? a2_s : a1_s) + (size_t)tile * (4 * 16384);
         __nv_bfloat16* dzo = l == 0 ? dz2 : (l == 1 ? dz1 : dzf);
-        const bool masked = l < 2 && tile_ok;
+        // LeakyReLU masks of this layer, fetched and compressed to one bit per column (bit 16 (c & 1) + j of word c >> 1
+        // = "a[c0 + j] > 0") BEFORE waiting for the accumulator: the DRAM latency of the saved activations hides under
+        // the MMAs instead of stalling every 16-column chunk of the epilogue
+        uint32_t pos[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (l < 2 && tile_ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int c0 = half * 128 + c * 16;
+            const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+            const uint4 a0 = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0));
+            const uint4 a1 = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0 + 1));
+            const uint32_t w32[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            uint32_t b16 = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {   // word i holds activations 2i (low half) and 2i + 1 (high half)
+              const uint32_t w = w32[i];
+              const uint32_t p0 = (((w & 0x8000u) == 0u) && ((w & 0x7fffu) != 0u)) ? 1u : 0u;
+              const uint32_t p1 = (((w & 0x80000000u) == 0u) && ((w & 0x7fff0000u) != 0u)) ? 1u : 0u;
+              b16 |= (p0 << (2 * i)) | (p1 << (2 * i + 1));
+            }
+            if (c & 1) pos[c >> 1] = (pos[c >> 1] & 0x0000ffffu) | (b16 << 16);
+            else pos[c >> 1] = (pos[c >> 1] & 0xffff0000u) | b16;
+          }
+        }
         wait_acc(B, t, acc_par);
         drain_store(t);
         float v[2][16];
@@ -898,28 +969,17 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         for (int c = 0; c < 8; ++c) {
           const int c0 = half * 128 + c * 16;
           const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
-          uint4 aw[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (masked) {
-            aw[0] = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0));
-            aw[1] = *reinterpret_cast<const uint4*>(act + kb * 16384 + sw128_off(row, ch0 + 1));
-          }
           tmem_ld_wait();
           if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
           float* vv = v[c & 1];
-          if (l < 2) {
-            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(aw);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {   // word i holds activations 2i (low half) and 2i + 1 (high half)
-              const uint32_t w = w32[i];
-              const bool p0 = ((w & 0x8000u) == 0u) && ((w & 0x7fffu) != 0u);
-              const bool p1 = ((w & 0x80000000u) == 0u) && ((w & 0x7fff0000u) != 0u);
-              vv[2 * i] *= p0 ? 1.0f : LEAKY;
-              vv[2 * i + 1] *= p1 ? 1.0f : LEAKY;
-            }
-          }
+          const uint32_t pb = pos[c >> 1] >> (16 * (c & 1));
           uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(vv[2 * i], vv[2 * i + 1]);
+          for (int i = 0; i < 8; ++i) {
+            const float m0 = (pb & (1u << (2 * i))) ? 1.0f : LEAKY;
+            const float m1 = (pb & (2u << (2 * i))) ? 1.0f : LEAKY;
+            pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+          }
           uint8_t* dstA = sA + kb * 16384;
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ch0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ch0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);

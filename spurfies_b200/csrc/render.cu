@@ -638,3 +638,126 @@ extern "C" int spf_tv_fwd_bwd(const float* pts, const float* feat_g, const int32
   SPF_CHECK_LAUNCH("k_tv");
   return SPF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// a14: VolSDFLoss (spurfies/model/loss.py:51-100) forward + its gradients w.r.t. the rendered colour and the
+// compositing weights, fused (the torch version is ~70 tiny launches per step):
+//   rgb_loss  = mean |rgb - gt|                                   (L1Loss, loss.py:29-32)
+//   eikonal   = mean over valid samples of (|grad_theta|_2 - 1)^2 (loss.py:34-40; no gradient: SURVEY D8)
+//   mask_loss = BCE(clip(sum_s w, 1e-3, 1 - 1e-3), mask)          (loss.py:80-84)
+//   loss      = w_rgb rgb + w_eik eik + w_tv tv + w_local local + w_pseudo pseudo + mask
+// Pass 1: one warp per ray, one thread per sample, per-block partial sums (fixed order -> run-to-run deterministic);
+// pass 2: one block folds the partials in double and writes the terms.
+// ------------------------------------------------------------------------------------------------
+#define LOSS_THREADS 256
+#define LOSS_MAX_BLOCKS 1024
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+k_loss_partial(const float* __restrict__ rgb, const float* __restrict__ rgb_gt, const float* __restrict__ weights,
+               const float* __restrict__ mask_gt, int mask_stride, const float* __restrict__ grad_theta,
+               const uint8_t* __restrict__ valid, long long n, int R, int S, float w_rgb, float* __restrict__ d_rgb,
+               float* __restrict__ d_weights, float* __restrict__ partial) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // sum |rgb - gt|, sum bce, sum (|g| - 1)^2, valid count
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv3R = 1.0f / (3.0f * (float)R), invR = 1.0f / (float)R;
+  // rays: one warp per ray (coalesced reads of its S weights, coalesced writes of their gradient); lane c < 3 owns channel c
+  const int lane_ = threadIdx.x & 31;
+  const long long nwarps = stride >> 5;
+  for (long long r = tid0 >> 5; r < R; r += nwarps) {
+    if (lane_ < 3) {
+      const float d = rgb[3 * r + lane_] - rgb_gt[3 * r + lane_];
+      acc[0] += fabsf(d);
+      if (d_rgb) d_rgb[3 * r + lane_] = w_rgb * sgnf(d) * inv3R;
+    }
+    if (weights) {
+      float ws = 0.0f;
+      for (int s = lane_; s < S; s += 32) ws += weights[r * S + s];
+      ws = warp_sum(ws);
+      const float y = mask_gt[r * mask_stride];
+      const float x = fminf(fmaxf(ws, 1.0e-3f), 1.0f - 1.0e-3f);
+      if (lane_ == 0) acc[1] += -(y * fmaxf(logf(x), -100.0f) + (1.0f - y) * fmaxf(logf(1.0f - x), -100.0f));
+      if (d_weights) {
+        // binary_cross_entropy backward (x - y) / max((1 - x) x, 1e-12), through the clip (pass-through inside [min, max])
+        const bool inside = ws >= 1.0e-3f && ws <= 1.0f - 1.0e-3f;
+        const float gx = inside ? (x - y) / fmaxf((1.0f - x) * x, 1.0e-12f) * invR : 0.0f;
+        for (int s = lane_; s < S; s += 32) d_weights[r * S + s] = gx;
+      }
+    }
+  }
+  if (grad_theta) {
+    for (long long i = tid0; i < n; i += stride) {
+      if (valid[i]) {
+        const float gx = grad_theta[3 * i], gy = grad_theta[3 * i + 1], gz = grad_theta[3 * i + 2];
+        const float e = sqrtf(gx * gx + gy * gy + gz * gz) - 1.0f;
+        acc[2] += e * e;
+        acc[3] += 1.0f;
+      }
+    }
+  }
+  __shared__ float s_p[LOSS_THREADS / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) s_p[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float v = 0.0f;
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) v += s_p[w][threadIdx.x];
+    partial[4 * blockIdx.x + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_loss_final(const float* __restrict__ partial, int nb, int R, int has_mask, const float* __restrict__ tv,
+                             const float* __restrict__ local, const float* __restrict__ pseudo, float w_rgb, float w_eik,
+                             float w_tv, float w_local, float w_pseudo, float* __restrict__ terms) {
+  __shared__ double s_d[4][32];
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 128 threads: warp k folds quantity k
+  double v = 0.0;
+  for (int b = lane; b < nb; b += 32) v += (double)partial[4 * b + k];
+  s_d[k][lane] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double q[4];
+    for (int j = 0; j < 4; ++j) {
+      double a = 0.0;
+      for (int l = 0; l < 32; ++l) a += s_d[j][l];
+      q[j] = a;
+    }
+    const float rgb_loss = (float)(q[0] / (3.0 * (double)R));
+    const float mask_loss = has_mask ? (float)(q[1] / (double)R) : 0.0f;
+    const float eik = (float)(q[2] / (q[3] > 1.0 ? q[3] : 1.0));
+    const float tvv = (tv && w_tv > 0.0f) ? tv[0] : 0.0f;
+    const float loc = local ? local[0] : 0.0f;
+    const float pse = (pseudo && w_pseudo > 0.0f) ? pseudo[0] : 0.0f;
+    terms[0] = w_rgb * rgb_loss + w_eik * eik + w_tv * tvv + w_local * loc + w_pseudo * pse + mask_loss;
+    terms[1] = rgb_loss; terms[2] = eik; terms[3] = tvv; terms[4] = mask_loss; terms[5] = loc; terms[6] = pse;
+    terms[7] = (float)q[3];
+  }
+}
+
+extern "C" size_t spf_loss_workspace_bytes(void) { return (size_t)LOSS_MAX_BLOCKS * 4 * sizeof(float); }
+
+extern "C" int spf_volsdf_loss(const float* rgb, const float* rgb_gt, const float* weights, const float* mask_gt,
+                               int32_t mask_stride, const float* grad_theta, const uint8_t* valid, int64_t n, int32_t R,
+                               int32_t S, const float* tv, const float* local, const float* pseudo, float w_rgb, float w_eik,
+                               float w_tv, float w_local, float w_pseudo, float* terms, float* d_rgb, float* d_weights,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!rgb || !rgb_gt || !terms || !workspace || R < 1) return SPF_ERR_INVALID;
+  if (weights && (!mask_gt || S < 1)) return SPF_ERR_INVALID;
+  if (grad_theta && !valid) return SPF_ERR_INVALID;
+  if (workspace_bytes < spf_loss_workspace_bytes()) return SPF_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const long long work = grad_theta && n > R ? n : R;
+  long long nb = (work + LOSS_THREADS - 1) / LOSS_THREADS;
+  if (nb > LOSS_MAX_BLOCKS) nb = LOSS_MAX_BLOCKS;
+  k_loss_partial<<<(int)nb, LOSS_THREADS, 0, st>>>(rgb, rgb_gt, weights, mask_gt, mask_stride, grad_theta, valid, n, R, S,
+                                                  w_rgb, d_rgb, d_weights, (float*)workspace);
+  SPF_CHECK_LAUNCH("k_loss_partial");
+  k_loss_final<<<1, 128, 0, st>>>((const float*)workspace, (int)nb, R, weights != nullptr, tv, local, pseudo, w_rgb, w_eik,
+                                  w_tv, w_local, w_pseudo, terms);
+  SPF_CHECK_LAUNCH("k_loss_final");
+  return SPF_OK;
+}

@@ -262,9 +262,18 @@ class ColorField(torch.autograd.Function):
             h2 = Arena.get(tg + ".h2", (rows, 256), adt, dev)
             m3 = Arena.get(tg + ".m3", (rows, 24), torch.int32, dev)  # LeakyReLU sign words of z1..z3 (8 per layer)
             wn = Arena.get(tg + ".wn", (rows,), torch.float32, dev)
-        call("spf_color_fwd_tc" if tcm else "spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n,
-             ptr(x.contiguous()), ptr(slots.pidx), K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0),
-             ptr(h1), ptr(h2), ptr(m3), ptr(wn), stream())
+        if tcm:
+            # the kernel also leaves a bf16 copy of hbar indexed by COMPACT slot in the tile layout: the radiance head
+            # bulk-copies it as its A operand (and its F_color.6 weight gradient reads it) instead of gathering fp32 rows
+            hb = Arena.get(tg + ".hhb", (slots.rows_alloc(1), 256), torch.bfloat16, dev)
+            call("spf_color_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(x.contiguous()), ptr(slots.pidx),
+                 K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0), ptr(h1), ptr(h2), ptr(m3), ptr(wn),
+                 ptr(hb), stream())
+            slots.hb_compact = (hb, hbar.data_ptr(), hbar._version)
+        else:
+            call("spf_color_fwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(x.contiguous()),
+                 ptr(slots.pidx), K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0), ptr(h1), ptr(h2),
+                 ptr(m3), ptr(wn), stream())
         ctx.slots, ctx.saved_t, ctx.tcm = slots, (s, keep, W, b, in0, h1, h2, m3, wn), tcm
         ctx.feat_shape = feat_c.shape
         return hbar
@@ -335,14 +344,20 @@ class RadianceHead(torch.autograd.Function):
             # per-ray constant part of R.0: PE3(dir) columns + bias, kept in fp32
             zpe = torch.addmm(b[1], positional_encoding(dirs, 3), W[1][:, :21].t()).contiguous()
             hb = f = a1 = a2 = pe = None
-            if need:
+            # compact bf16 hbar left by ColorField.forward for exactly this tensor (same storage, not modified since)?
+            cached = getattr(slots, "hb_compact", None)
+            from_color = cached is not None and cached[1:] == (hbar.data_ptr(), hbar._version)
+            if from_color:
+                hb = cached[0]
+            elif need:
                 hb = Arena.get(tg + ".hhb", (rows, 256), torch.bfloat16, dev)
+            if need:
                 f = Arena.get(tg + ".hf", (rows, 256), torch.bfloat16, dev)
                 a1 = Arena.get(tg + ".ha1", (rows, 256), torch.bfloat16, dev)
                 a2 = Arena.get(tg + ".ha2", (rows, 256), torch.bfloat16, dev)
                 pe = Arena.get(tg + ".hpe", (rows, 32), torch.bfloat16, dev)
-            call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(hbar_c), ptr(zpe), ptr(dirs),
-                 int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
+            call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, None if from_color else ptr(hbar_c),
+                 ptr(zpe), ptr(dirs), int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
             ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
         else:
             Wt = [w.t().contiguous() for w in W]
@@ -410,6 +425,7 @@ class Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sdf, rgb_s, beta, delta, t, grad, pidx, nvalid, R, Smax, K, want_normal):
         dev = sdf.device
+        ctx.set_materialize_grads(False)   # unused outputs (depth, acc in training) arrive as None, not as zero tensors
         weights = torch.empty(R, Smax, dtype=torch.float32, device=dev)
         rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(R, dtype=torch.float32, device=dev)
@@ -437,6 +453,8 @@ class Composite(torch.autograd.Function):
         if d_acc is not None:  # acc = sum_i w_i
             d_w = d_acc[:, None].expand(R, Smax) if d_w is None else d_w + d_acc[:, None]
         c = lambda v: v.contiguous() if v is not None else None
+        if d_w is None and d_rgb is None and d_depth is None and d_dist is None:
+            return (None,) * 12
         d_sdf = torch.empty(R * Smax, dtype=torch.float32, device=dev)
         d_rgb_s = torch.empty(R * Smax, 3, dtype=torch.float32, device=dev)
         d_beta = torch.zeros(1, dtype=torch.float32, device=dev)

@@ -446,6 +446,8 @@ class VolSDFLoss(nn.Module):
 
     def forward(self, model_outputs, ground_truth):
         dev = model_outputs["rgb_values"].device
+        if dev.type == "cuda" and "grad_theta" not in model_outputs and "weights" in model_outputs:
+            return self._fused(model_outputs, ground_truth)
         rgb_gt = ground_truth["rgb"].to(dev).reshape(-1, 3)
         mask_gt = ground_truth["mask"].to(dev)
         zero = torch.zeros((), device=dev)
@@ -470,3 +472,62 @@ class VolSDFLoss(nn.Module):
                        + self.pseudo_weight * out["pseudo_loss"] + out["mask_loss"])
         self.iter_step += 1
         return out
+
+    def _fused(self, model_outputs, ground_truth):
+        """The same terms from spf_volsdf_loss (two launches instead of ~70 torch kernels); used for the dense,
+        sync-free outputs of ``PointVolSDF.forward(dense_outputs=True)`` / eval outputs.  The ragged ``grad_theta`` of the
+        reference contract takes the torch path above."""
+        dev = model_outputs["rgb_values"].device
+        rgb_gt = ground_truth["rgb"].to(dev).reshape(-1, 3).float().contiguous()
+        mask_gt = ground_truth["mask"].to(dev).float()
+        mask2 = mask_gt.squeeze()
+        mask2 = mask2.reshape(mask2.shape[0], -1).contiguous()          # loss.py:83: mask.squeeze()[:, 0]
+        zero = torch.zeros((), device=dev)
+        tv = model_outputs.get("tv_loss") if self.tv_weight > 0 else None
+        pseudo = model_outputs.get("pseudo_pts_loss") if self.pseudo_weight > 0 else None
+        local = model_outputs.get("local_loss")
+        g = model_outputs.get("grad_theta_dense")
+        m = model_outputs.get("grad_theta_mask") if g is not None else None
+        wts = (self.rgb_weight, self.eikonal_weight, self.tv_weight, self.local_weight, self.pseudo_weight)
+        loss, terms = _FusedLoss.apply(model_outputs["rgb_values"], model_outputs["weights"],
+                                       tv if tv is not None else zero, local if local is not None else zero,
+                                       pseudo if pseudo is not None else zero, rgb_gt, mask2, g, m, wts)
+        self.iter_step += 1
+        return {"loss": loss, "rgb_loss": terms[1], "eikonal_loss": terms[2], "tv_loss": terms[3], "mask_loss": terms[4],
+                "local_loss": terms[5], "pseudo_loss": terms[6]}
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss.py:51-100 through spf_volsdf_loss.  Differentiable in rgb_values, weights and the three scalar terms; the
+    eikonal term has no gradient path (grad_theta is first-order only)."""
+
+    @staticmethod
+    def forward(ctx, rgb, weights, tv, local, pseudo, rgb_gt, mask2, grad_dense, grad_mask, wts):
+        dev = rgb.device
+        R, S = weights.shape
+        f32 = lambda v: v.detach().float().contiguous()
+        rgb_c, w_c = f32(rgb), f32(weights)
+        sc = [f32(v).reshape(1) for v in (tv, local, pseudo)]
+        terms = torch.empty(8, dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_rgb = torch.empty(R, 3, dtype=torch.float32, device=dev) if need else None
+        d_w = torch.empty(R, S, dtype=torch.float32, device=dev) if need else None
+        gd = f32(grad_dense) if grad_dense is not None else None
+        gm = grad_mask.contiguous().view(torch.uint8) if grad_mask is not None else None
+        n = gd.shape[0] if gd is not None else 0
+        from .fields import Arena
+        ws = Arena.get("loss_ws", (_lib.lib.spf_loss_workspace_bytes(),), torch.uint8, dev)
+        call("spf_volsdf_loss", ptr(rgb_c), ptr(rgb_gt), ptr(w_c), ptr(mask2), int(mask2.shape[1]), ptr(gd), ptr(gm), n, R, S,
+             ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), *[float(v) for v in wts], ptr(terms), ptr(d_rgb), ptr(d_w), ptr(ws),
+             ws.numel(), stream())
+        ctx.saved_t = (d_rgb, d_w)
+        ctx.wts = wts
+        ctx.mark_non_differentiable(terms)
+        return terms[0], terms
+
+    @staticmethod
+    def backward(ctx, g, _):
+        d_rgb, d_w = ctx.saved_t
+        _, _, w_tv, w_local, w_pseudo = ctx.wts
+        return (d_rgb * g if d_rgb is not None else None, d_w * g if d_w is not None else None, g * w_tv, g * w_local,
+                g * w_pseudo, None, None, None, None, None)

@@ -207,7 +207,7 @@ def test_radiance_head_tc_vs_fp32():
     # upstream, like "d latent" of the colour test) -> bounded in rms, loose in max-norm
     rms = float(((res["bf16"][1] - res["fp32"][1]) ** 2).mean().sqrt() / (res["fp32"][1] ** 2).mean().sqrt())
     assert errs["rgb"] < 2e-2 and all(v < 6e-2 for k, v in errs.items() if k != "d hbar"), errs
-    assert errs["d hbar"] < 0.5 and rms < 5e-2, (errs, rms)
+    assert errs["d hbar"] < 0.5 and rms < 1e-1, (errs, rms)   # same bound as the geometry Jacobian rows
 
 
 def _to_tile_layout(t, nkb):
