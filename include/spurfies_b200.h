@@ -337,6 +337,16 @@ int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int
  * out holds ceil(K/64) * n_pad * 128 bytes. */
 int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
                    void* stream);
+/* the same for up to SPF_PACK_MAX_JOBS images in one launch (the trainable weights are re-packed every step) */
+#define SPF_PACK_MAX_JOBS 16
+typedef struct {
+  const float* W; void* out;
+  int32_t ld, N, K, transpose, n_pad, reserved;
+} spf_pack_job;
+int spf_pack_sw128_batch(const spf_pack_job* jobs /* HOST array */, int32_t n_jobs, void* stream);
+/* zpe [R,256] = PE3(ray_dirs) @ W[:, :21]^T + bias with W = R.0.weight (row stride ld >= 21), bias = R.0.bias [256] */
+int spf_head_zpe(const float* ray_dirs /*[R,3]*/, const float* W, int32_t ld, const float* bias, int32_t R, float* zpe,
+                 void* stream);
 /* weight gradient of one linear layer: dW[256][N] += dZ^T @ A, db[256] += colsum(dZ) (both accumulated in fp32), over
  * the first ceil(count * rows_per_unit / 128) * 128 rows of dZ [.,256] / A [.,lda] (bf16): exactly the rows the dgrad
  * kernels write.  N multiple of 16, <= 256.  layout bit 0 / bit 1: dZ / A is stored in the tile layout written by the

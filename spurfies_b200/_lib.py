@@ -57,6 +57,11 @@ class HeadWeightsTC(C.Structure):
                 ("b4", C.c_void_p), ("rb2", C.c_void_p), ("rb3", C.c_void_p)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("out", C.c_void_p), ("ld", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("transpose", C.c_int32), ("n_pad", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ColorWeightsF32(C.Structure):
     _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
                 ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p)]
@@ -120,6 +125,8 @@ _SIGS = {
     "spf_head_fwd_tc": [_P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_pack_sw128": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "spf_pack_sw128_batch": [_P, _I, _P],
+    "spf_head_zpe": [_P, _P, _I, _P, _I, _P, _P],
     "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }

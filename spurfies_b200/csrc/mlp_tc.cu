@@ -288,6 +288,73 @@ extern "C" int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, 
   return SPF_OK;
 }
 
+// all weight images of a step in ONE launch (the trainable weights change every step): blockIdx.y = job
+struct PackJobsDev { spf_pack_job j[SPF_PACK_MAX_JOBS]; };
+__global__ void k_pack_sw128_batch(PackJobsDev jobs) {
+  const spf_pack_job& J = jobs.j[blockIdx.y];
+  const int nkb = (J.K + 63) / 64;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkb * J.n_pad * 8) return;
+  const int cs = i & 7, n = (i >> 3) % J.n_pad, kb = i / (8 * J.n_pad);
+  const int c = cs ^ (n & 7);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kb * 64 + c * 8 + e;
+    v[e] = (n < J.N && k < J.K) ? (J.transpose ? J.W[(size_t)k * J.ld + n] : J.W[(size_t)n * J.ld + k]) : 0.0f;
+  }
+  reinterpret_cast<uint4*>(J.out)[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+extern "C" int spf_pack_sw128_batch(const spf_pack_job* jobs, int32_t n_jobs, void* stream_) {
+  if (!jobs || n_jobs < 1 || n_jobs > SPF_PACK_MAX_JOBS) return SPF_ERR_INVALID;
+  PackJobsDev d;
+  int max_total = 0;
+  for (int q = 0; q < n_jobs; ++q) {
+    const spf_pack_job& J = jobs[q];
+    if (!J.W || !J.out || J.N < 1 || J.K < 1 || J.n_pad < J.N || J.n_pad % 8) return SPF_ERR_INVALID;
+    d.j[q] = J;
+    const int total = ((J.K + 63) / 64) * J.n_pad * 8;
+    if (total > max_total) max_total = total;
+  }
+  dim3 grid((max_total + 255) / 256, n_jobs);
+  k_pack_sw128_batch<<<grid, 256, 0, (cudaStream_t)stream_>>>(d);
+  SPF_CHECK_LAUNCH("k_pack_sw128_batch");
+  return SPF_OK;
+}
+
+// per-ray constant part of R.0 (pointneus_disent.py:100-107, embedder.py:10-36): zpe[r] = R.0.weight[:, :21] PE3(dir_r) + R.0.bias.
+// One block per ray, thread = output unit.
+__global__ void __launch_bounds__(256) k_head_zpe(const float* __restrict__ dirs, const float* __restrict__ W, int ld,
+                                                  const float* __restrict__ bias, float* __restrict__ zpe) {
+  __shared__ float pe[21];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  if (tid < 21) {
+    float v;
+    if (tid < 3) v = dirs[3 * r + tid];
+    else {
+      const int l = (tid - 3) / 6, rem = (tid - 3) % 6, a = rem % 3;
+      const float arg = dirs[3 * r + a] * (float)(1 << l);
+      v = rem < 3 ? sinf(arg) : cosf(arg);
+    }
+    pe[tid] = v;
+  }
+  __syncthreads();
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 21; ++j) acc = fmaf(pe[j], W[(size_t)tid * ld + j], acc);
+  zpe[(size_t)r * 256 + tid] = acc + bias[tid];
+}
+
+extern "C" int spf_head_zpe(const float* dirs, const float* W, int32_t ld, const float* bias, int32_t R, float* zpe,
+                            void* stream_) {
+  if (!dirs || !W || !bias || !zpe || ld < 21) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  k_head_zpe<<<R, 256, 0, (cudaStream_t)stream_>>>(dirs, W, ld, bias, zpe);
+  SPF_CHECK_LAUNCH("k_head_zpe");
+  return SPF_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // building-block self test: out[128][N] = A[128][K] (bf16 row-major, K multiple of 16, <= 256) @ Wp^T, where Wp is
 // the packed (k-block major, SW128) image of W [N][K].  Exercises: generic-proxy writes of the A tile in the

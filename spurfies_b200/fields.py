@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import (ColorWeightsF32, ColorWeightsTC, GeoWeightsF32, GeoWeightsTC, HeadWeightsF32, HeadWeightsTC, call, ptr,
                    stream)
-from .packing import image_bytes, pack_sw128, pack_sw128_dev
+from .packing import image_bytes, pack_flush, pack_sw128, pack_sw128_dev
 
 K_NEIGH = 8
 ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
@@ -197,31 +197,54 @@ def _img(name, dev, nbytes):
 
 def _color_struct_tc(W, b):
     """bf16 weight images for k_color_fwd_tc / k_color_bwd_tc (input columns permuted to [c (64) | PE6 (39)]),
-    packed on the device by spf_pack_sw128 (six launches) into persistent buffers."""
+    packed on the device by one spf_pack_sw128_batch launch into persistent buffers."""
     dev = W[0].device
+    jobs = []
     w1p = _img("c.w1p", dev, 65536)
-    pack_sw128_dev(w1p, W[0], 256, 64, col_off=39)                       # k-block 0: latent columns
-    pack_sw128_dev(w1p, W[0], 256, 39, col_off=0, row_off_bytes=32768)   # k-block 1: PE6 columns
+    pack_sw128_dev(w1p, W[0], 256, 64, col_off=39, batch=jobs)                       # k-block 0: latent columns
+    pack_sw128_dev(w1p, W[0], 256, 39, col_off=0, row_off_bytes=32768, batch=jobs)   # k-block 1: PE6 columns
     imgs = [w1p]
     for nm, w, tr in (("c.w2p", W[1], False), ("c.w3p", W[2], False), ("c.w3tp", W[2], True), ("c.w2tp", W[1], True)):
         im = _img(nm, dev, 131072)
-        pack_sw128_dev(im, w, 256, 256, transpose=tr)
+        pack_sw128_dev(im, w, 256, 256, transpose=tr, batch=jobs)
         imgs.append(im)
     w1ftp = _img("c.w1ftp", dev, 32768)
-    pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39)     # (W1[:, 39:103])^T : [64][256]
+    pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39, batch=jobs)     # (W1[:, 39:103])^T : [64][256]
     imgs.append(w1ftp)
+    pack_flush(jobs)   # one launch
     s = ColorWeightsTC()
     s.w1p, s.w2p, s.w3p, s.w3tp, s.w2tp, s.w1ftp = (i.data_ptr() for i in imgs)
     s.b1, s.b2, s.b3 = (v.data_ptr() for v in b)
     return s, imgs
 
 
-def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True, layout=0):
+class _ZeroPool:
+    """One zero-filled fp32 buffer per backward call, handed out in 16-byte aligned pieces (the split-K weight-gradient
+    kernel accumulates with atomics, so its outputs start at zero: one fill instead of one per tensor)."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        out = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4
+        assert self.off <= self.buf.numel()
+        return out
+
+
+def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True, layout=0, pool: Optional[_ZeroPool] = None):
     """dW [256,N], db [256] (fp32) = spf_wgrad_tc over the rows the dgrad kernel wrote; no host sync.
     layout bit 0 / 1: dz / act is in the colour kernels' tile layout (include/spurfies_b200.h)."""
     dev = dz.device
-    dW = torch.zeros(256, N, dtype=torch.float32, device=dev)
-    db = torch.zeros(256, dtype=torch.float32, device=dev) if want_db else None
+    if pool is not None:
+        dW, db = pool.take(256, N), (pool.take(256) if want_db else None)
+    else:
+        dW = torch.zeros(256, N, dtype=torch.float32, device=dev)
+        db = torch.zeros(256, dtype=torch.float32, device=dev) if want_db else None
     call("spf_wgrad_tc", ptr(dz), ptr(act), int(lda), int(N), ptr(slots.count), int(rows_per_unit), slots.n, int(layout), ptr(dW),
          ptr(db),
          stream())
@@ -294,9 +317,10 @@ class ColorField(torch.autograd.Function):
              ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
              ptr(dz3), ptr(gfeat), stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
-            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K, layout=3)
-            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K, layout=3)
-            dW1p, db1 = _wgrad_tc(dz1, in0, 128, 112, slots, slots.K, layout=3)
+            pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
+            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K, layout=3, pool=pool)
+            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K, layout=3, pool=pool)
+            dW1p, db1 = _wgrad_tc(dz1, in0, 128, 112, slots, slots.K, layout=3, pool=pool)
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
         else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
             r = slots.V * slots.K
@@ -330,19 +354,21 @@ class RadianceHead(torch.autograd.Function):
         need = any(ctx.needs_input_grad[:9])
         hbar_c = hbar.detach().contiguous()
         if tcm:
-            imgs = []
+            imgs, jobs = [], []
             for nm, w, N_, K_, tr, npad, co in (("h.w4p", W[0], 256, 256, False, 256, 0), ("h.r1fp", W[1], 256, 256, False, 256, 21),
                                                ("h.r2p", W[2], 256, 256, False, 256, 0), ("h.r3p", W[3], 3, 256, False, 32, 0),
                                                ("h.r3tp", W[3], 256, 3, True, 256, 0), ("h.r2tp", W[2], 256, 256, True, 256, 0),
                                                ("h.r1ftp", W[1], 256, 256, True, 256, 21), ("h.w4tp", W[0], 256, 256, True, 256, 0)):
                 im = _img(nm, dev, image_bytes(npad, K_))
-                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co)
+                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co, batch=jobs)
                 imgs.append(im)
+            pack_flush(jobs)
             s = HeadWeightsTC()
             s.w4p, s.r1fp, s.r2p, s.r3p, s.r3tp, s.r2tp, s.r1ftp, s.w4tp = (i.data_ptr() for i in imgs)
             s.b4, s.rb2, s.rb3 = b[0].data_ptr(), b[2].data_ptr(), b[3].data_ptr()
             # per-ray constant part of R.0: PE3(dir) columns + bias, kept in fp32
-            zpe = torch.addmm(b[1], positional_encoding(dirs, 3), W[1][:, :21].t()).contiguous()
+            zpe = Arena.get(tg + ".zpe", (dirs.shape[0], 256), torch.float32, dev)
+            call("spf_head_zpe", ptr(dirs), ptr(W[1]), int(W[1].stride(0)), ptr(b[1]), int(dirs.shape[0]), ptr(zpe), stream())
             hb = f = a1 = a2 = pe = None
             # compact bf16 hbar left by ColorField.forward for exactly this tensor (same storage, not modified since)?
             cached = getattr(slots, "hb_compact", None)
@@ -393,16 +419,17 @@ class RadianceHead(torch.autograd.Function):
         if tcm:
             hb, pe = hb
             dz3 = Arena.get(tg + ".hdz3b", (rows, 16), torch.bfloat16, dev)
-            drb3 = torch.zeros(3, dtype=torch.float32, device=dev)
+            pool = _ZeroPool(3 * 256 * 256 + 256 * 32 + 256 * 16 + 3 * 256 + 4, dev)
+            drb3 = pool.take(3)
             call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
                  ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), ptr(drb3), stream())
             # hb, f, a1, a2 and dzf, dz1, dz2 are in the tile layout (layout bits), pe and dz3 row-major
-            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1, layout=3)
-            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1, layout=3)
-            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False, layout=1)
+            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1, layout=3, pool=pool)
+            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1, layout=3, pool=pool)
+            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False, layout=1, pool=pool)
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
-            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1, layout=3)
-            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False, layout=1)   # (a2^T @ dz3) = dR3^T, [256,16]
+            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1, layout=3, pool=pool)
+            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False, layout=1, pool=pool)   # (a2^T @ dz3) = dR3^T, [256,16]
             dR3 = dR3t[:, :3].t().contiguous()
             return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)

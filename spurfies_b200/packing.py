@@ -28,17 +28,35 @@ def pack_sw128(W: torch.Tensor, n_pad: int | None = None) -> torch.Tensor:
 
 
 def pack_sw128_dev(out: torch.Tensor, W: torch.Tensor, N: int, K: int, transpose: bool = False, n_pad: int | None = None,
-                   col_off: int = 0, row_off_bytes: int = 0) -> None:
+                   col_off: int = 0, row_off_bytes: int = 0, batch: list | None = None) -> None:
     """Kernel version (spf_pack_sw128) for per-step packing of trainable weights: writes the image of
     W[:, col_off:col_off+K] ([N, K]) -- or, with transpose, of W[:, col_off:col_off+N]^T where W is [K, .] -- into the
-    uint8 buffer `out` starting at byte `row_off_bytes`.  W must be fp32, CUDA, with unit column stride."""
+    uint8 buffer `out` starting at byte `row_off_bytes`.  W must be fp32, CUDA, with unit column stride.  With `batch`
+    (a list) the job is only recorded; ``pack_flush(batch)`` then packs all recorded images in one launch."""
     import ctypes as C
     from . import _lib
     assert W.dtype == torch.float32 and W.is_cuda and W.stride(1) == 1
     n_pad = n_pad or N
+    if batch is not None:   # collected; one launch for all of them in pack_flush
+        batch.append((W.data_ptr() + 4 * col_off, out.data_ptr() + row_off_bytes, int(W.stride(0)), int(N), int(K),
+                      int(bool(transpose)), int(n_pad), W))
+        return
     src = C.c_void_p(W.data_ptr() + 4 * col_off)
     dst = C.c_void_p(out.data_ptr() + row_off_bytes)
     _lib.call("spf_pack_sw128", src, int(W.stride(0)), int(N), int(K), int(bool(transpose)), int(n_pad), dst, _lib.stream())
+
+
+def pack_flush(batch: list) -> None:
+    """One spf_pack_sw128_batch launch for the jobs collected by ``pack_sw128_dev(..., batch=batch)``."""
+    import ctypes as C
+    from . import _lib
+    for i in range(0, len(batch), 16):
+        part = batch[i:i + 16]
+        arr = (_lib.PackJob * len(part))()
+        for j, (src, dst, ld, N, K, tr, n_pad, _keep) in enumerate(part):
+            arr[j].W, arr[j].out, arr[j].ld, arr[j].N, arr[j].K, arr[j].transpose, arr[j].n_pad = src, dst, ld, N, K, tr, n_pad
+        _lib.call("spf_pack_sw128_batch", C.cast(arr, C.c_void_p), len(part), _lib.stream())
+    batch.clear()
 
 
 def image_bytes(N_pad: int, K: int) -> int:
