@@ -311,6 +311,7 @@ int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const i
 int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                      const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
+                     const void* d_hb /* optional: d_hbar as bf16 by COMPACT slot, tile layout (then d_hbar may be NULL) */,
                      void* stream);
 typedef struct {
   const uint8_t* w4p;    /* pack(F_color.6.weight) */
@@ -332,7 +333,9 @@ int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int
  * drb3 [3] (fp32) is accumulated in-kernel */
 int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
-                    void* dz1, void* dz2, void* dz3, float* drb3, void* stream);
+                    void* dz1, void* dz2, void* dz3, float* drb3,
+                    void* d_hb /* optional out: d_hbar as bf16 by compact sample row, tile layout, INSTEAD of d_hbar */,
+                    void* stream);
 /* bf16 128B-swizzled k-block-major image of W [N][K] (row stride ld, fp32) or of its transpose (then W is [K][N]);
  * out holds ceil(K/64) * n_pad * 128 bytes. */
 int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,

@@ -324,33 +324,49 @@ extern "C" int spf_pack_sw128_batch(const spf_pack_job* jobs, int32_t n_jobs, vo
 }
 
 // per-ray constant part of R.0 (pointneus_disent.py:100-107, embedder.py:10-36): zpe[r] = R.0.weight[:, :21] PE3(dir_r) + R.0.bias.
-// One block per ray, thread = output unit.
+// A block stages the 256 x 21 weight slice in shared memory once (transposed: conflict-free reads) and walks ZPE_RAYS
+// rays; thread = output unit.
+#define ZPE_RAYS 16
 __global__ void __launch_bounds__(256) k_head_zpe(const float* __restrict__ dirs, const float* __restrict__ W, int ld,
-                                                  const float* __restrict__ bias, float* __restrict__ zpe) {
-  __shared__ float pe[21];
-  const int r = blockIdx.x, tid = threadIdx.x;
-  if (tid < 21) {
-    float v;
-    if (tid < 3) v = dirs[3 * r + tid];
-    else {
-      const int l = (tid - 3) / 6, rem = (tid - 3) % 6, a = rem % 3;
-      const float arg = dirs[3 * r + a] * (float)(1 << l);
-      v = rem < 3 ? sinf(arg) : cosf(arg);
+                                                  const float* __restrict__ bias, int R, float* __restrict__ zpe) {
+  __shared__ float Ws[21 * 256];
+  __shared__ float pe[ZPE_RAYS][24];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 256 * 21; e += 256) {
+    const int row = e / 21, j = e - row * 21;
+    Ws[j * 256 + row] = W[(size_t)row * ld + j];
+  }
+  const int r0 = blockIdx.x * ZPE_RAYS;
+  for (int e = tid; e < ZPE_RAYS * 21; e += 256) {
+    const int q = e / 21, k = e - q * 21, r = r0 + q;
+    float v = 0.0f;
+    if (r < R) {
+      if (k < 3) v = dirs[3 * r + k];
+      else {
+        const int l = (k - 3) / 6, rem = (k - 3) % 6, a = rem % 3;
+        const float arg = dirs[3 * r + a] * (float)(1 << l);
+        v = rem < 3 ? sinf(arg) : cosf(arg);
+      }
     }
-    pe[tid] = v;
+    pe[q][k] = v;
   }
   __syncthreads();
-  float acc = 0.0f;
+  const float bv = bias[tid];
+#pragma unroll 4
+  for (int q = 0; q < ZPE_RAYS; ++q) {
+    if (r0 + q >= R) break;
+    float acc = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 21; ++j) acc = fmaf(pe[j], W[(size_t)tid * ld + j], acc);
-  zpe[(size_t)r * 256 + tid] = acc + bias[tid];
+    for (int j = 0; j < 21; ++j) acc = fmaf(pe[q][j], Ws[j * 256 + tid], acc);
+    zpe[(size_t)(r0 + q) * 256 + tid] = acc + bv;
+  }
 }
 
 extern "C" int spf_head_zpe(const float* dirs, const float* W, int32_t ld, const float* bias, int32_t R, float* zpe,
                             void* stream_) {
   if (!dirs || !W || !bias || !zpe || ld < 21) return SPF_ERR_INVALID;
   if (R <= 0) return SPF_OK;
-  k_head_zpe<<<R, 256, 0, (cudaStream_t)stream_>>>(dirs, W, ld, bias, zpe);
+  k_head_zpe<<<(R + ZPE_RAYS - 1) / ZPE_RAYS, 256, 0, (cudaStream_t)stream_>>>(dirs, W, ld, bias, R, zpe);
   SPF_CHECK_LAUNCH("k_head_zpe");
   return SPF_OK;
 }

@@ -519,7 +519,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
                 const int* __restrict__ pidx, const float* __restrict__ d_hbar, const uint32_t* __restrict__ msign,
                 const float* __restrict__ wn_in, __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2,
-                __nv_bfloat16* __restrict__ dz3, float* __restrict__ gfeat) {
+                __nv_bfloat16* __restrict__ dz3, float* __restrict__ gfeat, const uint8_t* __restrict__ d_hb_c) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = carve_bars(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -563,13 +563,31 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
         if (sl >= 0) mw = *reinterpret_cast<const uint4*>(msign + grow * M_STRIDE + 16 + half * 4);
         const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
         const float4* src = reinterpret_cast<const float4*>(d_hbar + (size_t)(sl >= 0 ? sl : 0) * 256 + half * 128);
+        // compact mode: row li of the radiance head's bf16 tile-layout gradient (the 8 rows of a slot read the same line)
+        const uint8_t* srcc = d_hb_c + (size_t)(li >> 7) * (4 * 16384);
+        const int hrow = li & 127;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float vv[16];
+          if (d_hb_c) {
+            const int c0 = half * 128 + c * 16;
+            uint4 a[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (sl >= 0) {
+              a[0] = *reinterpret_cast<const uint4*>(srcc + (c0 >> 6) * 16384 + sw128_off(hrow, (c0 & 63) >> 3));
+              a[1] = *reinterpret_cast<const uint4*>(srcc + (c0 >> 6) * 16384 + sw128_off(hrow, ((c0 & 63) >> 3) + 1));
+            }
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(a);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 d = sl >= 0 ? src[c * 4 + q] : make_float4(0, 0, 0, 0);
-            vv[4 * q] = d.x; vv[4 * q + 1] = d.y; vv[4 * q + 2] = d.z; vv[4 * q + 3] = d.w;
+            for (int i = 0; i < 8; ++i) {
+              vv[2 * i] = __uint_as_float(w32[i] << 16);
+              vv[2 * i + 1] = __uint_as_float(w32[i] & 0xffff0000u);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 d = sl >= 0 ? src[c * 4 + q] : make_float4(0, 0, 0, 0);
+              vv[4 * q] = d.x; vv[4 * q + 1] = d.y; vv[4 * q + 2] = d.z; vv[4 * q + 3] = d.w;
+            }
           }
           const uint32_t sb = (c & 1) ? (mwa[c >> 1] << 1) : mwa[c >> 1];
           uint32_t pk[8];
@@ -644,13 +662,15 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
 extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                 const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                                 const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
-                                void* stream_) {
-  if (!W || !list || !count || !pidx || !d_hbar || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad) return SPF_ERR_INVALID;
+                                const void* d_hb, void* stream_) {
+  if (!W || !list || !count || !pidx || (!d_hbar && !d_hb) || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad)
+    return SPF_ERR_INVALID;
   if (K != 8) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_color_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "colorb_tc2 attr");
   k_color_bwd_tc2<<<pair_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
-      *W, list, count, pidx, d_hbar, m3, wn, (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, feat_c_grad);
+      *W, list, count, pidx, d_hbar, m3, wn, (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, feat_c_grad,
+      (const uint8_t*)d_hb);
   SPF_CHECK_LAUNCH("k_color_bwd_tc2");
   return SPF_OK;
 }
@@ -876,7 +896,7 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
                const float* __restrict__ d_rgb, const float* __restrict__ rgb, const uint8_t* __restrict__ a1_s,
                const uint8_t* __restrict__ a2_s, float* __restrict__ d_hbar, __nv_bfloat16* __restrict__ dzf,
                __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
-               float* __restrict__ drb3) {
+               float* __restrict__ drb3, __nv_bfloat16* __restrict__ d_hb_c) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = carve_bars(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -986,9 +1006,10 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         }
         signal_a_ready(B, t, rank, tile_ok ? dzo + (size_t)tile * (4 * 8192) : nullptr, sA, 4 * 16384);
       }
-      // d_hbar[slot] = dzf @ F_color.6 (fp32, consumed by the colour-field backward at valid slots)
+      // d_hbar = dzf @ F_color.6, consumed by the colour-field backward at valid slots: fp32 by slot, or (d_hb_c) bf16 by
+      // COMPACT sample row in the tile layout -- one coalesced 64 KB bulk store per tile instead of 512-byte strided rows
       wait_acc(B, t, acc_par);
-      drain_store(t);   // the next iteration's prologue overwrites the A tile
+      drain_store(t);
       {
         float v[2][16];
         tmem_ld16(t_acc, v[0]);
@@ -998,13 +1019,29 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           tmem_ld_wait();
           if (c < 7) tmem_ld16(t_acc + (c + 1) * 16, v[(c + 1) & 1]);
           const float* vv = v[c & 1];
-          if (slot >= 0) {
+          if (d_hb_c) {
+            const int c0 = half * 128 + c * 16;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(vv[2 * i], vv[2 * i + 1]);
+            uint8_t* dstA = sA + (c0 >> 6) * 16384;
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else if (slot >= 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[c * 4 + q] = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
           }
         }
       }
       tc_fence_before();
+      if (d_hb_c) {
+        fence_proxy_async();
+        epi_bar(t);
+        if ((tid & (EPI_THREADS - 1)) == 0) {
+          if (tile_ok) { bulk_s2g(d_hb_c + (size_t)tile * (4 * 8192), sA, 4 * 16384); bulk_commit(); }
+          bulk_wait_read0();   // the next iteration's prologue overwrites the A tile
+        }
+      }
       epi_bar(t);
     }
   }
@@ -1013,14 +1050,14 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
 
 extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar,
-                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* stream_) {
-  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || !d_hbar || !dzf || !dz1 || !dz2 || !dz3)
+                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* d_hb, void* stream_) {
+  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || (!d_hbar && !d_hb) || !dzf || !dz1 || !dz2 || !dz3)
     return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_head_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "headb_tc2 attr");
   k_head_bwd_tc2<<<sample_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
       *W, list, count, d_rgb, rgb, (const uint8_t*)a1, (const uint8_t*)a2, d_hbar, (__nv_bfloat16*)dzf,
-      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3);
+      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3, (__nv_bfloat16*)d_hb);
   SPF_CHECK_LAUNCH("k_head_bwd_tc2");
   return SPF_OK;
 }

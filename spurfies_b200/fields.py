@@ -313,9 +313,19 @@ class ColorField(torch.autograd.Function):
         dz2 = Arena.get(tg + ".dz2", (rows, 256), adt, dev)
         dz3 = Arena.get(tg + ".dz3", (rows, 256), adt, dev)
         gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
-        call("spf_color_bwd_tc" if tcm else "spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n,
-             ptr(slots.pidx), slots.K, ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
-             ptr(dz3), ptr(gfeat), stream())
+        if tcm:
+            # the radiance head may have left its gradient as bf16 by compact sample row in the tile layout (see
+            # RadianceHead.backward); `d_hbar` is then only the placeholder autograd carried here
+            cached = getattr(slots, "d_hb_compact", None)
+            compact = cached is not None and cached[1] == d_hbar.data_ptr()
+            call("spf_color_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
+                 None if compact else ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
+                 ptr(dz3), ptr(gfeat), ptr(cached[0]) if compact else None, stream())
+            slots.d_hb_compact = None
+        else:
+            call("spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
+                 ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2), ptr(dz3), ptr(gfeat),
+                 stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
             pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
             dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K, layout=3, pool=pool)
@@ -385,6 +395,7 @@ class RadianceHead(torch.autograd.Function):
             call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, None if from_color else ptr(hbar_c),
                  ptr(zpe), ptr(dirs), int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
             ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
+            ctx.from_color = from_color
         else:
             Wt = [w.t().contiguous() for w in W]
             s = HeadWeightsF32()
@@ -421,8 +432,16 @@ class RadianceHead(torch.autograd.Function):
             dz3 = Arena.get(tg + ".hdz3b", (rows, 16), torch.bfloat16, dev)
             pool = _ZeroPool(3 * 256 * 256 + 256 * 32 + 256 * 16 + 3 * 256 + 4, dev)
             drb3 = pool.take(3)
+            # `slots.single_consumer` (set by PointVolSDF.forward): hbar feeds nothing but this head, so its gradient can
+            # travel to ColorField.backward as bf16 by compact sample row in the tile layout (one coalesced bulk store per
+            # tile here, half the bytes there); the fp32 `d_hbar` returned to autograd is then an unwritten placeholder
+            d_hbc = None
+            if ctx.from_color and getattr(slots, "single_consumer", False):
+                d_hbc = Arena.get(tg + ".d_hbc", (rows, 256), torch.bfloat16, dev)
+                slots.d_hb_compact = (d_hbc, d_hbar.data_ptr())
             call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
-                 ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), ptr(drb3), stream())
+                 ptr(a1), ptr(a2), None if d_hbc is not None else ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3),
+                 ptr(drb3), ptr(d_hbc), stream())
             # hb, f, a1, a2 and dzf, dz1, dz2 are in the tile layout (layout bits), pe and dz3 row-major
             dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1, layout=3, pool=pool)
             dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1, layout=3, pool=pool)

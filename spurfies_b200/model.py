@@ -378,6 +378,7 @@ class PointVolSDF(nn.Module):
         rl = [m for m in self.R if isinstance(m, nn.Linear)]
         hbar = ColorField.apply(self.neural_feats_color, fc[0].weight, fc[0].bias, fc[1].weight, fc[1].bias,
                                 fc[2].weight, fc[2].bias, xs, slots, self.neural_pts, self.conf.rbf)
+        slots.single_consumer = True   # hbar feeds only the radiance head: its gradient may travel in compact bf16 form
         rgb_s = RadianceHead.apply(hbar, fc[3].weight, fc[3].bias, rl[0].weight, rl[0].bias, rl[1].weight, rl[1].bias,
                                    rl[2].weight, rl[2].bias, ray_dirs, slots, S)
         beta = self.density.get_beta()
