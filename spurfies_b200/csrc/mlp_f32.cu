@@ -240,20 +240,36 @@ extern "C" int spf_sdf_fwd_f32(const spf_geo_weights_f32* W, const int32_t* list
   return SPF_OK;
 }
 
-// backward of the geometry field: feat_g_grad[p][:] += d_sdf[slot] * jw[row][:]   (one warp per pair row,
-// one lane per latent channel -> each row is a single coalesced 128-byte reduction)
+// backward of the geometry field: feat_g_grad[p][:] += d_sdf[slot] * jw[row][:].  Eight lanes per pair row (one float4 of
+// the 32 latent channels each, 16-byte vector atomics), four rows per warp and two row groups in flight per iteration: the
+// kernel is bound by the dependent list -> pidx -> jw load chain, so bytes in flight per warp are what matters.
 __global__ void k_sdf_bwd(const int* __restrict__ list, const int* __restrict__ count, const int* __restrict__ pidx,
                           const float* __restrict__ jw, const float* __restrict__ d_sdf, float* __restrict__ gfeat) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
   const long long nrows = (long long)(*count) * 8;
-  const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += wstride) {
-    const int slot = list[row >> 3];
-    const int p = pidx[(size_t)slot * 8 + (row & 7)];
-    if (p < 0) continue;
-    const float g = d_sdf[slot];
-    if (g == 0.0f) continue;
-    atomicAdd(&gfeat[(size_t)p * 32 + lane], g * jw[row * 32 + lane]);
+  const long long wstride = (((long long)gridDim.x * blockDim.x) >> 5) * 8;
+  for (long long r0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8; r0 < nrows; r0 += wstride) {
+    long long row[2];
+    int p[2] = {-1, -1};
+    float g[2] = {0.f, 0.f};
+    float4 j[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      row[u] = r0 + 4 * u + sub;
+      if (row[u] < nrows) {
+        const int slot = list[row[u] >> 3];
+        p[u] = pidx[(size_t)slot * 8 + (row[u] & 7)];
+        g[u] = d_sdf[slot];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (p[u] >= 0 && g[u] != 0.0f) j[u] = reinterpret_cast<const float4*>(jw)[row[u] * 8 + l8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (p[u] >= 0 && g[u] != 0.0f)
+        atomicAdd(reinterpret_cast<float4*>(gfeat + (size_t)p[u] * 32) + l8,
+                  make_float4(g[u] * j[u].x, g[u] * j[u].y, g[u] * j[u].z, g[u] * j[u].w));
   }
 }
 
@@ -262,7 +278,7 @@ extern "C" int spf_sdf_bwd(const int32_t* list, const int32_t* count, int64_t n_
   if (!list || !count || !pidx || !jw || !d_sdf || !feat_g_grad) return SPF_ERR_INVALID;
   if (K != 8) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
-  long long warps = n_max * 8;
+  long long warps = n_max;                 // 8 pair rows (one slot) per warp and iteration
   long long blocks = (warps + 7) / 8;
   long long cap = (long long)spf_num_sms() * 16;
   k_sdf_bwd<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream_>>>(list, count, pidx, jw, d_sdf,
