@@ -217,7 +217,9 @@ __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float q
   if (z0 > z1) return key;
   // (Skipping the cells of the 27 that the radius ball cannot reach was measured and rejected: with cell edge ~ radius
   // only ~20 % of the corner columns can be skipped, and the per-column distance test costs more instructions than the
-  // shorter scan saves: k_knn_slots 0.27 -> 0.32 ms.)
+  // shorter scan saves: k_knn_slots 0.27 -> 0.32 ms.  Likewise rejected: fetching the nine columns' bounds in one round
+  // trip and streaming the chained segments 32 candidates per step with the next step prefetched -- the kernel is
+  // issue-bound on the insertion shuffles (SM pipe 79 % busy), not latency-bound: 0.273 -> 0.307 ms.)
   for (int cx = max(0, fx - L); cx <= min(dx - 1, fx + L); ++cx)
     for (int cy = max(0, fy - L); cy <= min(dy - 1, fy + L); ++cy) {
       const int base = cx * (dy * dz) + cy * dz;
