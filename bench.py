@@ -42,8 +42,8 @@ WORKLOADS = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-# capture of this command (profiles/r01d_ncu_full.md: k_sdf_tc2<1>, 24.2 MB read + 111.0 MB written)
-TRAFFIC_BYTES = {"spf_sdf_fwd_tc": 135.2e6}
+# capture of this command (profiles/r01n_ncu_full.md: k_sdf_tc2<1>, 23.7 MB read + 111.0 MB written)
+TRAFFIC_BYTES = {"spf_sdf_fwd_tc": 134.7e6}
 
 # kernels launched per C-ABI call (for gpu_launches)
 LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3, "spf_grad_sumsq": 2, "spf_adam_step": 2}
@@ -216,7 +216,10 @@ def run_ours(args):
     f0.record()
     last = 0.0
     for i in range(args.steps):
-        losses = one(to_device(hb[(args.warmup + i) % nb], device))
+        h = hb[(args.warmup + i) % nb]
+        # graph replay copies the pinned host tensors straight into its static inputs (one H2D per tensor); the eager
+        # step needs device tensors first
+        losses = one(h if graphed else to_device(h, device))
         last = float(losses["loss"].item())  # D2H of the step's result
     f1.record()
     barrier()
@@ -257,7 +260,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": dom + " (fine pass, fwd + d sdf/d input)", "achieved": achieved,
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
             "traffic": TRAFFIC_BYTES.get(dom) if args.workload == "train" else None,
-            "traffic_source": "profiles/r01d_ncu_full.md (ncu --set full of this command, per launch)",
+            "traffic_source": "profiles/r01n_ncu_full.md (ncu --set full of this command, per launch)",
             "peak_source": pk["source"] + " bf16 sustained", "ms_per_launch": ms_launch,
             "pairs_per_launch": pairs_per_step, "flops_per_pair_algorithmic": GEO_FLOPS_ALGO,
             "flops_per_pair_executed": GEO_FLOPS_EXEC,

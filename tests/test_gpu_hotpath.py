@@ -84,6 +84,61 @@ def test_train_forward_backward_matches_reference(setup):
     assert all(p.grad is None for p in model.F_geometry.parameters())
 
 
+def test_sync_free_dense_step_matches_reference(setup):
+    """The training step as TrainStep runs it -- dense outputs (no host sync) and the fused VolSDFLoss kernels
+    (spf_volsdf_loss) -- against the same reference-generated golden loss terms and parameter gradients."""
+    from spurfies_b200.model import VolSDFLoss
+    g, P, model = setup
+    model.train()
+    inp = {"intrinsics": g["intrinsics"].cuda(), "uv": g["uv"].cuda(), "pose": g["pose"].cuda(), "iter_step": 1,
+           "local_data": None}
+    out = model(inp, fast=1, rng=cuda_rng(g), dense_outputs=True)
+    assert "grad_theta" not in out and out["grad_theta_dense"].shape[0] == out["grad_theta_mask"].shape[0]
+    lo = VolSDFLoss()(out, {k: v.cuda() for k, v in g["gt"].items()})
+    for k, v in g["train_loss"].items():
+        assert abs(float(lo[k]) - float(v)) < 5 * TOL * max(1.0, abs(float(v))), (k, float(lo[k]), float(v))
+    model.zero_grad()
+    lo["loss"].backward()
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    for n, r in g["train_grads"].items():
+        assert n in got, n
+        assert rel_err(got[n], r) < 1e-3, (n, rel_err(got[n], r))
+
+
+def test_rays_that_miss_everything():
+    """Empty input of the path: a camera looking away from the cloud (no sample passes the occupancy mask, V = 0) and a
+    one-ray batch, in both precision modes -- finite outputs, zero weights, finite loss, no gradient but the TV term's."""
+    from spurfies_b200 import scenes
+    from spurfies_b200.model import PointVolSDF, VolSDFLoss, default_conf
+    sc = scenes.dtu_like(5000, seed=2, radii=(0.35, 0.5))
+    for precision in ("fp32", "bf16"):
+        model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"],
+                            precision=precision)
+        model.train()
+        cam = scenes.camera(0, sc["cam_radius"])
+        pose = cam["pose"].clone()
+        pose[0, :3, :3] = -pose[0, :3, :3]      # look straight away from the object
+        for R in (33, 1):
+            uv = scenes.pixel_batch(R, seed=3)
+            rng, gt = scenes.rng_inputs(R, step=1), scenes.synthetic_gt(R, 1)
+            for dense in (False, True):
+                out = model({"intrinsics": cam["intrinsics"].cuda(), "uv": uv.cuda(), "pose": pose.cuda(), "local_data": None},
+                            fast=1, rng={k: v.cuda() for k, v in rng.items()}, dense_outputs=dense)
+                assert float(out["weights"].abs().max()) == 0.0 and torch.isfinite(out["rgb_values"]).all()
+                assert out["rgb_values"].shape == (R, 3) and out["weights"].shape == (R, 80)
+                if not dense:
+                    # the reference's ragged contract: grad_theta is [0,3] and its eikonal mean is NaN there too (loss.py:34-40)
+                    assert out["grad_theta"].shape == (0, 3)
+                    continue
+                lo = VolSDFLoss()(out, {k: v.cuda() for k, v in gt.items()})
+                assert torch.isfinite(lo["loss"]), (precision, R, dense)
+                model.zero_grad()
+                lo["loss"].backward()
+                assert model.neural_feats_color.grad is None or float(model.neural_feats_color.grad.abs().max()) == 0.0
+                for p in model.R.parameters():
+                    assert p.grad is None or float(p.grad.abs().max()) == 0.0
+
+
 def test_eval_forward_matches_reference(setup):
     g, P, model = setup
     model.eval()
