@@ -212,6 +212,15 @@ int spf_volsdf_loss(const float* rgb /*[R,3]*/, const float* rgb_gt /*[R,3]*/, c
                     float* terms /*[8]*/, float* d_rgb, float* d_weights, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* pseudo-point loss (pointneus_disent.py:765-780).  x[r] = cam + dist[r] dir[r] (spf_ray_points); after the kNN and the
+ * geometry field at x: value[0] = mean |sdf_r| over rays with ray_nvalid[r] > 0 and pidx[r*K] >= 0 (1000 if rays hit but
+ * none has a neighbour, 0 if nothing hit); u_sdf[r] = d value / d sdf_r; u_dist[r] (optional) = u_sdf[r] (grad_r . dir_r). */
+int spf_ray_points(const float* cam_loc /*[3]*/, const float* ray_dirs /*[R,3]*/, const float* dist /*[R]*/, int32_t R,
+                   float* x /*[R,3]*/, void* stream);
+int spf_pseudo_loss(const float* sdf /*[R]*/, const float* grad /*[R,3]*/, const int32_t* pidx /*[R,K]*/, int32_t K,
+                    const int32_t* ray_nvalid /*[R]*/, const float* ray_dirs /*[R,3]*/, int32_t R, float* value /*[1]*/,
+                    float* u_sdf /*[R]*/, float* u_dist /*[R] or NULL*/, void* stream);
+
 /* ---- a15: rays (rend_util.py:60-95, 143-156) ------------------------------------------------ */
 int spf_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, const float* intrinsics /*[4,4]*/,
                     int32_t R, float* ray_dirs /*[R,3]*/, float* cam_loc /*[3]*/, float* depth_scale /*[R]*/,

@@ -110,6 +110,8 @@ _SIGS = {
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "spf_ray_points": [_P, _P, _P, _I, _P, _P],
+    "spf_pseudo_loss": [_P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],
     "spf_volsdf_loss": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P, _P, _Z, _P],
     "spf_grad_sumsq": [_P, _L, _F, _P, _P, _Z, _P],
     "spf_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _D, _D, _F, _I, _P, _P],

@@ -761,3 +761,77 @@ extern "C" int spf_volsdf_loss(const float* rgb, const float* rgb_gt, const floa
   SPF_CHECK_LAUNCH("k_loss_final");
   return SPF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// a14: pseudo-point loss (pointneus_disent.py:765-780): L1 of the SDF at each hit ray's expected-depth point, mean over
+// the rays that hit AND whose point has a neighbour; 1000 when rays hit but no point has one (the reference's 1000-filled
+// rows), 0 when nothing hit.  One block; also writes the per-ray gradient factors the backward scales by the upstream
+// gradient: u_sdf[r] = sign(sdf_r) ok_r / cnt (d loss / d sdf_r) and u_dist[r] = u_sdf[r] * (grad_r . dir_r) (d loss / d dist_r
+// through x_r = cam + dist_r dir_r).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_pseudo_loss(const float* __restrict__ sdf, const float* __restrict__ grad,
+                                                      const int* __restrict__ pidx, int K, const int* __restrict__ ray_nvalid,
+                                                      const float* __restrict__ ray_dirs, int R, float* __restrict__ value,
+                                                      float* __restrict__ u_sdf, float* __restrict__ u_dist) {
+  __shared__ float s_sum[32];
+  __shared__ int s_cnt[32], s_hit[32];
+  __shared__ float s_inv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float sum = 0.0f;
+  int cnt = 0, hit = 0;
+  for (int r = tid; r < R; r += blockDim.x) {
+    const bool h = ray_nvalid[r] > 0;
+    const bool ok = h && pidx[(size_t)r * K] >= 0;
+    hit |= h ? 1 : 0;
+    if (ok) { sum += fabsf(sdf[r]); ++cnt; }
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(SPF_FULL, cnt, o); hit |= __shfl_xor_sync(SPF_FULL, hit, o); }
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; s_hit[warp] = hit; }
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.0f;
+    int c = 0, h = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += s_sum[w]; c += s_cnt[w]; h |= s_hit[w]; }
+    value[0] = c > 0 ? t / (float)c : (h ? 1000.0f : 0.0f);
+    s_inv = c > 0 ? 1.0f / (float)c : 0.0f;
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  for (int r = tid; r < R; r += blockDim.x) {
+    const bool ok = ray_nvalid[r] > 0 && pidx[(size_t)r * K] >= 0;
+    const float u = ok ? sgnf(sdf[r]) * inv : 0.0f;
+    u_sdf[r] = u;
+    if (u_dist)
+      u_dist[r] = ok ? u * (grad[3 * r] * ray_dirs[3 * r] + grad[3 * r + 1] * ray_dirs[3 * r + 1] + grad[3 * r + 2] * ray_dirs[3 * r + 2]) : 0.0f;
+  }
+}
+
+extern "C" int spf_pseudo_loss(const float* sdf, const float* grad, const int32_t* pidx, int32_t K, const int32_t* ray_nvalid,
+                               const float* ray_dirs, int32_t R, float* value, float* u_sdf, float* u_dist, void* stream_) {
+  if (!sdf || !pidx || !ray_nvalid || !value || !u_sdf || K < 1 || R < 1) return SPF_ERR_INVALID;
+  if (u_dist && (!grad || !ray_dirs)) return SPF_ERR_INVALID;
+  k_pseudo_loss<<<1, 1024, 0, (cudaStream_t)stream_>>>(sdf, grad, pidx, K, ray_nvalid, ray_dirs, R, value, u_sdf, u_dist);
+  SPF_CHECK_LAUNCH("k_pseudo_loss");
+  return SPF_OK;
+}
+
+// x[r] = cam + dist[r] * dir[r] (the expected-depth point of each ray, pointneus_disent.py:766-768)
+__global__ void k_ray_points(const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ dist,
+                             int R, float* __restrict__ x) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float d = dist[r];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[3 * r + a] = cam[a] + dirs[3 * r + a] * d;
+}
+
+extern "C" int spf_ray_points(const float* cam_loc, const float* ray_dirs, const float* dist, int32_t R, float* x,
+                              void* stream_) {
+  if (!cam_loc || !ray_dirs || !dist || !x) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  k_ray_points<<<(R + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(cam_loc, ray_dirs, dist, R, x);
+  SPF_CHECK_LAUNCH("k_ray_points");
+  return SPF_OK;
+}

@@ -510,6 +510,42 @@ class Composite(torch.autograd.Function):
         return d_sdf, d_rgb_s, d_beta.reshape(()), None, None, None, None, None, None, None, None, None
 
 
+class PseudoPointLoss(torch.autograd.Function):
+    """pseudo_pts_loss of pointneus_disent.py:765-780 in one piece: expected-depth point of every hit ray -> kNN -> geometry
+    field -> masked L1 mean.  Gradients: the geometry latents (scatter-add of the saved Jacobian rows) and ``dist`` (through
+    x = cam + dist * dir and d sdf / d x).  Replaces ~40 torch launches of mask / where / sum / sign glue per step."""
+
+    @staticmethod
+    def forward(ctx, feat_g, dist, cam_loc, ray_dirs, nvalid, grid, k, r, pack, pts, rbf):
+        dev = dist.device
+        R = dist.shape[0]
+        x = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        call("spf_ray_points", ptr(cam_loc), ptr(ray_dirs), ptr(dist.detach().contiguous()), R, ptr(x), stream())
+        slots = SlotSet(grid.query_points(x, k, r), "pseudo")
+        feat_needs, dist_needs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        sdf, grad, jw = geo_sdf_raw(pack, slots, x, pts, feat_g.detach(), rbf, dist_needs, feat_needs)
+        value = torch.empty(1, dtype=torch.float32, device=dev)
+        u_sdf = torch.empty(R, dtype=torch.float32, device=dev)
+        u_dist = torch.empty(R, dtype=torch.float32, device=dev) if dist_needs else None
+        call("spf_pseudo_loss", ptr(sdf), ptr(grad), ptr(slots.pidx), slots.K, ptr(nvalid), ptr(ray_dirs), R, ptr(value),
+             ptr(u_sdf), ptr(u_dist), stream())
+        ctx.slots, ctx.jw, ctx.u = slots, jw, (u_sdf, u_dist)
+        ctx.feat_shape = feat_g.shape
+        return value.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        slots = ctx.slots
+        u_sdf, u_dist = ctx.u
+        gfeat = None
+        if ctx.jw is not None:
+            gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=g.device)
+            call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
+                 ptr((u_sdf * g).contiguous()), ptr(gfeat), stream())
+        d_dist = u_dist * g if u_dist is not None else None
+        return gfeat, d_dist, None, None, None, None, None, None, None, None, None
+
+
 class TVRegul(torch.autograd.Function):
     """tv_regul (utils.py:221-281) on the cached self-kNN lists of the (static) neural points."""
 

@@ -25,7 +25,8 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import call, ptr, stream
-from .fields import (ColorField, Composite, GeoPack, GeoSDF, LocalLoss, RadianceHead, SlotSet, TVRegul, geo_sdf_raw,
+from .fields import (ColorField, Composite, GeoPack, GeoSDF, LocalLoss, PseudoPointLoss, RadianceHead, SlotSet, TVRegul,
+                     geo_sdf_raw,
                      local_feature_args, set_precision, surface_search)
 from .knnquery import VoxelGrid
 
@@ -394,14 +395,8 @@ class PointVolSDF(nn.Module):
             self._last_surface = (d_surface, cross)
         # pseudo points (pointneus_disent.py:765-780): expected-depth point per hit ray, SDF should vanish there
         if aux_losses:
-            pts_rendered = cam_loc[None, :] + ray_dirs * dist[:, None]
-            p_sdf, p_valid = self.pseudo_sdf(pts_rendered, dense=True)
-            p_ok = p_valid & ray_mask
-            cnt = p_ok.sum()
-            # F.l1_loss over the valid rows; the reference returns 1000-filled rows when nothing is valid
-            pseudo = torch.where(cnt > 0, (p_sdf.abs() * p_ok).sum() / cnt.clamp(min=1),
-                                 torch.where(ray_mask.any(), torch.full((), 1000.0, device=dev),
-                                             torch.zeros((), device=dev)))
+            pseudo = PseudoPointLoss.apply(self.neural_feats_geometry, dist, cam_loc, ray_dirs, nvalid, grid, self.conf.k,
+                                           self.conf.r, self._pack(), self.neural_pts, self.conf.rbf)
         else:
             pseudo = torch.zeros((), device=dev)
         far_cfg = float(self.conf.ray_sampler.far)
