@@ -149,6 +149,15 @@ def geo_sdf_raw(pack: GeoPack, slots: SlotSet, x, pts, feat_g, rbf, want_grad, w
     return sdf, grad, jw
 
 
+def _direct_grad(param) -> Optional[torch.Tensor]:
+    """Gradient-accumulation fusion (opt-in, set by TrainStep on the latent tables once their .grad is a view of the flat,
+    optimiser-cleared gradient buffer): the scatter-add kernels then accumulate straight into ``param.grad`` and the
+    Function returns None for that input -- no zero-filled temporary, no AccumulateGrad pass over the [N, C] table."""
+    if getattr(param, "_spf_direct_grad", False) and param.grad is not None and param.grad.is_contiguous():
+        return param.grad
+    return None
+
+
 class GeoSDF(torch.autograd.Function):
     """sdf[slot] = sum_k w_k T(F_geometry([g_k | x - p_k])) / sum_k w_k and d sdf / d x  (pointneus_disent.py:241-247,
     300-323).  Gradients: latents (scatter-add of the saved Jacobian rows) and, when x requires grad (pseudo-point
@@ -161,6 +170,7 @@ class GeoSDF(torch.autograd.Function):
         sdf, grad, jw = geo_sdf_raw(pack, slots, x, pts, feat_g.detach(), rbf, want_grad or x_needs, feat_needs)
         ctx.slots, ctx.jw, ctx.grad = slots, jw, grad
         ctx.feat_shape = feat_g.shape
+        ctx.direct = _direct_grad(feat_g)
         ctx.x_needs = x_needs
         if grad is None:
             grad = torch.zeros(0, 3, device=x.device)
@@ -173,9 +183,11 @@ class GeoSDF(torch.autograd.Function):
         gfeat = None
         d_sdf = d_sdf.contiguous()
         if ctx.jw is not None:
-            gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=d_sdf.device)
+            target = ctx.direct
+            if target is None:
+                target = gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=d_sdf.device)
             call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
-                 ptr(d_sdf), ptr(gfeat), stream())
+                 ptr(d_sdf), ptr(target), stream())
         dx = None
         if ctx.x_needs:
             dx = torch.where(slots.valid_mask()[:, None], d_sdf[:, None] * ctx.grad, torch.zeros_like(ctx.grad))
@@ -299,6 +311,7 @@ class ColorField(torch.autograd.Function):
                  ptr(m3), ptr(wn), stream())
         ctx.slots, ctx.saved_t, ctx.tcm = slots, (s, keep, W, b, in0, h1, h2, m3, wn), tcm
         ctx.feat_shape = feat_c.shape
+        ctx.direct = _direct_grad(feat_c)
         return hbar
 
     @staticmethod
@@ -312,7 +325,7 @@ class ColorField(torch.autograd.Function):
         dz1 = Arena.get(tg + ".dz1", (rows, 256), adt, dev)
         dz2 = Arena.get(tg + ".dz2", (rows, 256), adt, dev)
         dz3 = Arena.get(tg + ".dz3", (rows, 256), adt, dev)
-        gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
+        gfeat = ctx.direct if ctx.direct is not None else torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
         if tcm:
             # the radiance head may have left its gradient as bf16 by compact sample row in the tile layout (see
             # RadianceHead.backward); `d_hbar` is then only the placeholder autograd carried here
@@ -337,7 +350,7 @@ class ColorField(torch.autograd.Function):
             dW3, db3 = dz3[:r].t() @ h2[:r], dz3[:r].sum(0)
             dW2, db2 = dz2[:r].t() @ h1[:r], dz2[:r].sum(0)
             dW1, db1 = (dz1[:r].t() @ in0[:r])[:, :103], dz1[:r].sum(0)
-        return gfeat, dW1, db1, dW2, db2, dW3, db3, None, None, None, None
+        return (None if ctx.direct is not None else gfeat), dW1, db1, dW2, db2, dW3, db3, None, None, None, None
 
 
 def positional_encoding(x: torch.Tensor, multires: int) -> torch.Tensor:
@@ -531,6 +544,7 @@ class PseudoPointLoss(torch.autograd.Function):
              ptr(u_sdf), ptr(u_dist), stream())
         ctx.slots, ctx.jw, ctx.u = slots, jw, (u_sdf, u_dist)
         ctx.feat_shape = feat_g.shape
+        ctx.direct = _direct_grad(feat_g)
         return value.reshape(())
 
     @staticmethod
@@ -539,9 +553,11 @@ class PseudoPointLoss(torch.autograd.Function):
         u_sdf, u_dist = ctx.u
         gfeat = None
         if ctx.jw is not None:
-            gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=g.device)
+            target = ctx.direct
+            if target is None:
+                target = gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=g.device)
             call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
-                 ptr((u_sdf * g).contiguous()), ptr(gfeat), stream())
+                 ptr((u_sdf * g).contiguous()), ptr(target), stream())
         d_dist = u_dist * g if u_dist is not None else None
         return gfeat, d_dist, None, None, None, None, None, None, None, None, None
 

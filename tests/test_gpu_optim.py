@@ -107,3 +107,38 @@ def test_train_step_uses_fused_optimizer_and_learns():
     moved = (step.opt.flat_p - before).abs().max()
     assert 0.0 < float(moved) <= 30 * 5.0e-4 * 4.0       # Adam's per-step move is O(lr) whatever the gradient scale
     assert min(losses[10:]) < losses[0]                  # same batch every step: the loss goes down
+
+
+def test_direct_grad_accumulation_equals_autograd_accumulation():
+    """The latent tables' scatter-add kernels writing straight into the flat gradient buffer (TrainStep's opt-in,
+    fields._direct_grad) give the same gradients as zero-filled temporaries + autograd's AccumulateGrad."""
+    from spurfies_b200 import scenes
+    from spurfies_b200.model import PointVolSDF, VolSDFLoss, default_conf
+    from spurfies_b200.optim import FusedAdam
+    sc = scenes.dtu_like(8000, seed=1, radii=(0.35, 0.5))
+    R = 256
+    cam = scenes.camera(0, sc["cam_radius"])
+    batch = {"uv": scenes.pixel_batch(R, 3).cuda(), "pose": cam["pose"].cuda(), "intrinsics": cam["intrinsics"].cuda(),
+             "local_data": None}
+    gt = {k: v.cuda() for k, v in scenes.synthetic_gt(R, 3).items()}
+    rng = {k: v.cuda() for k, v in scenes.rng_inputs(R, 3).items()}
+    flats = {}
+    for direct in (False, True):
+        torch.manual_seed(0)
+        model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], precision="fp32")
+        with torch.no_grad():
+            model.neural_feats_geometry.mul_(8.0)
+        for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
+            prm.requires_grad_(False)
+        opt = FusedAdam([p for p in model.parameters() if p.requires_grad])   # attaches every p.grad to one flat buffer
+        opt.zero_grad()
+        model.neural_feats_color._spf_direct_grad = direct
+        model.neural_feats_geometry._spf_direct_grad = direct
+        model.train()
+        out = model(batch, fast=1, rng=rng, dense_outputs=True)
+        VolSDFLoss()(out, gt)["loss"].backward()
+        assert opt.grads_attached()
+        flats[direct] = opt.flat_g.clone()
+    a, b = flats[True], flats[False]
+    assert float(b.abs().max()) > 0
+    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())   # fp32 atomics: order of accumulation only
