@@ -574,10 +574,14 @@ class TVRegul(torch.autograd.Function):
         call("spf_tv_fwd_bwd", ptr(pts), ptr(feat_g.detach().contiguous()), ptr(self_pidx), N, K, ptr(value), ptr(grad),
              1.0, stream())
         ctx.grad = grad
+        ctx.direct = _direct_grad(feat_g) if grad is not None else None
         return value.reshape(())
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.direct is not None:
+            ctx.direct.addcmul_(ctx.grad, g)   # one pass: grad buffer += unit gradient * upstream scalar
+            return None, None, None
         return (ctx.grad * g if ctx.grad is not None else None), None, None
 
 
