@@ -337,8 +337,8 @@ typedef struct {
  * the rows of its last tile beyond count are zeroed in place. */
 int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* hbar, const float* zpe, const float* ray_dirs, int32_t Smax, float* rgb, void* hb, void* f,
-                    void* a1, void* a2, void* pe /*[rows,32] bf16: PE3(dir) per sample*/, void* stream);
-/* a1, a2 in and dzf, dz1, dz2 out: bf16 [rows,256] in the TILE layout; dz3 is bf16 [rows,16] row-major (3 used);
+                    void* a1, void* a2, void* pe /*[rows,64] bf16 tile layout, 32 columns used: PE3(dir) per sample*/, void* stream);
+/* a1, a2 in and dzf, dz1, dz2 out: bf16 [rows,256] in the TILE layout; dz3 is bf16 [rows,64] in the tile layout (3 used);
  * drb3 [3] (fp32) is accumulated in-kernel */
 int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
@@ -366,6 +366,15 @@ int spf_head_zpe(const float* ray_dirs /*[R,3]*/, const float* W, int32_t ld, co
  * c ^ (r & 7); A then has ceil(lda / 64) k-blocks per tile) instead of row-major.  No host synchronisation. */
 int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count, int32_t rows_per_unit,
                  int64_t n_max, int32_t layout, float* dW, float* db, void* stream);
+/* up to SPF_WGRAD_MAX_JOBS such products over the same rows in one launch; every operand in the TILE layout (dZ
+ * [rows,256], A [rows,lda] with lda a multiple of 64); db may be NULL.  The CTAs are split among the jobs by bytes per row. */
+#define SPF_WGRAD_MAX_JOBS 8
+typedef struct {
+  const void* dz; const void* act; float* dW; float* db;
+  int32_t lda, N;
+} spf_wgrad_job;
+int spf_wgrad_tc_multi(const spf_wgrad_job* jobs /* HOST array */, int32_t n_jobs, const int32_t* count,
+                       int32_t rows_per_unit, int64_t n_max, void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

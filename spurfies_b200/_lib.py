@@ -62,6 +62,11 @@ class PackJob(C.Structure):
                 ("transpose", C.c_int32), ("n_pad", C.c_int32), ("reserved", C.c_int32)]
 
 
+class WgradJob(C.Structure):
+    _fields_ = [("dz", C.c_void_p), ("act", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p), ("lda", C.c_int32),
+                ("N", C.c_int32)]
+
+
 class ColorWeightsF32(C.Structure):
     _fields_ = [("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
                 ("w3t", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p)]
@@ -124,6 +129,7 @@ _SIGS = {
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
     "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
     "spf_wgrad_tc": [_P, _P, _I, _I, _P, _I, _L, _I, _P, _P, _P],
+    "spf_wgrad_tc_multi": [_P, _I, _P, _I, _L, _P],
     "spf_head_fwd_tc": [_P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_pack_sw128": [_P, _I, _I, _I, _I, _I, _P, _P],

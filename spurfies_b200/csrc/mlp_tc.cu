@@ -239,6 +239,149 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Several weight-gradient products over the SAME rows in ONE launch (all operands in the tile layout): the persistent CTAs
+// are partitioned among the jobs in proportion to their bytes per row, so every CTA still streams one product but over a
+// longer row range -- one launch / TMEM allocation / tail instead of one per layer, and the fp32 atomic merge traffic
+// (256 x N floats per CTA) is paid once per CTA instead of once per CTA and layer.  Body = k_wgrad_tiled.
+struct WgJobDev { const uint8_t* dz; const uint8_t* act; float* dW; float* db; int act_nkb, N, cta0, ncta; };
+struct WgJobsDev { WgJobDev j[SPF_WGRAD_MAX_JOBS]; int n; };
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + WG_STAGES;
+  uint64_t* bar_done = bar_empty + WG_STAGES;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int q = 0;
+  while (q + 1 < jobs.n && (int)blockIdx.x >= jobs.j[q + 1].cta0) ++q;
+  const WgJobDev J = jobs.j[q];
+  const int bid = (int)blockIdx.x - J.cta0, nb = J.ncta;
+  const long long rows = ((long long)(*count) * rows_per_unit + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+  const int ntiles = (int)(rows / 64);
+  if (bid >= ntiles) return;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 9); }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t sbase = smem_u32(smem);
+  const int my_tiles = (ntiles - bid + nb - 1) / nb;
+  const int N = J.N;
+  const int act_panels = (N + 63) >> 6;
+  const uint32_t idesc = idesc_bf16_mn(128, N);
+  float bsum = 0.0f;
+
+  auto load_tile = [&](int it) {   // one thread
+    const int st = it % WG_STAGES;
+    const long long j = (long long)bid + (long long)it * nb;   // 64-row tile
+    uint8_t* sdz = smem + st * WG_STAGE_BYTES;
+    uint8_t* sact = sdz + 32768;
+    mbar_expect_tx(bar_full + st, (uint32_t)(4 + act_panels) * 8192u);
+    const uint8_t* gdz = J.dz + (j >> 1) * (4ll * 16384) + (j & 1) * 8192;
+    const uint8_t* gact = J.act + (j >> 1) * ((long long)J.act_nkb * 16384) + (j & 1) * 8192;
+    for (int kb = 0; kb < 4; ++kb) bulk_g2s(sdz + kb * 8192, gdz + kb * 16384, 8192, bar_full + st);
+    for (int kb = 0; kb < act_panels; ++kb) bulk_g2s(sact + kb * 8192, gact + kb * 16384, 8192, bar_full + st);
+  };
+
+  if (tid == 32)
+    for (int it = 0; it < WG_STAGES && it < my_tiles; ++it) load_tile(it);
+  for (int it = 0; it < my_tiles; ++it) {
+    const int st = it % WG_STAGES;
+    const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+    mbar_wait(bar_full + st, ph);
+    const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = smem_desc_mn_sw128(sact + ks * 2048, 8192);
+          mma_bf16(tmem, smem_desc_mn_sw128(sdz + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+          mma_bf16(tmem + 256, smem_desc_mn_sw128(sdz + 16384 + ks * 2048, 8192), bd, idesc, (it | ks) != 0);
+        }
+        mma_commit(bar_empty + st);
+      }
+      __syncwarp();
+    }
+    if (J.db) {   // bias gradient: thread = output column, column sum over this tile's 64 rows (read from the swizzled tile)
+      const uint8_t* pdz = smem + st * WG_STAGE_BYTES + (tid >> 6) * 8192;
+      const int c = (tid & 63) >> 3, e = tid & 7;
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(pdz + k * 128 + ((c ^ (k & 7)) << 4) + e * 2);
+        bsum += __bfloat162float(v);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(bar_empty + st);
+    if (tid == 32 && it + WG_STAGES < my_tiles) {
+      mbar_wait(bar_empty + st, ph);   // MMAs of tile `it` retired and every warp has read the stage
+      load_tile(it + WG_STAGES);
+    }
+  }
+  if (warp == 0) {
+    if (elect_one()) mma_commit(bar_done);
+    __syncwarp();
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  if (J.db) atomicAdd(J.db + tid, bsum);
+  {
+    const int out_row = 128 * (warp >> 2) + 32 * (warp & 3) + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 256;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(t_lane + c0, v);
+      tmem_ld_wait();
+      float* dst = J.dW + (size_t)out_row * N + c0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        if (c0 + 4 * j4 < N) atomicAdd(reinterpret_cast<float4*>(dst) + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, const int32_t* count, int32_t rows_per_unit,
+                                  int64_t n_max, void* stream_) {
+  if (!jobs || !count || n_jobs < 1 || n_jobs > SPF_WGRAD_MAX_JOBS || rows_per_unit < 1) return SPF_ERR_INVALID;
+  if (n_max <= 0) return SPF_OK;
+  WgJobsDev d;
+  d.n = n_jobs;
+  const int sms = spf_num_sms();
+  if (sms < n_jobs) return SPF_ERR_UNSUPPORTED;
+  long long wsum = 0, w[SPF_WGRAD_MAX_JOBS];
+  for (int q = 0; q < n_jobs; ++q) {
+    const spf_wgrad_job& J = jobs[q];
+    if (!J.dz || !J.act || !J.dW) return SPF_ERR_INVALID;
+    if (J.N % 16 || J.N < 16 || J.N > 256 || J.lda < J.N || J.lda % 64) return SPF_ERR_UNSUPPORTED;
+    w[q] = 512 + (long long)(J.lda >> 6) * 128;   // bytes per row of this product
+    wsum += w[q];
+  }
+  int used = 0;
+  for (int q = 0; q < n_jobs; ++q) {
+    int c = (int)((w[q] * sms) / wsum);
+    if (c < 1) c = 1;
+    if (q == n_jobs - 1 || used + c > sms - (n_jobs - 1 - q)) c = sms - (n_jobs - 1 - q) - used;
+    const spf_wgrad_job& J = jobs[q];
+    d.j[q] = {(const uint8_t*)J.dz, (const uint8_t*)J.act, J.dW, J.db, J.lda >> 6, J.N, used, c};
+    used += c;
+  }
+  SPF_CUDA(cudaFuncSetAttribute(k_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
+  k_wgrad_multi<<<used, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>(d, count, rows_per_unit);
+  SPF_CHECK_LAUNCH("k_wgrad_multi");
+  return SPF_OK;
+}
+
 extern "C" int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const int32_t* count,
                             int32_t rows_per_unit, int64_t n_max, int32_t layout, float* dW, float* db, void* stream_) {
   if (!dz || !act || !count || !dW) return SPF_ERR_INVALID;

@@ -680,7 +680,7 @@ extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* li
 //   f = F_color.6(hbar) ; a1 = lrelu(R.0_f f + zpe[ray]) ; a2 = lrelu(R.2 a1) ; rgb = sigmoid(R.4 a2)
 // zpe[ray] = R.0[:, :21] PE3(dir_ray) + R.0.bias is constant per ray and enters as an fp32 per-row bias.
 // Saved for the backward by compact sample row: hb (= bf16 hbar), f, a1, a2 [.,256] in the engine's TILE layout (one TMA
-// bulk store of the A tile each, see signal_a_ready), pe [.,32] row-major (PE3(dir), operand of the R.0 wgrad).
+// bulk store of the A tile each, see signal_a_ready), pe [.,64] (PE3(dir), 32 columns used, operand of the R.0 wgrad).
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
@@ -755,7 +755,13 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         }
 #pragma unroll
         for (int j = 21; j < 32; ++j) pe[j] = 0.0f;
-        store_g32(pe_s + grow * 32, pe);
+        // tile layout with one k-block (64 columns, 32 used): the R.0 weight gradient reads it like every other operand
+        uint8_t* pdst = reinterpret_cast<uint8_t*>(pe_s) + (size_t)tile * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(pdst + sw128_off(row, q)) =
+              make_uint4(pack_bf16(pe[8 * q], pe[8 * q + 1]), pack_bf16(pe[8 * q + 2], pe[8 * q + 3]),
+                         pack_bf16(pe[8 * q + 4], pe[8 * q + 5]), pack_bf16(pe[8 * q + 6], pe[8 * q + 7]));
       }
       if (hbar) {
         // A0 = hbar[slot] (bf16), gathered by row; saved as hb
@@ -890,7 +896,7 @@ extern "C" int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list
 
 // backward: dz3 = d_rgb * rgb (1 - rgb); dz2 = (dz3 @ R.4) * lrelu'(a2); dz1 = (dz2 @ R.2) * lrelu'(a1);
 //           dzf = dz1 @ R.0[:, 21:]; d_hbar = dzf @ F_color.6.   a1 / a2 are read back from the tile layout for their
-// signs (sign(a) == sign(z)); dz2, dz1, dzf leave in the tile layout for the wgrad kernel, dz3 [rows,16] row-major.
+// signs (sign(a) == sign(z)); dz2, dz1, dzf and dz3 ([rows,64], 16 columns used) leave in the tile layout for the wgrad kernel.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
                const float* __restrict__ d_rgb, const float* __restrict__ rgb, const uint8_t* __restrict__ a1_s,
@@ -941,9 +947,10 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           for (int c = 0; c < 3; ++c) { const float y = rgb[3 * (size_t)slot + c]; g[c] = d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
         }
         const uint4 gz = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
-        if (tile_ok) {                                                             // [rows,16] bf16: operand of the R.4 wgrad
-          reinterpret_cast<uint4*>(dz3 + grow * 16)[0] = gz;
-          reinterpret_cast<uint4*>(dz3 + grow * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (tile_ok) {   // operand of the R.4 wgrad: tile layout with one k-block (64 columns, 16 used)
+          uint8_t* zdst = reinterpret_cast<uint8_t*>(dz3) + (size_t)tile * 16384;
+          *reinterpret_cast<uint4*>(zdst + sw128_off(row, 0)) = gz;
+          *reinterpret_cast<uint4*>(zdst + sw128_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
         }
         if (drb3 && tile_ok) {                                                     // bias gradient of R.4
           const float s0 = warp_sum(g[0]), s1 = warp_sum(g[1]), s2 = warp_sum(g[2]);

@@ -273,6 +273,21 @@ def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a_t.t() @ b).float()
 
 
+def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool):
+    """[(dz, act, lda, N, want_db)] -> [(dW [256,N], db [256] or None)]: all products in ONE spf_wgrad_tc_multi launch (every
+    operand in the tile layout, lda a multiple of 64); no host sync."""
+    arr = (_lib.WgradJob * len(jobs))()
+    out = []
+    for i, (dz, act, lda, N, want_db) in enumerate(jobs):
+        dW, db = pool.take(256, N), (pool.take(256) if want_db else None)
+        arr[i].dz, arr[i].act, arr[i].dW = dz.data_ptr(), act.data_ptr(), dW.data_ptr()
+        arr[i].db = db.data_ptr() if db is not None else None
+        arr[i].lda, arr[i].N = int(lda), int(N)
+        out.append((dW, db))
+    call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(jobs), ptr(slots.count), int(rows_per_unit), slots.n, stream())
+    return out
+
+
 class ColorField(torch.autograd.Function):
     """hbar[slot] = sum_k w_k/norm * h3_k with h3 = first three layers of F_color on [PE6(x-p_k) | c_k]
     (pointneus_disent.py:325-336; F_color.6 is applied per sample in RadianceHead)."""
@@ -341,9 +356,8 @@ class ColorField(torch.autograd.Function):
                  stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
             pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
-            dW3, db3 = _wgrad_tc(dz3, h2, 256, 256, slots, slots.K, layout=3, pool=pool)
-            dW2, db2 = _wgrad_tc(dz2, h1, 256, 256, slots, slots.K, layout=3, pool=pool)
-            dW1p, db1 = _wgrad_tc(dz1, in0, 128, 112, slots, slots.K, layout=3, pool=pool)
+            (dW3, db3), (dW2, db2), (dW1p, db1) = _wgrad_multi(
+                [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool)
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
         else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
             r = slots.V * slots.K
@@ -404,7 +418,7 @@ class RadianceHead(torch.autograd.Function):
                 f = Arena.get(tg + ".hf", (rows, 256), torch.bfloat16, dev)
                 a1 = Arena.get(tg + ".ha1", (rows, 256), torch.bfloat16, dev)
                 a2 = Arena.get(tg + ".ha2", (rows, 256), torch.bfloat16, dev)
-                pe = Arena.get(tg + ".hpe", (rows, 32), torch.bfloat16, dev)
+                pe = Arena.get(tg + ".hpe", (rows, 64), torch.bfloat16, dev)   # tile layout, one k-block (32 columns used)
             call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, None if from_color else ptr(hbar_c),
                  ptr(zpe), ptr(dirs), int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
             ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
@@ -442,7 +456,7 @@ class RadianceHead(torch.autograd.Function):
         dz2 = Arena.get(tg + ".hdz2", (rows, 256), adt, dev)
         if tcm:
             hb, pe = hb
-            dz3 = Arena.get(tg + ".hdz3b", (rows, 16), torch.bfloat16, dev)
+            dz3 = Arena.get(tg + ".hdz3b", (rows, 64), torch.bfloat16, dev)   # tile layout, one k-block (3 columns used)
             pool = _ZeroPool(3 * 256 * 256 + 256 * 32 + 256 * 16 + 3 * 256 + 4, dev)
             drb3 = pool.take(3)
             # `slots.single_consumer` (set by PointVolSDF.forward): hbar feeds nothing but this head, so its gradient can
@@ -455,13 +469,11 @@ class RadianceHead(torch.autograd.Function):
             call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
                  ptr(a1), ptr(a2), None if d_hbc is not None else ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3),
                  ptr(drb3), ptr(d_hbc), stream())
-            # hb, f, a1, a2 and dzf, dz1, dz2 are in the tile layout (layout bits), pe and dz3 row-major
-            dW4, db4 = _wgrad_tc(dzf, hb, 256, 256, slots, 1, layout=3, pool=pool)
-            dR1f, drb1 = _wgrad_tc(dz1, f, 256, 256, slots, 1, layout=3, pool=pool)
-            dR1pe, _ = _wgrad_tc(dz1, pe, 32, 32, slots, 1, want_db=False, layout=1, pool=pool)
+            # every operand is in the tile layout (pe and dz3 with a single k-block)
+            (dW4, db4), (dR1f, drb1), (dR1pe, _), (dR2, drb2), (dR3t, _) = _wgrad_multi(
+                [(dzf, hb, 256, 256, True), (dz1, f, 256, 256, True), (dz1, pe, 64, 32, False), (dz2, a1, 256, 256, True),
+                 (a2, dz3, 64, 16, False)], slots, 1, pool)              # (a2^T @ dz3) = dR3^T, [256,16]
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
-            dR2, drb2 = _wgrad_tc(dz2, a1, 256, 256, slots, 1, layout=3, pool=pool)
-            dR3t, _ = _wgrad_tc(a2, dz3, 16, 16, slots, 1, want_db=False, layout=1, pool=pool)   # (a2^T @ dz3) = dR3^T, [256,16]
             dR3 = dR3t[:, :3].t().contiguous()
             return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)

@@ -248,3 +248,36 @@ def test_wgrad_tc(n_units, rpu, N, lda, layout):
     refb = dz[:rows].float().sum(0)
     assert float((dW - ref).abs().max() / ref.abs().max()) < 1e-4
     assert float((db - refb).abs().max() / refb.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("n_units,rpu", [(1000, 8), (5000, 1), (37, 1)])
+def test_wgrad_tc_multi(n_units, rpu):
+    """Several weight-gradient products over the same rows in one launch (CTAs partitioned among the jobs) vs torch:
+    the colour field's three layers' shapes and the radiance head's narrow operands (one k-block, 32 / 16 columns used)."""
+    import ctypes as C
+    from spurfies_b200 import _lib
+    g = torch.Generator().manual_seed(7 * n_units + rpu)
+    rows = (n_units * rpu + 127) // 128 * 128
+    shapes = [(256, 256, True), (128, 112, True), (64, 32, False), (64, 16, False), (256, 256, True)]   # (lda, N, db)
+    dzs = [torch.randn(rows + 128, 256, generator=g).cuda().to(torch.bfloat16) for _ in shapes]
+    acts = [torch.randn(rows + 128, lda, generator=g).cuda().to(torch.bfloat16) for lda, _, _ in shapes]
+    count = torch.tensor([n_units], dtype=torch.int32, device="cuda")
+    arr = (_lib.WgradJob * len(shapes))()
+    outs, keep = [], []
+    for i, (lda, N, want_db) in enumerate(shapes):
+        dW = torch.zeros(256, N, device="cuda")
+        db = torch.zeros(256, device="cuda") if want_db else None
+        dz_t, act_t = _to_tile_layout(dzs[i], 4), _to_tile_layout(acts[i], lda // 64)
+        keep += [dz_t, act_t]
+        arr[i].dz, arr[i].act, arr[i].dW = dz_t.data_ptr(), act_t.data_ptr(), dW.data_ptr()
+        arr[i].db = db.data_ptr() if db is not None else None
+        arr[i].lda, arr[i].N = lda, N
+        outs.append((dW, db))
+    _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), rpu, n_units + 50, _lib.stream())
+    torch.cuda.synchronize()
+    for i, (lda, N, want_db) in enumerate(shapes):
+        ref = dzs[i][:rows].float().t() @ acts[i][:rows, :N].float()
+        assert float((outs[i][0] - ref).abs().max() / ref.abs().max()) < 1e-4, i
+        if want_db:
+            refb = dzs[i][:rows].float().sum(0)
+            assert float((outs[i][1] - refb).abs().max() / refb.abs().max()) < 1e-4, i
