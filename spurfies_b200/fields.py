@@ -273,17 +273,20 @@ def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a_t.t() @ b).float()
 
 
-def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool):
+def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None):
     """[(dz, act, lda, N, want_db)] -> [(dW [256,N], db [256] or None)]: all products in ONE spf_wgrad_tc_multi launch (every
-    operand in the tile layout, lda a multiple of 64); no host sync."""
+    operand in the tile layout, lda a multiple of 64); no host sync.  ``targets[i] = (dW_grad, db_grad)`` (either may be
+    None) makes job i accumulate straight into those gradient buffers (see _direct_grad); None is then returned for them."""
     arr = (_lib.WgradJob * len(jobs))()
     out = []
     for i, (dz, act, lda, N, want_db) in enumerate(jobs):
-        dW, db = pool.take(256, N), (pool.take(256) if want_db else None)
+        tW, tb = targets[i] if targets is not None else (None, None)
+        dW = tW if tW is not None else pool.take(256, N)
+        db = (tb if tb is not None else pool.take(256)) if want_db else None
         arr[i].dz, arr[i].act, arr[i].dW = dz.data_ptr(), act.data_ptr(), dW.data_ptr()
         arr[i].db = db.data_ptr() if db is not None else None
         arr[i].lda, arr[i].N = int(lda), int(N)
-        out.append((dW, db))
+        out.append((None if tW is not None else dW, None if (tb is not None or db is None) else db))
     call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(jobs), ptr(slots.count), int(rows_per_unit), slots.n, stream())
     return out
 
@@ -327,6 +330,7 @@ class ColorField(torch.autograd.Function):
         ctx.slots, ctx.saved_t, ctx.tcm = slots, (s, keep, W, b, in0, h1, h2, m3, wn), tcm
         ctx.feat_shape = feat_c.shape
         ctx.direct = _direct_grad(feat_c)
+        ctx.direct_w = [_direct_grad(p) for p in (W1, b1, W2, b2, W3, b3)] if tcm else [None] * 6
         return hbar
 
     @staticmethod
@@ -356,8 +360,10 @@ class ColorField(torch.autograd.Function):
                  stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
             pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
+            tw = ctx.direct_w   # W1's gradient needs its columns permuted back: through the pool; the rest may go direct
             (dW3, db3), (dW2, db2), (dW1p, db1) = _wgrad_multi(
-                [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool)
+                [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool,
+                targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])])
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
         else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
             r = slots.V * slots.K
@@ -423,6 +429,7 @@ class RadianceHead(torch.autograd.Function):
                  ptr(zpe), ptr(dirs), int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
             ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
             ctx.from_color = from_color
+            ctx.direct_w = [_direct_grad(p) for p in (W4, b4, R1, rb1, R2, rb2, R3, rb3)]
         else:
             Wt = [w.t().contiguous() for w in W]
             s = HeadWeightsF32()
@@ -458,7 +465,8 @@ class RadianceHead(torch.autograd.Function):
             hb, pe = hb
             dz3 = Arena.get(tg + ".hdz3b", (rows, 64), torch.bfloat16, dev)   # tile layout, one k-block (3 columns used)
             pool = _ZeroPool(3 * 256 * 256 + 256 * 32 + 256 * 16 + 3 * 256 + 4, dev)
-            drb3 = pool.take(3)
+            tw = ctx.direct_w   # R.0 (concatenated) and R.4 (transposed) go through the pool; the rest may go direct
+            drb3 = tw[7] if tw[7] is not None else pool.take(3)
             # `slots.single_consumer` (set by PointVolSDF.forward): hbar feeds nothing but this head, so its gradient can
             # travel to ColorField.backward as bf16 by compact sample row in the tile layout (one coalesced bulk store per
             # tile here, half the bytes there); the fp32 `d_hbar` returned to autograd is then an unwritten placeholder
@@ -472,10 +480,11 @@ class RadianceHead(torch.autograd.Function):
             # every operand is in the tile layout (pe and dz3 with a single k-block)
             (dW4, db4), (dR1f, drb1), (dR1pe, _), (dR2, drb2), (dR3t, _) = _wgrad_multi(
                 [(dzf, hb, 256, 256, True), (dz1, f, 256, 256, True), (dz1, pe, 64, 32, False), (dz2, a1, 256, 256, True),
-                 (a2, dz3, 64, 16, False)], slots, 1, pool)              # (a2^T @ dz3) = dR3^T, [256,16]
+                 (a2, dz3, 64, 16, False)], slots, 1, pool,               # (a2^T @ dz3) = dR3^T, [256,16]
+                targets=[(tw[0], tw[1]), (None, tw[3]), (None, None), (tw[4], tw[5]), (None, None)])
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
             dR3 = dR3t[:, :3].t().contiguous()
-            return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
+            return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, (None if tw[7] is not None else drb3), None, None, None
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)
         call("spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
              ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), stream())

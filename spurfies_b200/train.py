@@ -156,8 +156,8 @@ class TrainStep:
             self._reducer.flat().zero_()
         # gradient-accumulation fusion for the [N, C] latent tables: their scatter-add kernels write straight into the
         # flat buffer's views (fields._direct_grad), which the optimiser kernel cleared
-        self.model.neural_feats_color._spf_direct_grad = True
-        self.model.neural_feats_geometry._spf_direct_grad = True
+        for p in self.params:
+            p._spf_direct_grad = True
         # every p.grad is a view of the flat buffer: autograd accumulates into it in place.  It is all-zero here: the
         # optimiser kernel clears it in the same pass that consumes it (zero_grad, train.py:355).
         losses["loss"].backward()

@@ -109,8 +109,9 @@ def test_train_step_uses_fused_optimizer_and_learns():
     assert min(losses[10:]) < losses[0]                  # same batch every step: the loss goes down
 
 
-def test_direct_grad_accumulation_equals_autograd_accumulation():
-    """The latent tables' scatter-add kernels writing straight into the flat gradient buffer (TrainStep's opt-in,
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_direct_grad_accumulation_equals_autograd_accumulation(precision):
+    """The scatter-add / split-K kernels writing straight into the flat gradient buffer (TrainStep's opt-in,
     fields._direct_grad) give the same gradients as zero-filled temporaries + autograd's AccumulateGrad."""
     from spurfies_b200 import scenes
     from spurfies_b200.model import PointVolSDF, VolSDFLoss, default_conf
@@ -125,15 +126,15 @@ def test_direct_grad_accumulation_equals_autograd_accumulation():
     flats = {}
     for direct in (False, True):
         torch.manual_seed(0)
-        model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], precision="fp32")
+        model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], precision=precision)
         with torch.no_grad():
             model.neural_feats_geometry.mul_(8.0)
         for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
             prm.requires_grad_(False)
         opt = FusedAdam([p for p in model.parameters() if p.requires_grad])   # attaches every p.grad to one flat buffer
         opt.zero_grad()
-        model.neural_feats_color._spf_direct_grad = direct
-        model.neural_feats_geometry._spf_direct_grad = direct
+        for p in opt.params:        # latent tables (both modes) and, in bf16 mode, the split-K weight-gradient outputs
+            p._spf_direct_grad = direct
         model.train()
         out = model(batch, fast=1, rng=rng, dense_outputs=True)
         VolSDFLoss()(out, gt)["loss"].backward()
@@ -141,7 +142,7 @@ def test_direct_grad_accumulation_equals_autograd_accumulation():
         flats[direct] = opt.flat_g.clone()
     a, b = flats[True], flats[False]
     assert float(b.abs().max()) > 0
-    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())   # fp32 atomics: order of accumulation only
+    assert float((a - b).abs().max()) <= (1e-5 if precision == "fp32" else 1e-4) * float(b.abs().max())   # atomics order only
 
 
 def test_prefetched_inputs_give_the_same_step():
