@@ -13,6 +13,9 @@ using namespace eng;
 
 #define LEAKY 0.01f
 
+// (L2 prefetches of the next tile's gather rows -- latent rows, points, the compact d_hbar lines, sign words -- were
+// measured and rejected: no change within noise; the gathers already hit L2 and the kernels are epilogue-issue bound.)
+
 __device__ __forceinline__ float rbf_w2(float dx, float dy, float dz, float rbf) {
   float dist = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
   float tq = dist * rbf;
@@ -637,18 +640,15 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
       if ((tid & 255) == 0) TL(6, t, 2);
       drain_store(t);   // the next iteration's prologue overwrites the A tile
       if ((tid & 255) == 0) TL(0, t, 2);
-      if (half == 0) {
+      {   // both column-half warp sets take 32 of the 64 latent columns each
         const int p = sl >= 0 ? pidx[(size_t)sl * 8 + (row & 7)] : -1;
+        float v[32];
+        tmem_ld32(t_row + half * 32, v);
+        tmem_ld_wait();
+        if (p >= 0) {
+          float4* dst = reinterpret_cast<float4*>(gfeat + (size_t)p * 64 + half * 32);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float v[32];
-          tmem_ld32(t_row + q * 32, v);
-          tmem_ld_wait();
-          if (p >= 0) {
-            float4* dst = reinterpret_cast<float4*>(gfeat + (size_t)p * 64 + q * 32);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) atomicAdd(dst + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-          }
+          for (int j4 = 0; j4 < 8; ++j4) atomicAdd(dst + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
         }
       }
       tc_fence_before();
