@@ -42,11 +42,11 @@ WORKLOADS = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-# capture of this command (profiles/r01n_ncu_full.md: k_sdf_tc2<1>, 23.7 MB read + 111.0 MB written)
-TRAFFIC_BYTES = {"spf_sdf_fwd_tc": 134.7e6}
+# capture of this command (profiles/r01w_ncu_full.md: k_sdf_tc2<1>, 24.3 MB read + 110.5 MB written)
+TRAFFIC_BYTES = {"spf_sdf_fwd_tc": 134.8e6}
 
 # kernels launched per C-ABI call (for gpu_launches)
-LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3, "spf_grad_sumsq": 2, "spf_adam_step": 2}
+LAUNCHES = {"spf_grid_build": 4, "spf_compact_valid": 3, "spf_grad_sumsq": 2, "spf_adam_step": 2, "spf_volsdf_loss": 2}
 
 # FLOPs per (sample, neighbour) pair of the geometry field, 2 * MAC.
 #  algorithmic = SURVEY 8(d): reference graph, 35->256->256->256->256->256->1 = 271 360 MAC, forward + the
@@ -73,7 +73,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -272,7 +272,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": dom + " (fine pass, fwd + d sdf/d input)", "achieved": achieved,
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
             "traffic": TRAFFIC_BYTES.get(dom) if args.workload == "train" else None,
-            "traffic_source": "profiles/r01n_ncu_full.md (ncu --set full of this command, per launch)",
+            "traffic_source": "profiles/r01w_ncu_full.md (ncu --set full of this command, per launch)",
             "peak_source": pk["source"] + " bf16 sustained", "ms_per_launch": ms_launch,
             "pairs_per_launch": pairs_per_step, "flops_per_pair_algorithmic": GEO_FLOPS_ALGO,
             "flops_per_pair_executed": GEO_FLOPS_EXEC,
@@ -331,7 +331,9 @@ def other_rooflines(prof, prof_steps, pairs, model, pk):
     add("spf_color_bwd_tc", 2 * (2 * 65536 + 256 * 64) * pairs, "TFLOP/s", tc, "294 912 FLOP/pair (dgrad)")
     # all wgrad launches of the step: colour (3 layers over pairs) + head (4 layers over samples); bytes = bf16 dZ + A rows
     wg_bytes = pairs * (3 * 512 + 512 + 512 + 256) + V * (3 * 512 + 512 + 512 + 512 + 64 + 512 + 32)
-    add("spf_wgrad_tc", wg_bytes, "GB/s", hbm, "bf16 dZ + activation rows read once per layer")
+    # (the colour field's three products and the head's five run as one spf_wgrad_tc_multi launch each)
+    add("spf_wgrad_tc_multi" if "spf_wgrad_tc_multi" in prof else "spf_wgrad_tc", wg_bytes, "GB/s", hbm,
+        "bf16 dZ + activation rows read once per layer")
     add("spf_head_fwd_tc", 2 * 137_216 * V, "TFLOP/s", tc, "274 432 FLOP/sample")
     add("spf_head_bwd_tc", 2 * 137_216 * V, "TFLOP/s", tc, "274 432 FLOP/sample (dgrad)")
     # kNN, fine pass: 12 B query + 27*8 B cell headers + 16 B * C_q candidates + 32 B out per masked-in query (8(d));

@@ -242,9 +242,9 @@ class _ZeroPool:
         n = 1
         for d in shape:
             n *= int(d)
+        assert self.off + n <= self.buf.numel(), "zero pool exhausted"
         out = self.buf[self.off:self.off + n].view(*shape)
         self.off += (n + 3) // 4 * 4
-        assert self.off <= self.buf.numel()
         return out
 
 

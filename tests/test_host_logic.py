@@ -55,3 +55,31 @@ def test_mesh_grids_match_the_restated_reference_grids():
     P = mesh.grid_points([x, y, z])
     i = (2 * 3 + 1) * 5 + 4
     assert P[i].tolist() == [1.0, 12.0, 24.0]
+
+
+def test_zero_pool_hands_out_aligned_disjoint_pieces():
+    """fields._ZeroPool: one zero fill per backward, 16-byte aligned non-overlapping views (the split-K weight-gradient
+    kernel's vector atomics need the alignment)."""
+    import torch
+    from spurfies_b200.fields import _ZeroPool
+    pool = _ZeroPool(256 * 112 + 3 * 256 + 4 + 256 * 16, "cpu")
+    a, b, c, d = pool.take(256, 112), pool.take(3), pool.take(256), pool.take(256, 16)
+    base = pool.buf.data_ptr()
+    spans = []
+    for t in (a, b, c, d):
+        assert (t.data_ptr() - base) % 16 == 0 and t.is_contiguous() and float(t.abs().sum()) == 0.0
+        spans.append((t.data_ptr(), t.data_ptr() + 4 * t.numel()))
+    spans.sort()
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    import pytest
+    with pytest.raises(AssertionError):
+        pool.take(256, 256)
+
+
+def test_pack_jobs_struct_matches_the_header():
+    """ctypes mirrors of the host-array structs (spf_pack_job, spf_wgrad_job) have the C layout the header declares."""
+    import ctypes as C
+    from spurfies_b200 import _lib
+    assert C.sizeof(_lib.PackJob) == 2 * C.sizeof(C.c_void_p) + 6 * 4
+    assert C.sizeof(_lib.WgradJob) == 4 * C.sizeof(C.c_void_p) + 2 * 4
+    assert _lib.PackJob.out.offset == 8 and _lib.PackJob.ld.offset == 16 and _lib.WgradJob.lda.offset == 32
