@@ -2,7 +2,8 @@
 
 PyTorch is used for device memory, streams and autograd bookkeeping only; every tensor op on the hot path is a
 hand-written kernel reached through the C ABI (include/spurfies_b200.h).  The only library GEMMs are the plain
-weight-gradient products dW = dZ^T @ A of the trainable colour MLP / radiance head (cuBLAS through torch.matmul).
+weight-gradient products dW = dZ^T @ A of the EXACT (fp32) mode (cuBLAS through torch.matmul); the bf16 mode uses the
+split-K tcgen05 kernel (spf_wgrad_tc_multi).
 
 Layout: a *slot* is one query position (ray sample or point).  ``pidx`` [n, K] holds its neighbours sorted by
 (d^2, id), -1 padded.  Valid slots (>= 1 neighbour) are compacted on the device into ``list`` / ``count``; per-slot
@@ -246,31 +247,6 @@ class _ZeroPool:
         out = self.buf[self.off:self.off + n].view(*shape)
         self.off += (n + 3) // 4 * 4
         return out
-
-
-def _wgrad_tc(dz, act, lda, N, slots, rows_per_unit, want_db=True, layout=0, pool: Optional[_ZeroPool] = None):
-    """dW [256,N], db [256] (fp32) = spf_wgrad_tc over the rows the dgrad kernel wrote; no host sync.
-    layout bit 0 / 1: dz / act is in the colour kernels' tile layout (include/spurfies_b200.h)."""
-    dev = dz.device
-    if pool is not None:
-        dW, db = pool.take(256, N), (pool.take(256) if want_db else None)
-    else:
-        dW = torch.zeros(256, N, dtype=torch.float32, device=dev)
-        db = torch.zeros(256, dtype=torch.float32, device=dev) if want_db else None
-    call("spf_wgrad_tc", ptr(dz), ptr(act), int(lda), int(N), ptr(slots.count), int(rows_per_unit), slots.n, int(layout), ptr(dW),
-         ptr(db),
-         stream())
-    return dW, db
-
-
-def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a_t^T @ b with fp32 output for bf16 operands (plain library GEMM: the weight-gradient product)."""
-    if a_t.dtype == torch.float32:
-        return a_t.t() @ b
-    try:
-        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
-    except (TypeError, RuntimeError):
-        return (a_t.t() @ b).float()
 
 
 def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None):
