@@ -341,9 +341,13 @@ extern "C" int spf_sampler_coarse(const float* t_vals, const float* t_rand, floa
   return SPF_OK;
 }
 
-// error bound for one beta (ray_sampler.py:576-588); lanes own contiguous chunks of the M-1 sections
+// error bound for one beta (ray_sampler.py:576-588); lanes own contiguous chunks of the M-1 sections.  The per-section
+// terms (error-integral increment, free-energy increment) are needed twice -- for the chunk sums that feed the warp scans
+// and again when the lane walks its chunk -- so they are parked in the lane's own slice of two shared scratch rows
+// (se_s, sf_s) instead of being recomputed (two exps, an expm1 and three divisions per section and call).
 __device__ float error_bound_warp(const float* __restrict__ sz, const float* __restrict__ sd,
-                                  const float* __restrict__ sds, int M, float beta, int lane) {
+                                  const float* __restrict__ sds, float* __restrict__ se_s, float* __restrict__ sf_s,
+                                  int M, float beta, int lane) {
   const int n = M - 1;
   const int ch = (n + 31) >> 5;
   const int i0 = lane * ch, i1 = min(n, i0 + ch);
@@ -351,18 +355,20 @@ __device__ float error_bound_warp(const float* __restrict__ sz, const float* __r
   float se = 0.0f, sf = 0.0f;
   for (int i = i0; i < i1; ++i) {
     float a = sz[i + 1] - sz[i];
-    se += expf(-sds[i] / beta) * (a * a) / fb2;
-    sf += a * laplace_density(sd[i], beta);
+    const float ei = expf(-sds[i] / beta) * (a * a) / fb2;
+    const float fi = a * laplace_density(sd[i], beta);
+    se_s[i] = ei; sf_s[i] = fi;
+    se += ei;
+    sf += fi;
   }
   float ie = warp_scan_incl(se, lane) - se;  // exclusive offsets
   float jf = warp_scan_incl(sf, lane) - sf;
   float mx = -INFINITY;
   bool anynan = false;
   for (int i = i0; i < i1; ++i) {
-    float a = sz[i + 1] - sz[i];
-    ie += expf(-sds[i] / beta) * (a * a) / fb2;                   // inclusive error integral
+    ie += se_s[i];                                                // inclusive error integral
     float b = (fminf(expf(ie), 1.0e6f) - 1.0f) * expf(-jf);       // uses the exclusive density integral
-    jf += a * laplace_density(sd[i], beta);
+    jf += sf_s[i];
     anynan |= isnan(b);
     mx = fmaxf(mx, b);
   }
@@ -382,10 +388,12 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + wid;
   const int stride = M + 1;
-  float* sz = smem + (size_t)wid * 4 * stride;   // z
+  float* sz = smem + (size_t)wid * 6 * stride;   // z
   float* sd = sz + stride;                        // sdf
   float* sds = sd + stride;                       // d_star, later scratch for the final sort
   float* scdf = sds + stride;                     // cdf
+  float* se_s = scdf + stride;                    // per-section error-integral increments (lane-private slices)
+  float* sf_s = se_s + stride;                    // per-section / per-sample free-energy increments
   if (r >= R) return;
   for (int i = lane; i < M; i += 32) { sz[i] = z[(size_t)r * M + i]; sd[i] = sdf[(size_t)r * M + i]; }
   __syncwarp();
@@ -413,12 +421,12 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   const float beta0 = beta_dev[0];
   float beta = first_iter ? sqrtf(bound_coef * ss) : beta_io[r];  // ray_sampler.py:388-392
   // line search (ray_sampler.py:435-445)
-  float e0 = error_bound_warp(sz, sd, sds, M, beta0, lane);
+  float e0 = error_bound_warp(sz, sd, sds, se_s, sf_s, M, beta0, lane);
   if (e0 <= eps) beta = beta0;
   float bmin = beta0, bmax = beta;
   for (int j = 0; j < beta_iters; ++j) {
     float mid = (bmin + bmax) / 2.0f;
-    float e = error_bound_warp(sz, sd, sds, M, mid, lane);
+    float e = error_bound_warp(sz, sd, sds, se_s, sf_s, M, mid, lane);
     if (e <= eps) bmax = mid;
     else if (e > eps) bmin = mid;
   }
@@ -432,25 +440,27 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   const int j0 = lane * chM, j1 = min(M, j0 + chM);
   float sf = 0.0f, se = 0.0f;
   const float fb2 = 4.0f * (beta * beta);
+  __syncwarp();   // the chunking below differs from error_bound_warp's: its scratch reads must be done
   for (int i = j0; i < j1; ++i) {
     float a = i < n ? sz[i + 1] - sz[i] : 1e10f;
-    sf += a * laplace_density(sd[i], beta);
-    if (i < n) se += expf(-sds[i] / beta) * (a * a) / fb2;
+    const float fi = a * laplace_density(sd[i], beta);
+    sf_s[i] = fi;
+    sf += fi;
+    if (i < n) { const float ei = expf(-sds[i] / beta) * (a * a) / fb2; se_s[i] = ei; se += ei; }
   }
   float jf = warp_scan_incl(sf, lane) - sf;
   float ie = warp_scan_incl(se, lane) - se;
   // unnormalised pdf into scdf[0..n)
   float tot = 0.0f;
   for (int i = j0; i < j1; ++i) {
-    float a = i < n ? sz[i + 1] - sz[i] : 1e10f;
-    float fe = a * laplace_density(sd[i], beta);
+    float fe = sf_s[i];
     float T = expf(-jf);
     float p;
     if (final_) {
       float w = (1.0f - expf(-fe)) * T;
       p = w + 1e-5f;                                               // ray_sampler.py:495-497
     } else {
-      if (i < n) ie += expf(-sds[i] / beta) * (a * a) / fb2;
+      if (i < n) ie += se_s[i];
       p = (fminf(expf(ie), 1.0e6f) - 1.0f) * T + add_tiny;         // ray_sampler.py:476-486
     }
     jf += fe;
@@ -497,16 +507,26 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   if (lane == 0) { ssort[N] = near_; ssort[N + 1] = far_; }
   for (int e = lane; e < n_extra; e += 32) ssort[N + 2 + e] = sz[extra_idx[e]];
   __syncwarp();
+  bool mynan = false;
+  for (int i = lane; i < cols; i += 32) mynan |= ssort[i] != ssort[i];
+  const bool row_has_nan = __any_sync(SPF_FULL, mynan);
   for (int i = lane; i < cols; i += 32) {
     float v = ssort[i];
-    const bool vnan = v != v;
     int rank = 0;
-    for (int j = 0; j < cols; ++j) {
-      // torch.sort order: NaN sorts last (a miss ray's samples are NaN, as in the reference); ties by position, so
-      // the ranks are a permutation and every output element is written
-      float o = ssort[j];
-      const bool onan = o != o;
-      rank += (!onan && (vnan || o < v)) || ((o == v || (onan && vnan)) && j < i);
+    if (!row_has_nan) {   // the common case: plain stable rank (ties by position)
+      for (int j = 0; j < cols; ++j) {
+        float o = ssort[j];
+        rank += (o < v) || (o == v && j < i);
+      }
+    } else {
+      const bool vnan = v != v;
+      for (int j = 0; j < cols; ++j) {
+        // torch.sort order: NaN sorts last (a miss ray's samples are NaN, as in the reference); ties by position, so
+        // the ranks are a permutation and every output element is written
+        float o = ssort[j];
+        const bool onan = o != o;
+        rank += (!onan && (vnan || o < v)) || ((o == v || (onan && vnan)) && j < i);
+      }
     }
     out_z[(size_t)r * cols + rank] = v;
 #pragma unroll
@@ -528,7 +548,7 @@ extern "C" int spf_sampler_iter(const float* z, const float* sdf, int32_t R, int
   if (n_extra > 0 && !extra_idx) return SPF_ERR_INVALID;
   if (R <= 0) return SPF_OK;
   const int wpb = 4;
-  size_t smem = (size_t)wpb * 4 * (M + 1) * sizeof(float);
+  size_t smem = (size_t)wpb * 6 * (M + 1) * sizeof(float);
   if (smem > 200 * 1024) return SPF_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     SPF_CUDA(cudaFuncSetAttribute(k_sampler_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
