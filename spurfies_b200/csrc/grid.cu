@@ -219,7 +219,9 @@ __device__ __forceinline__ unsigned long long knn_warp(const GridDev& g, float q
   // only ~20 % of the corner columns can be skipped, and the per-column distance test costs more instructions than the
   // shorter scan saves: k_knn_slots 0.27 -> 0.32 ms.  Likewise rejected: fetching the nine columns' bounds in one round
   // trip and streaming the chained segments 32 candidates per step with the next step prefetched -- the kernel is
-  // issue-bound on the insertion shuffles (SM pipe 79 % busy), not latency-bound: 0.273 -> 0.307 ms.)
+  // issue-bound on the insertion shuffles (SM pipe 79 % busy), not latency-bound: 0.273 -> 0.307 ms.  And: visiting the
+  // query's own (x, y) column first so that the threshold tightens early -- fewer insertions, but the index arithmetic and
+  // the divergent skip of out-of-range columns cost more: 0.285 -> 0.326 ms.)
   for (int cx = max(0, fx - L); cx <= min(dx - 1, fx + L); ++cx)
     for (int cy = max(0, fy - L); cy <= min(dy - 1, fy + L); ++cy) {
       const int base = cx * (dy * dz) + cy * dz;

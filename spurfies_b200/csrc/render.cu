@@ -621,20 +621,20 @@ __global__ void k_tv(const float* __restrict__ pts, const float* __restrict__ fe
     float norm = warp_sum(w);
     float fi = feat[(size_t)i * 32 + lane];
     float gi = 0.0f;
+    float part = 0.0f;   // this channel's share of sum_k w_k |f_j - f_i|_1: ONE warp reduction per point, not one per neighbour
     for (int k = 0; k < K; ++k) {
       int j = __shfl_sync(SPF_FULL, my, k);
       float wk = __shfl_sync(SPF_FULL, w, k);
       if (j < 0) continue;
       float diff = feat[(size_t)j * 32 + lane] - fi;
-      float l1 = warp_sum(fabsf(diff));
-      tv_i += wk * l1;
+      part += wk * fabsf(diff);
       if (grad) {
         float gsc = grad_scale * wk / norm / (float)N * sgnf(diff);
         if (gsc != 0.0f) atomicAdd(&grad[(size_t)j * 32 + lane], gsc);
         gi -= gsc;
       }
     }
-    tv_i = tv_i / norm;
+    tv_i = warp_sum(part) / norm;
     if (grad && gi != 0.0f) atomicAdd(&grad[(size_t)i * 32 + lane], gi);
   }
   __shared__ float s_v[8];
