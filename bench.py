@@ -211,6 +211,11 @@ def run_ours(args):
     pairs_per_step = float(model._last["slots"].V) * 8  # last step's fine-pass pairs (representative)
     model._bench_cq = knn_candidate_stats(model)
     # ---------------- timed region 2: end to end from pinned host buffers, loss read back every step
+    # (one untimed pass through the prefetch path first: it creates the copy stream and the staging buffers)
+    step.prefetch(*split(hb[0]))
+    step.step_prefetched()
+    host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -219,8 +224,6 @@ def run_ours(args):
     # a side stream before step i's loss is read back, so it overlaps step i's kernels (TrainStep.prefetch)
     # The loss of every step is copied to pinned host memory right behind it and READ one step later, so the host is
     # always one launch ahead of the device (what a training loop that logs its loss does).
-    host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     step.prefetch(*split(hb[args.warmup % nb]))
     for i in range(args.steps):
         losses = step.step_prefetched()
