@@ -76,3 +76,16 @@ def test_edge_cases():
     assert out["pidx"][0, 0].tolist() == [0]
     st = g.stats()
     assert st["occupied_voxels"] == 2 and st["max_points_per_voxel"] == 2 and st["points_in_grid"] == 3
+
+
+def test_exact_ties_are_broken_by_point_id():
+    """Duplicate and equidistant points: the K nearest are chosen and ordered by (d^2, point id) -- the deterministic rule
+    the product kernels reproduce bit-exactly (the reference's own order depends on its atomics)."""
+    c, h = 0.125, 1.0 / 64.0   # exactly representable: ids 5, 6, 7 are equidistant from the query in fp32 arithmetic
+    dup = [[c, c, c]] * 5 + [[c + h, c, c], [c - h, c, c], [c, c + h, c]]
+    pts = torch.tensor([dup])
+    g = OracleGrid(pts, (0.025,) * 3, (3,) * 3, (3,) * 3, (-1, -1, -1, 1, 1, 1))
+    q = torch.tensor([[[c, c, c]]])
+    assert g.query_dense(q, 3, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2]
+    assert g.query_dense(q, 7, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2, 3, 4, 5, 6]
+    assert g.query_dense(q, 8, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2, 3, 4, 5, 6, 7]
