@@ -157,7 +157,7 @@ def run_ours(args):
     # weak scaling: every rank runs the full per-GPU batch; strong scaling: the batch is sharded over the ranks
     rays_gpu = wl["rays"] if wl["scaling"] == "weak" else wl["rays"] // world
     sc, model = build_scene(device, precision=args.precision, scene=wl["scene"], n_points=wl["n_points"])
-    step = TrainStep(model, world_size=world)
+    step = TrainStep(model, world_size=world, grad_compress=args.grad_compress)
     nb = 8
     hb = host_batches(nb, rank, n_rays=rays_gpu, cam_radius=sc["cam_radius"])
     db = [to_device(h, device) for h in hb]
@@ -292,7 +292,7 @@ def run_ours(args):
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"] % (wl["n_points"], wl["rays"]),
                    "rays_per_gpu": rays_gpu, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
-                   "cuda_graph": graphed, "cuda_graph_note": step.graph_error,
+                   "cuda_graph": graphed, "cuda_graph_note": step.graph_error, "grad_exchange": args.grad_compress or "fp32",
                    "l2": "distinct ray batch each step; per-step working set (saved activations, > 1 GB) >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last,
@@ -574,6 +574,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core field kernels (2e-2 tolerance); fp32: exact SIMT kernels (1e-4)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--grad-compress", default=None, choices=["bf16"],
+                    help="experimental, N > 1: all-reduce the latent-table gradients as bf16 (default: exact fp32 exchange)")
     ap.add_argument("--workload", default="train", choices=["train", "garden", "eval", "mesh"],
                     help="train: BASELINE configs[1] (the headline); garden: configs[2]; eval: configs[3]; mesh: configs[4]")
     ap.add_argument("--mesh-res", type=int, default=512)

@@ -51,16 +51,35 @@ class FlatGradReducer:
     is stable, so the reduction can be captured in a CUDA graph together with the rest of the step)."""
 
     def __init__(self, params: Iterable[torch.Tensor], world_size: int, group: Optional[dist.ProcessGroup] = None,
-                 align: int = 1):
+                 align: int = 1, bf16_prefix: int = 0):
+        """bf16_prefix (opt-in, default off): the first `bf16_prefix` elements of the flat buffer -- the [N, C] latent
+        tables, which are the first parameters and 96 % of the bytes -- travel as bf16 (rounded once before the sum,
+        the sum itself rounded per hop by the collective); the rest (MLP weights, beta) stays fp32.  Meant for the
+        bf16 precision mode, whose gradients already carry bf16-level noise; the fp32 mode keeps the exact reduction."""
         self.params: List[torch.Tensor] = list(params)
         self.world_size = int(world_size)
         self.group = group
         self.offsets, self.numel = flat_offsets(self.params, align)   # padding (if any) stays zero
         self._flat: Optional[torch.Tensor] = None
+        self.bf16_prefix = max(0, min(int(bf16_prefix), self.numel))
+        self._half: Optional[torch.Tensor] = None
 
     @property
     def bytes_per_step(self) -> int:
-        return 4 * self.numel
+        return 4 * self.numel - 2 * self.bf16_prefix
+
+    def _all_reduce_flat(self, flat: torch.Tensor) -> None:
+        n = self.bf16_prefix
+        if n == 0:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        if self._half is None or self._half.device != flat.device:
+            self._half = torch.empty(n, dtype=torch.bfloat16, device=flat.device)   # persistent: graph-capturable
+        self._half.copy_(flat[:n])
+        dist.all_reduce(self._half, op=dist.ReduceOp.SUM, group=self.group)
+        if n < self.numel:
+            dist.all_reduce(flat[n:], op=dist.ReduceOp.SUM, group=self.group)
+        flat[:n].copy_(self._half)
 
     def flat(self) -> torch.Tensor:
         if self._flat is None:
@@ -96,7 +115,7 @@ class FlatGradReducer:
             return
         flat = self.flat()
         if self.attached():
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._all_reduce_flat(flat)
             if average:
                 flat.mul_(1.0 / self.world_size)
             return
@@ -106,7 +125,7 @@ class FlatGradReducer:
                 flat[off:off + k].zero_()
             else:
                 flat[off:off + k].copy_(p.grad.reshape(-1))
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        self._all_reduce_flat(flat)
         if average:
             flat.mul_(1.0 / self.world_size)
         for p, off in zip(self.params, self.offsets):

@@ -87,6 +87,51 @@ def test_flat_grad_reducer_world2():
     assert res == [(0, True), (1, True)]
 
 
+def _worker_reduce_bf16(rank, world, port, q):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(17)
+    base = [torch.randn(300, 8, generator=g), torch.randn(300, 4, generator=g), torch.randn(16, 16, generator=g),
+            torch.randn(5, generator=g)]
+    w = [torch.nn.Parameter(torch.zeros_like(b)) for b in base]
+    n_lat = 300 * 8 + 300 * 4
+    red = FlatGradReducer(w, world, align=4, bf16_prefix=n_lat)   # the two "latent tables" travel as bf16
+    red.attach()
+    for p, b in zip(w, base):
+        p.grad.copy_(b * (rank + 1))
+    try:
+        red.reduce(average=False)
+    except RuntimeError as e:          # a gloo build without bf16 reductions
+        q.put((rank, "unsupported: " + str(e)[:80]))
+        dist.destroy_process_group()
+        return
+    want = [b * 3.0 for b in base]     # ranks contribute 1x and 2x
+    ok = True
+    for i, (p, t) in enumerate(zip(w, want)):
+        if i < 2:                      # bf16 round trip: 2^-8 relative per element, exact structure
+            ok = ok and bool(((p.grad - t).abs() <= 2.0 ** -7 * t.abs() + 1e-6).all()) and not torch.equal(p.grad, t)
+        else:                          # the fp32 tail is exact
+            ok = ok and torch.equal(p.grad, t)
+    ok = ok and red.bytes_per_step == 4 * red.numel - 2 * n_lat
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_reducer_bf16_prefix_world2():
+    """Opt-in compression of the latent-table part of the gradient exchange: bf16 for the prefix, fp32 for the rest."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_reduce_bf16, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    if any(isinstance(r[1], str) for r in res):
+        pytest.skip(str(res))
+    assert res == [(0, True), (1, True)]
+
+
 def _oracle_setup():
     from oracle import hotpath as H
     from spurfies_b200 import scenes
