@@ -29,3 +29,15 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_compiles_as_plain_c_and_cpp(tmp_path):
+    """The boundary is a C ABI: the header must be usable from C99 and C++ without CUDA or torch headers."""
+    import shutil
+    import subprocess
+    for cc, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "cpp")):
+        if shutil.which(cc) is None:
+            continue
+        src = tmp_path / f"use_header.{ext}"
+        src.write_text('#include "include/spurfies_b200.h"\nint main(void) { const char* (*f)(void) = spf_version; return f == 0; }\n')
+        subprocess.check_call([cc, std, "-Wall", "-Werror", "-fsyntax-only", "-I", ROOT, str(src)])
