@@ -348,6 +348,12 @@ def other_rooflines(prof, prof_steps, pairs, model, pk):
     # compositing: 28 B in + 4 B out per slot, + 28 B per ray
     R, S = model._last["t"].shape
     add("spf_composite_fwd", R * S * 32.0 + R * 28.0, "GB/s", hbm, "32 B/slot + 28 B/ray")
+    # gather backward (geometry latents): per valid pair 128 B of Jacobian row read + 128 B read-modify-write of the latent row
+    add("spf_sdf_bwd", pairs * 384.0, "GB/s", hbm, "384 B/pair (jw row + RMW of the latent gradient row)")
+    # sampler (1 iteration, train schedule): 128 x 8 B in + 64 x 4 B draws + 98 x 16 B out per ray
+    add("spf_sampler_iter", R * (128 * 8 + 64 * 4 + 98 * 16.0), "GB/s", hbm, "2 848 B/ray; latency / SFU bound (11 error-bound evaluations per ray)")
+    # TV regulariser: per point 8 neighbour rows gathered + 8 scattered (128 B each) + its own
+    add("spf_tv_fwd_bwd", N * (17 * 128.0), "GB/s", hbm, "17 x 128 B per neural point")
     # optimiser: p, g, m, v read + p, m, v, g written (fused clip + Adam + zero_grad), + one read of g for the norm
     n_par = float(sum(p.numel() for p in model.parameters() if p.requires_grad))
     add("spf_adam_step", n_par * 32.0, "GB/s", hbm, "32 B/parameter")

@@ -31,3 +31,31 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_reference_arm_other_ranks_do_no_work():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_other_rooflines_from_a_fake_profile():
+    """bench.other_rooflines (the per-kernel algorithmic-work rooflines beside the headline one) on a synthetic profile:
+    every kernel it knows gets achieved / peak / frac, missing kernels are skipped, nothing needs a GPU."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    names = ["spf_color_fwd_tc", "spf_color_bwd_tc", "spf_wgrad_tc_multi", "spf_head_fwd_tc", "spf_head_bwd_tc", "spf_knn_slots",
+             "spf_composite_fwd", "spf_adam_step", "spf_grad_sumsq", "spf_sdf_bwd", "spf_sampler_iter", "spf_tv_fwd_bwd"]
+    prof = {k: {"ms": 2.0, "calls": 2, "max_ms": 1.0} for k in names}
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1000))
+            self.neural_pts = torch.zeros(100, 3)
+            self._last = {"t": torch.zeros(4096, 80)}
+            self._bench_cq = {"queries": 1000, "candidates": 500000}
+
+    pk = bench.peaks()
+    out = bench.other_rooflines(prof, 2, 1.2e6, Fake(), pk)
+    assert set(out) == set(names)
+    for k, v in out.items():
+        assert v["unit"] in ("GB/s", "TFLOP/s") and v["peak"] > 0 and abs(v["frac"] - v["achieved"] / v["peak"]) < 1e-12
+        assert abs(v["ms_per_step"] - 1.0) < 1e-9
+    del prof["spf_tv_fwd_bwd"]
+    assert "spf_tv_fwd_bwd" not in bench.other_rooflines(prof, 2, 1.2e6, Fake(), pk)
