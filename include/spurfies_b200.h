@@ -345,8 +345,10 @@ int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int
                     void* dz1, void* dz2, void* dz3, float* drb3,
                     void* d_hb /* optional out: d_hbar as bf16 by compact sample row, tile layout, INSTEAD of d_hbar */,
                     void* stream);
-/* bf16 128B-swizzled k-block-major image of W [N][K] (row stride ld, fp32) or of its transpose (then W is [K][N]);
- * out holds ceil(K/64) * n_pad * 128 bytes. */
+/* 16-bit 128B-swizzled k-block-major image of W [N][K] (row stride ld, fp32) or of its transpose (then W is [K][N]);
+ * out holds ceil(K/64) * n_pad * 128 bytes.  `transpose` is a flag word: bit 0 = transpose, SPF_PACK_F16 = write fp16
+ * (the FORWARD weight images: forward operands are fp16, gradient-chain operands bf16) instead of bf16. */
+#define SPF_PACK_F16 2
 int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
                    void* stream);
 /* the same for up to SPF_PACK_MAX_JOBS images in one launch (the trainable weights are re-packed every step) */
@@ -372,6 +374,8 @@ int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const 
 typedef struct {
   const void* dz; const void* act; float* dW; float* db;
   int32_t lda, N;
+  int32_t fmt;      /* bit 0: dz is bf16 (else fp16); bit 1: act is bf16 (else fp16).  db needs a bf16 dz. */
+  int32_t reserved;
 } spf_wgrad_job;
 int spf_wgrad_tc_multi(const spf_wgrad_job* jobs /* HOST array */, int32_t n_jobs, const int32_t* count,
                        int32_t rows_per_unit, int64_t n_max, void* stream);

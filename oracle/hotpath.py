@@ -105,16 +105,17 @@ def mlp(x, layers, act_last=False):
     return x
 
 
-# Arithmetic model of the product's tensor-core ("bf16") mode for the trainable colour path, used ONLY to check that
-# mode: operands of every matrix product (inputs, weights, inter-layer activations) are rounded to bf16, products are
-# accumulated in fp32, biases / LeakyReLU / interpolation / sigmoid stay fp32; the per-ray PE3(dir) columns of R.0 stay
+# Arithmetic model of the product's tensor-core ("bf16") mode for the trainable colour path, a DIAGNOSTIC for that mode
+# (tools/bf16_grad_study.py, printed by the bf16 test; parity itself is asserted against the reference golden): operands
+# of every FORWARD matrix product (inputs, weights, inter-layer activations) are rounded to fp16 -- the kernels' forward
+# operand format, csrc/umma.cuh -- products are accumulated in fp32, biases / LeakyReLU / interpolation / sigmoid stay fp32; the per-ray PE3(dir) columns of R.0 stay
 # fp32; F_color.6 (linear, no activation: pointneus_disent.py:83) is applied after the neighbour interpolation.
 # Off by default: the oracle then follows the reference's fp32 graph op for op.
 BF16_OPERANDS = False
 
 
 def _bf(t):
-    return t.to(torch.bfloat16).float()  # differentiable (identity gradient)
+    return t.to(torch.float16).float()  # differentiable (identity gradient)
 
 
 def _color_bf16_operands(p: Params, fin, dirs_v, w, norm, idx, V):

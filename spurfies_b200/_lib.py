@@ -64,7 +64,7 @@ class PackJob(C.Structure):
 
 class WgradJob(C.Structure):
     _fields_ = [("dz", C.c_void_p), ("act", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p), ("lda", C.c_int32),
-                ("N", C.c_int32)]
+                ("N", C.c_int32), ("fmt", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ColorWeightsF32(C.Structure):

@@ -243,7 +243,7 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
 // are partitioned among the jobs in proportion to their bytes per row, so every CTA still streams one product but over a
 // longer row range -- one launch / TMEM allocation / tail instead of one per layer, and the fp32 atomic merge traffic
 // (256 x N floats per CTA) is paid once per CTA instead of once per CTA and layer.  Body = k_wgrad_tiled.
-struct WgJobDev { const uint8_t* dz; const uint8_t* act; float* dW; float* db; int act_nkb, N, cta0, ncta; };
+struct WgJobDev { const uint8_t* dz; const uint8_t* act; float* dW; float* db; int act_nkb, N, cta0, ncta, fmt; };
 struct WgJobsDev { WgJobDev j[SPF_WGRAD_MAX_JOBS]; int n; };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -275,7 +275,7 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
   const int my_tiles = (ntiles - bid + nb - 1) / nb;
   const int N = J.N;
   const int act_panels = (N + 63) >> 6;
-  const uint32_t idesc = idesc_bf16_mn(128, N);
+  const uint32_t idesc = idesc_f16k_mn(128, N, J.fmt);   // dZ (A) and the saved activation (B) may differ in format
   float bsum = 0.0f;
 
   auto load_tile = [&](int it) {   // one thread
@@ -373,7 +373,8 @@ extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, con
     if (c < 1) c = 1;
     if (q == n_jobs - 1 || used + c > sms - (n_jobs - 1 - q)) c = sms - (n_jobs - 1 - q) - used;
     const spf_wgrad_job& J = jobs[q];
-    d.j[q] = {(const uint8_t*)J.dz, (const uint8_t*)J.act, J.dW, J.db, J.lda >> 6, J.N, used, c};
+    if (J.db && !(J.fmt & 1)) return SPF_ERR_UNSUPPORTED;   // the bias-gradient column sums read dZ as bf16
+    d.j[q] = {(const uint8_t*)J.dz, (const uint8_t*)J.act, J.dW, J.db, J.lda >> 6, J.N, used, c, J.fmt & 3};
     used += c;
   }
   SPF_CUDA(cudaFuncSetAttribute(k_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
@@ -416,9 +417,11 @@ __global__ void k_pack_sw128(const float* __restrict__ W, int ld, int N, int K, 
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kb * 64 + c * 8 + e;
-    v[e] = (n < N && k < K) ? (transpose ? W[(size_t)k * ld + n] : W[(size_t)n * ld + k]) : 0.0f;
+    v[e] = (n < N && k < K) ? ((transpose & 1) ? W[(size_t)k * ld + n] : W[(size_t)n * ld + k]) : 0.0f;
   }
-  out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  out[i] = (transpose & SPF_PACK_F16)
+               ? make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]))
+               : make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 extern "C" int spf_pack_sw128(const float* W, int32_t ld, int32_t N, int32_t K, int32_t transpose, int32_t n_pad, void* out,
@@ -444,9 +447,12 @@ __global__ void k_pack_sw128_batch(PackJobsDev jobs) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kb * 64 + c * 8 + e;
-    v[e] = (n < J.N && k < J.K) ? (J.transpose ? J.W[(size_t)k * J.ld + n] : J.W[(size_t)n * J.ld + k]) : 0.0f;
+    v[e] = (n < J.N && k < J.K) ? ((J.transpose & 1) ? J.W[(size_t)k * J.ld + n] : J.W[(size_t)n * J.ld + k]) : 0.0f;
   }
-  reinterpret_cast<uint4*>(J.out)[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  reinterpret_cast<uint4*>(J.out)[i] =
+      (J.transpose & SPF_PACK_F16)
+          ? make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]))
+          : make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 extern "C" int spf_pack_sw128_batch(const spf_pack_job* jobs, int32_t n_jobs, void* stream_) {

@@ -44,14 +44,14 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b1..b4, v5
   if (tid == 0) {
-    ch.L[0] = {W.w1p, 1, 3, 256};
-    ch.L[1] = {W.w2p, 4, 16, 256};
-    ch.L[2] = {W.w3p, 4, 16, 256};
-    ch.L[3] = {W.w4p, 4, 16, 256};
-    ch.L[4] = {W.w4tp, 4, 16, 256};
-    ch.L[5] = {W.w3tp, 4, 16, 256};
-    ch.L[6] = {W.w2tp, 4, 16, 256};
-    ch.L[7] = {W.w1tp, 4, 16, 48};
+    ch.L[0] = {W.w1p, 1, 3, 256, FMT_F16};      // forward layers: fp16 operands (umma.cuh)
+    ch.L[1] = {W.w2p, 4, 16, 256, FMT_F16};
+    ch.L[2] = {W.w3p, 4, 16, 256, FMT_F16};
+    ch.L[3] = {W.w4p, 4, 16, 256, FMT_F16};
+    ch.L[4] = {W.w4tp, 4, 16, 256, FMT_BF16};   // d sdf / d input chain: bf16 operands
+    ch.L[5] = {W.w3tp, 4, 16, 256, FMT_BF16};
+    ch.L[6] = {W.w2tp, 4, 16, 256, FMT_BF16};
+    ch.L[7] = {W.w1tp, 4, 16, 48, FMT_BF16};
     ch.n = WITH_J ? 8 : 4;
   }
   for (int i = tid; i < 256; i += THREADS) {
@@ -95,22 +95,22 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
-          uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+          uint4 u = make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
           *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
         }
       } else {
         const float4* src = reinterpret_cast<const float4*>(feat_g + (size_t)(p >= 0 ? p : 0) * 32 + 24);
         float4 a = p >= 0 ? src[0] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[1] : make_float4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(sA + sw128_off(row, 3)) =
-            make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-        float hi[3], lo[3];
+            make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
+        float hi[3], lo[3];   // x - p as fp16 hi + lo (22 significant bits) against the same weight columns
 #pragma unroll
         for (int a3 = 0; a3 < 3; ++a3) {
-          hi[a3] = __bfloat162float(__float2bfloat16_rn(xp[a3]));
+          hi[a3] = f16_round(xp[a3]);
           lo[a3] = xp[a3] - hi[a3];
         }
         *reinterpret_cast<uint4*>(sA + sw128_off(row, 4)) =
-            make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), 0u);
+            make_uint4(pack_f16(hi[0], hi[1]), pack_f16(hi[2], lo[0]), pack_f16(lo[1], lo[2]), 0u);
         *reinterpret_cast<uint4*>(sA + sw128_off(row, 5)) = make_uint4(0, 0, 0, 0);
       }
       if ((tid & 255) == 0) TL(3, t, it);
@@ -151,8 +151,8 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
               const float4 bq = bias4[c * 4 + q];
               float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
               z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
-              pk[2 * q] = pack_bf16(z0, z1);
-              pk[2 * q + 1] = pack_bf16(z2, z3);
+              pk[2 * q] = pack_f16(z0, z1);
+              pk[2 * q + 1] = pack_f16(z2, z3);
               if (WITH_J) {
                 sb = (sb >> 2) | (pk[2 * q] & 0x80008000u);
                 sb = (sb >> 2) | (pk[2 * q + 1] & 0x80008000u);
@@ -319,9 +319,9 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b1..b3
   if (tid == 0) {
-    ch.L[0] = {W.w1p, 2, 7, 256};
-    ch.L[1] = {W.w2p, 4, 16, 256};
-    ch.L[2] = {W.w3p, 4, 16, 256};
+    ch.L[0] = {W.w1p, 2, 7, 256, FMT_F16};
+    ch.L[1] = {W.w2p, 4, 16, 256, FMT_F16};
+    ch.L[2] = {W.w3p, 4, 16, 256, FMT_F16};
     ch.n = 3;
   }
   for (int i = tid; i < 256; i += THREADS) { s_bias[i] = W.b1[i]; s_bias[256 + i] = W.b2[i]; s_bias[512 + i] = W.b3[i]; }
@@ -365,7 +365,7 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 a = p >= 0 ? src[2 * q] : make_float4(0, 0, 0, 0), b = p >= 0 ? src[2 * q + 1] : make_float4(0, 0, 0, 0);
-          uint4 u = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+          uint4 u = make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
           *reinterpret_cast<uint4*>(sA + sw128_off(row, q)) = u;
         }
       } else {
@@ -389,8 +389,8 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
         for (int j = 39; j < 48; ++j) pe[j] = 0.0f;
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-          uint4 u = make_uint4(pack_bf16(pe[8 * q], pe[8 * q + 1]), pack_bf16(pe[8 * q + 2], pe[8 * q + 3]),
-                               pack_bf16(pe[8 * q + 4], pe[8 * q + 5]), pack_bf16(pe[8 * q + 6], pe[8 * q + 7]));
+          uint4 u = make_uint4(pack_f16(pe[8 * q], pe[8 * q + 1]), pack_f16(pe[8 * q + 2], pe[8 * q + 3]),
+                               pack_f16(pe[8 * q + 4], pe[8 * q + 5]), pack_f16(pe[8 * q + 6], pe[8 * q + 7]));
           *reinterpret_cast<uint4*>(sA + 16384 + sw128_off(row, q)) = u;
         }
       }
@@ -427,8 +427,8 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
             float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
             z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
             vv[4 * q] = z0; vv[4 * q + 1] = z1; vv[4 * q + 2] = z2; vv[4 * q + 3] = z3;
-            pk[2 * q] = pack_bf16(z0, z1);
-            pk[2 * q + 1] = pack_bf16(z2, z3);
+            pk[2 * q] = pack_f16(z0, z1);
+            pk[2 * q + 1] = pack_f16(z2, z3);
             sb = (sb >> 2) | (pk[2 * q] & 0x80008000u);
             sb = (sb >> 2) | (pk[2 * q + 1] & 0x80008000u);
           }
@@ -467,7 +467,7 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
               if (hb_c) {   // bf16 copy by COMPACT slot in the tile layout: the radiance head's A operand, loaded by TMA
                 const int vs = tile * 16 + (row >> 3), col = c0 + off;
                 *reinterpret_cast<uint32_t*>(hb_c + (size_t)(vs >> 7) * (4 * 16384) + (col >> 6) * 16384 +
-                                             sw128_off(vs & 127, (col & 63) >> 3) + (col & 7) * 2) = pack_bf16(a2[0], a2[1]);
+                                             sw128_off(vs & 127, (col & 63) >> 3) + (col & 7) * 2) = pack_f16(a2[0], a2[1]);
               }
             }
           }
@@ -534,9 +534,9 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
   const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   if (tid == 0) {
-    ch.L[0] = {W.w3tp, 4, 16, 256};
-    ch.L[1] = {W.w2tp, 4, 16, 256};
-    ch.L[2] = {W.w1ftp, 4, 16, 64};
+    ch.L[0] = {W.w3tp, 4, 16, 256, FMT_BF16};
+    ch.L[1] = {W.w2tp, 4, 16, 256, FMT_BF16};
+    ch.L[2] = {W.w1ftp, 4, 16, 64, FMT_BF16};
     ch.n = 3;
   }
   const uint32_t tmem = setup(smem, B);
@@ -699,10 +699,10 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);   // b4, rb2, rb3
   if (tid == 0) {
-    ch.L[0] = {W.w4p, 4, 16, 256};
-    ch.L[1] = {W.r1fp, 4, 16, 256};
-    ch.L[2] = {W.r2p, 4, 16, 256};
-    ch.L[3] = {W.r3p, 4, 16, 32};
+    ch.L[0] = {W.w4p, 4, 16, 256, FMT_F16};
+    ch.L[1] = {W.r1fp, 4, 16, 256, FMT_F16};
+    ch.L[2] = {W.r2p, 4, 16, 256, FMT_F16};
+    ch.L[3] = {W.r3p, 4, 16, 32, FMT_F16};
     ch.n = 4;
   }
   for (int i = tid; i < 256; i += THREADS) { s_bias[i] = W.b4[i]; s_bias[256 + i] = W.rb2[i]; }
@@ -760,8 +760,8 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(pdst + sw128_off(row, q)) =
-              make_uint4(pack_bf16(pe[8 * q], pe[8 * q + 1]), pack_bf16(pe[8 * q + 2], pe[8 * q + 3]),
-                         pack_bf16(pe[8 * q + 4], pe[8 * q + 5]), pack_bf16(pe[8 * q + 6], pe[8 * q + 7]));
+              make_uint4(pack_f16(pe[8 * q], pe[8 * q + 1]), pack_f16(pe[8 * q + 2], pe[8 * q + 3]),
+                         pack_f16(pe[8 * q + 4], pe[8 * q + 5]), pack_f16(pe[8 * q + 6], pe[8 * q + 7]));
       }
       if (hbar) {
         // A0 = hbar[slot] (bf16), gathered by row; saved as hb
@@ -842,8 +842,8 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           for (int q = 0; q < 4; ++q) {
             float z0 = vv[4 * q] + bq[q].x, z1 = vv[4 * q + 1] + bq[q].y, z2 = vv[4 * q + 2] + bq[q].z, z3 = vv[4 * q + 3] + bq[q].w;
             z0 = fmaxf(z0, slope * z0); z1 = fmaxf(z1, slope * z1); z2 = fmaxf(z2, slope * z2); z3 = fmaxf(z3, slope * z3);
-            pk[2 * q] = pack_bf16(z0, z1);
-            pk[2 * q + 1] = pack_bf16(z2, z3);
+            pk[2 * q] = pack_f16(z0, z1);
+            pk[2 * q + 1] = pack_f16(z2, z3);
           }
           const int c0 = half * 128 + c * 16;
           uint8_t* dstA = sA + (c0 >> 6) * 16384;
@@ -914,10 +914,10 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
   const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   if (tid == 0) {
-    ch.L[0] = {W.r3tp, 1, 1, 256};
-    ch.L[1] = {W.r2tp, 4, 16, 256};
-    ch.L[2] = {W.r1ftp, 4, 16, 256};
-    ch.L[3] = {W.w4tp, 4, 16, 256};
+    ch.L[0] = {W.r3tp, 1, 1, 256, FMT_BF16};
+    ch.L[1] = {W.r2tp, 4, 16, 256, FMT_BF16};
+    ch.L[2] = {W.r1ftp, 4, 16, 256, FMT_BF16};
+    ch.L[3] = {W.w4tp, 4, 16, 256, FMT_BF16};
     ch.n = 4;
   }
   const uint32_t tmem = setup(smem, B);

@@ -106,6 +106,7 @@ struct Layer {
   int nkb;              // k-blocks of 64
   int ksteps;           // K / 16 actually multiplied
   int N;                // output columns (multiple of 16, <= 256); each CTA holds N/2 weight rows
+  int fmt;              // operand formats (umma.cuh): FMT_F16 = forward layers, FMT_BF16 = gradient layers
 };
 struct Chain {
   Layer L[MAX_LAYERS];
@@ -192,7 +193,7 @@ __device__ __forceinline__ void mma_loop(const Chain& ch, int n_iter, uint8_t* s
   for (int it = 0; it < n_iter; ++it)
     for (int l = 0; l < ch.n; ++l) {
       const Layer L = ch.L[l];
-      const uint32_t idesc = idesc_bf16(256, L.N);
+      const uint32_t idesc = idesc_f16k(256, L.N, L.fmt);
       uint32_t slot = slot0, use = use0;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -267,14 +268,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
-// write 16 consecutive columns [c0, c0+16) of this thread's row as bf16 into an A tile
+// write 16 consecutive columns [c0, c0+16) of this thread's row as fp16 (a FORWARD operand) into an A tile
 __device__ __forceinline__ void store_a16(uint8_t* sA, int row, int c0, const float* v) {
   const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint4 u;
-    u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
     *reinterpret_cast<uint4*>(sA + kb * 16384 + sw128_off(row, ch0 + q)) = u;
   }
 }

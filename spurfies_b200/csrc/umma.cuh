@@ -89,6 +89,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Operand formats of kind::f16 (instruction-descriptor bits 7..9 = A, 10..12 = B: 0 = fp16, 1 = bf16).  FORWARD operands
+// (inputs, activations, weights) are fp16: 11 significant bits instead of bf16's 8, at the same tensor throughput, so 8x
+// fewer LeakyReLU pre-activations land on the wrong side of zero than with bf16 operands (each such flip moves that
+// unit's whole gradient contribution: tools/bf16_grad_study.py).  GRADIENT operands (dZ, the d sdf / d input chain) stay
+// bf16: they span many decades and are not range-safe in fp16.  `fmt` bit 0 / bit 1 = A / B operand is bf16.
+constexpr int FMT_F16 = 0, FMT_A_BF16 = 1, FMT_B_BF16 = 2, FMT_BF16 = 3;
+__host__ __device__ constexpr uint32_t idesc_f16k(int M, int N, int fmt) {
+  return (1u << 4) | ((uint32_t)(fmt & 1) << 7) | ((uint32_t)((fmt >> 1) & 1) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f16k_mn(int M, int N, int fmt) {
+  return idesc_f16k(M, N, fmt) | (1u << 15) | (1u << 16);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, one K=16 step; issued by ONE thread
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -214,6 +227,19 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 -> packed fp16 (a in the low half), round to nearest, saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float f16_round(float a) {   // the value pack_f16 stores, back in fp32
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(a));
+  float r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"(h));
+  return r;
 }
 
 }  // namespace tc

@@ -28,9 +28,13 @@ ROW_PAD = 128  # saved per-pair tensors are written in whole tiles
 class Arena:
     """Persistent device buffers for the big per-step intermediates (saved activations, Jacobian rows, dZ rows).
     They are sized for the worst case (every slot valid) and would otherwise be cudaMalloc'ed and freed every step
-    (several GB): the caching allocator then dominates the step.  One step is in flight per model and everything is
-    stream-ordered, so reusing the same storage step after step is safe."""
+    (several GB): the caching allocator then dominates the step.  Everything is stream-ordered, so reusing the same
+    storage step after step is safe -- as long as ONE forward per (model, query tag) is in flight between a forward and
+    its backward.  That is enforced, not assumed: buffer names carry a per-model prefix (two models never share
+    storage), every SlotSet claims a generation of its tag, and the backward passes call ``SlotSet.check_live()``, which
+    raises if a later forward of the same model re-issued the buffers holding their saved activations."""
     _bufs = {}
+    _gen = {}
 
     @classmethod
     def get(cls, name: str, shape, dtype, device) -> torch.Tensor:
@@ -46,6 +50,16 @@ class Arena:
         return buf[:nbytes].view(dtype).view(*shape)
 
     @classmethod
+    def claim(cls, tag: str, device) -> int:
+        key = (tag, str(device))
+        cls._gen[key] = cls._gen.get(key, 0) + 1
+        return cls._gen[key]
+
+    @classmethod
+    def current(cls, tag: str, device) -> int:
+        return cls._gen.get((tag, str(device)), 0)
+
+    @classmethod
     def clear(cls):
         cls._bufs.clear()
 
@@ -53,9 +67,11 @@ class Arena:
 class SlotSet:
     """Compacted list of the valid slots of one query (utils.py:90-113 glue, without the host sync)."""
 
-    def __init__(self, pidx: torch.Tensor, tag: str = "q"):
+    def __init__(self, pidx: torch.Tensor, tag: str = "q", owner: str = ""):
         assert pidx.dtype == torch.int32 and pidx.is_contiguous()
-        self.tag = tag  # names this query's arena buffers ("fine", "coarse", "pseudo", ...)
+        self.owner = owner       # per-model prefix of every arena buffer this query uses
+        self.tag = owner + tag   # names this query's arena buffers ("fine", "points", "pseudo", ...)
+        self.gen = Arena.claim(self.tag, pidx.device)
         self.K = pidx.shape[-1]
         self.pidx = pidx.view(-1, self.K)
         self.n = self.pidx.shape[0]
@@ -77,6 +93,15 @@ class SlotSet:
 
     def valid_mask(self) -> torch.Tensor:
         return self.pidx[:, 0] >= 0
+
+    def check_live(self) -> None:
+        """Called by every backward that reads activations saved in the arena under this query's tag."""
+        cur = Arena.current(self.tag, self.pidx.device)
+        if cur != self.gen:
+            raise RuntimeError(
+                f"spurfies_b200: the saved activations of query '{self.tag}' (generation {self.gen}) were overwritten by a "
+                f"later forward of the same model (generation {cur}) before this backward ran.  Run backward() before the "
+                "next forward / render / pseudo_sdf call of this model, or use a second model instance.")
 
     def rows_alloc(self, per_slot: int) -> int:
         return self.n * per_slot + ROW_PAD
@@ -113,9 +138,11 @@ class GeoPack:
                 s.v5, s.c5 = v5.data_ptr(), c5
                 s.w1, s.w2, s.w3, s.w4 = (W[i].data_ptr() for i in range(4))
                 self.f32 = s
-                # bf16 tensor-core images (mlp_tc.cu): x - p enters twice (bf16 hi + lo) against the same weights
+                # tensor-core images (mlp_tc2.cu): x - p enters twice (fp16 hi + lo) against the same weights
                 W1ext = torch.cat([W[0][:, :32], W[0][:, 32:35], W[0][:, 32:35]], dim=1)
-                self.tc_imgs = [pack_sw128(W1ext), pack_sw128(W[1]), pack_sw128(W[2]), pack_sw128(W[3]),
+                f16 = torch.float16   # forward operands are fp16, the d sdf / d input chain's bf16 (csrc/umma.cuh)
+                self.tc_imgs = [pack_sw128(W1ext, dtype=f16), pack_sw128(W[1], dtype=f16), pack_sw128(W[2], dtype=f16),
+                                pack_sw128(W[3], dtype=f16),
                                 pack_sw128(W[3].t()), pack_sw128(W[2].t()), pack_sw128(W[1].t()),
                                 pack_sw128(W[0].t(), n_pad=48)]
                 t = GeoWeightsTC()
@@ -181,6 +208,8 @@ class GeoSDF(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_sdf, _):
         slots = ctx.slots
+        if ctx.jw is not None:
+            slots.check_live()
         gfeat = None
         d_sdf = d_sdf.contiguous()
         if ctx.jw is not None:
@@ -208,20 +237,20 @@ def _img(name, dev, nbytes):
     return Arena.get("img." + name, (nbytes,), torch.uint8, dev)
 
 
-def _color_struct_tc(W, b):
+def _color_struct_tc(W, b, owner=""):
     """bf16 weight images for k_color_fwd_tc / k_color_bwd_tc (input columns permuted to [c (64) | PE6 (39)]),
-    packed on the device by one spf_pack_sw128_batch launch into persistent buffers."""
+    packed on the device by one spf_pack_sw128_batch launch into persistent (per-model) buffers."""
     dev = W[0].device
     jobs = []
-    w1p = _img("c.w1p", dev, 65536)
-    pack_sw128_dev(w1p, W[0], 256, 64, col_off=39, batch=jobs)                       # k-block 0: latent columns
-    pack_sw128_dev(w1p, W[0], 256, 39, col_off=0, row_off_bytes=32768, batch=jobs)   # k-block 1: PE6 columns
+    w1p = _img(owner + "c.w1p", dev, 65536)
+    pack_sw128_dev(w1p, W[0], 256, 64, col_off=39, batch=jobs, f16=True)                       # k-block 0: latent columns
+    pack_sw128_dev(w1p, W[0], 256, 39, col_off=0, row_off_bytes=32768, batch=jobs, f16=True)   # k-block 1: PE6 columns
     imgs = [w1p]
     for nm, w, tr in (("c.w2p", W[1], False), ("c.w3p", W[2], False), ("c.w3tp", W[2], True), ("c.w2tp", W[1], True)):
-        im = _img(nm, dev, 131072)
-        pack_sw128_dev(im, w, 256, 256, transpose=tr, batch=jobs)
+        im = _img(owner + nm, dev, 131072)
+        pack_sw128_dev(im, w, 256, 256, transpose=tr, batch=jobs, f16=not tr)   # forward fp16, dgrad (transposed) bf16
         imgs.append(im)
-    w1ftp = _img("c.w1ftp", dev, 32768)
+    w1ftp = _img(owner + "c.w1ftp", dev, 32768)
     pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39, batch=jobs)     # (W1[:, 39:103])^T : [64][256]
     imgs.append(w1ftp)
     pack_flush(jobs)   # one launch
@@ -250,12 +279,15 @@ class _ZeroPool:
 
 
 def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None):
-    """[(dz, act, lda, N, want_db)] -> [(dW [256,N], db [256] or None)]: all products in ONE spf_wgrad_tc_multi launch (every
-    operand in the tile layout, lda a multiple of 64); no host sync.  ``targets[i] = (dW_grad, db_grad)`` (either may be
+    """[(dz, act, lda, N, want_db[, fmt])] -> [(dW [256,N], db [256] or None)]: all products in ONE spf_wgrad_tc_multi launch
+    (every operand in the tile layout, lda a multiple of 64); no host sync.  fmt (default 1): bit 0 = dz is bf16, bit 1 =
+    act is bf16 -- normally dz is a bf16 gradient tile and act an fp16 saved forward activation.  ``targets[i] = (dW_grad, db_grad)`` (either may be
     None) makes job i accumulate straight into those gradient buffers (see _direct_grad); None is then returned for them."""
     arr = (_lib.WgradJob * len(jobs))()
     out = []
-    for i, (dz, act, lda, N, want_db) in enumerate(jobs):
+    for i, job in enumerate(jobs):
+        dz, act, lda, N, want_db = job[:5]
+        arr[i].fmt = job[5] if len(job) > 5 else 1
         tW, tb = targets[i] if targets is not None else (None, None)
         dW = tW if tW is not None else pool.take(256, N)
         db = (tb if tb is not None else pool.take(256)) if want_db else None
@@ -277,7 +309,7 @@ class ColorField(torch.autograd.Function):
         tcm = PRECISION["mode"] == "bf16"
         W = [w.detach().float().contiguous() for w in (W1, W2, W3)]
         b = [v.detach().float().contiguous() for v in (b1, b2, b3)]
-        s, keep = (_color_struct_tc if tcm else _color_struct)(W, b)
+        s, keep = _color_struct_tc(W, b, slots.owner) if tcm else _color_struct(W, b)
         n, K = slots.n, slots.K
         tg = slots.tag
         hbar = Arena.get(tg + ".hbar", (n, 256), torch.float32, dev)  # read back only at valid slots
@@ -285,7 +317,7 @@ class ColorField(torch.autograd.Function):
         rows = slots.rows_alloc(K)
         in0 = h1 = h2 = m3 = wn = None
         if need:
-            adt = torch.bfloat16 if tcm else torch.float32
+            adt = torch.float16 if tcm else torch.float32
             in0 = Arena.get(tg + ".in0", (rows, 128 if tcm else 104), adt, dev)  # tc: tile layout, 2 k-blocks
             h1 = Arena.get(tg + ".h1", (rows, 256), adt, dev)
             h2 = Arena.get(tg + ".h2", (rows, 256), adt, dev)
@@ -294,7 +326,7 @@ class ColorField(torch.autograd.Function):
         if tcm:
             # the kernel also leaves a bf16 copy of hbar indexed by COMPACT slot in the tile layout: the radiance head
             # bulk-copies it as its A operand (and its F_color.6 weight gradient reads it) instead of gathering fp32 rows
-            hb = Arena.get(tg + ".hhb", (slots.rows_alloc(1), 256), torch.bfloat16, dev)
+            hb = Arena.get(tg + ".hhb", (slots.rows_alloc(1), 256), torch.float16, dev)
             call("spf_color_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(x.contiguous()), ptr(slots.pidx),
                  K, ptr(pts), ptr(feat_c.detach()), float(rbf), ptr(hbar), ptr(in0), ptr(h1), ptr(h2), ptr(m3), ptr(wn),
                  ptr(hb), stream())
@@ -312,6 +344,7 @@ class ColorField(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_hbar):
         slots, tcm = ctx.slots, ctx.tcm
+        slots.check_live()
         s, keep, W, b, in0, h1, h2, m3, wn = ctx.saved_t
         dev = d_hbar.device
         rows = slots.rows_alloc(slots.K)
@@ -378,8 +411,8 @@ class RadianceHead(torch.autograd.Function):
                                                ("h.r2p", W[2], 256, 256, False, 256, 0), ("h.r3p", W[3], 3, 256, False, 32, 0),
                                                ("h.r3tp", W[3], 256, 3, True, 256, 0), ("h.r2tp", W[2], 256, 256, True, 256, 0),
                                                ("h.r1ftp", W[1], 256, 256, True, 256, 21), ("h.w4tp", W[0], 256, 256, True, 256, 0)):
-                im = _img(nm, dev, image_bytes(npad, K_))
-                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co, batch=jobs)
+                im = _img(slots.owner + nm, dev, image_bytes(npad, K_))
+                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co, batch=jobs, f16=not tr)
                 imgs.append(im)
             pack_flush(jobs)
             s = HeadWeightsTC()
@@ -395,12 +428,12 @@ class RadianceHead(torch.autograd.Function):
             if from_color:
                 hb = cached[0]
             elif need:
-                hb = Arena.get(tg + ".hhb", (rows, 256), torch.bfloat16, dev)
+                hb = Arena.get(tg + ".hhb", (rows, 256), torch.float16, dev)
             if need:
-                f = Arena.get(tg + ".hf", (rows, 256), torch.bfloat16, dev)
-                a1 = Arena.get(tg + ".ha1", (rows, 256), torch.bfloat16, dev)
-                a2 = Arena.get(tg + ".ha2", (rows, 256), torch.bfloat16, dev)
-                pe = Arena.get(tg + ".hpe", (rows, 64), torch.bfloat16, dev)   # tile layout, one k-block (32 columns used)
+                f = Arena.get(tg + ".hf", (rows, 256), torch.float16, dev)
+                a1 = Arena.get(tg + ".ha1", (rows, 256), torch.float16, dev)
+                a2 = Arena.get(tg + ".ha2", (rows, 256), torch.float16, dev)
+                pe = Arena.get(tg + ".hpe", (rows, 64), torch.float16, dev)   # tile layout, one k-block (32 columns used)
             call("spf_head_fwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, None if from_color else ptr(hbar_c),
                  ptr(zpe), ptr(dirs), int(Smax), ptr(rgb), ptr(hb), ptr(f), ptr(a1), ptr(a2), ptr(pe), stream())
             ctx.saved_t = (s, imgs, W, b, (hb, pe), rgb.detach(), f, a1, a2, dirs)
@@ -427,6 +460,7 @@ class RadianceHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb):
         slots, tcm = ctx.slots, ctx.tcm
+        slots.check_live()
         s, keep, W, b, hb, rgb, f, a1, a2, dirs = ctx.saved_t
         dev = d_rgb.device
         n = slots.n
@@ -456,7 +490,7 @@ class RadianceHead(torch.autograd.Function):
             # every operand is in the tile layout (pe and dz3 with a single k-block)
             (dW4, db4), (dR1f, drb1), (dR1pe, _), (dR2, drb2), (dR3t, _) = _wgrad_multi(
                 [(dzf, hb, 256, 256, True), (dz1, f, 256, 256, True), (dz1, pe, 64, 32, False), (dz2, a1, 256, 256, True),
-                 (a2, dz3, 64, 16, False)], slots, 1, pool,               # (a2^T @ dz3) = dR3^T, [256,16]
+                 (a2, dz3, 64, 16, False, 2)], slots, 1, pool,            # (a2^T @ dz3) = dR3^T, [256,16]: A fp16, B bf16
                 targets=[(tw[0], tw[1]), (None, tw[3]), (None, None), (tw[4], tw[5]), (None, None)])
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
             dR3 = dR3t[:, :3].t().contiguous()
@@ -526,12 +560,12 @@ class PseudoPointLoss(torch.autograd.Function):
     x = cam + dist * dir and d sdf / d x).  Replaces ~40 torch launches of mask / where / sum / sign glue per step."""
 
     @staticmethod
-    def forward(ctx, feat_g, dist, cam_loc, ray_dirs, nvalid, grid, k, r, pack, pts, rbf):
+    def forward(ctx, feat_g, dist, cam_loc, ray_dirs, nvalid, grid, k, r, pack, pts, rbf, owner=""):
         dev = dist.device
         R = dist.shape[0]
         x = torch.empty(R, 3, dtype=torch.float32, device=dev)
         call("spf_ray_points", ptr(cam_loc), ptr(ray_dirs), ptr(dist.detach().contiguous()), R, ptr(x), stream())
-        slots = SlotSet(grid.query_points(x, k, r), "pseudo")
+        slots = SlotSet(grid.query_points(x, k, r), "pseudo", owner)
         feat_needs, dist_needs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         sdf, grad, jw = geo_sdf_raw(pack, slots, x, pts, feat_g.detach(), rbf, dist_needs, feat_needs)
         value = torch.empty(1, dtype=torch.float32, device=dev)
@@ -547,6 +581,8 @@ class PseudoPointLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         slots = ctx.slots
+        if ctx.jw is not None:
+            slots.check_live()
         u_sdf, u_dist = ctx.u
         gfeat = None
         if ctx.jw is not None:
@@ -556,7 +592,7 @@ class PseudoPointLoss(torch.autograd.Function):
             call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
                  ptr((u_sdf * g).contiguous()), ptr(target), stream())
         d_dist = u_dist * g if u_dist is not None else None
-        return gfeat, d_dist, None, None, None, None, None, None, None, None, None
+        return gfeat, d_dist, None, None, None, None, None, None, None, None, None, None
 
 
 class TVRegul(torch.autograd.Function):

@@ -201,6 +201,8 @@ class ErrorBoundSampler_pn:
 
 
 class PointVolSDF(nn.Module):
+    _instances = 0
+
     def __init__(self, conf, scan_id=None, dataset=None, neural_points: Optional[torch.Tensor] = None,
                  neural_colors: Optional[torch.Tensor] = None, device="cuda", ranges=None,
                  max_points_per_voxel: int = 26, max_occ_voxels: int = 20000, precision: str = "fp32"):
@@ -254,6 +256,8 @@ class PointVolSDF(nn.Module):
         self.ray_sampler = ErrorBoundSampler_pn(self.scene_bounding_sphere, **conf.get_config("ray_sampler"))
         self._geo_pack = GeoPack()
         self._self_knn = None
+        PointVolSDF._instances += 1
+        self._owner = f"m{PointVolSDF._instances}."   # prefix of this model's arena buffers (fields.Arena)
         self.to(device)
 
     # ------------------------------------------------------------------ parameters (pointneus_disent.py:110-205)
@@ -284,7 +288,7 @@ class PointVolSDF(nn.Module):
 
     def _point_slots(self, x: torch.Tensor, tag: str = "points") -> SlotSet:
         pidx = self._grid().query_points(x.contiguous().float(), self.conf.k, self.conf.r)
-        return SlotSet(pidx, tag)
+        return SlotSet(pidx, tag, self._owner)
 
     # ------------------------------------------------------------------ point SDF queries
     def sdf_importance(self, inputs: torch.Tensor) -> torch.Tensor:
@@ -363,7 +367,7 @@ class PointVolSDF(nn.Module):
         points = self.ray_sampler.last_points  # cam_loc + z * dir, produced by the sampler kernel
         # kNN (pointneus_disent.py:654-660)
         pidx, loc, slot_sample, nvalid = grid.query_dense(points, K, self.conf.r, S)
-        slots = SlotSet(pidx, "fine")
+        slots = SlotSet(pidx, "fine", self._owner)
         n = R * S
         # filter_points (pointneus_disent.py:666-669)
         t = torch.empty(R, S, dtype=torch.float32, device=dev)
@@ -396,7 +400,7 @@ class PointVolSDF(nn.Module):
         # pseudo points (pointneus_disent.py:765-780): expected-depth point per hit ray, SDF should vanish there
         if aux_losses:
             pseudo = PseudoPointLoss.apply(self.neural_feats_geometry, dist, cam_loc, ray_dirs, nvalid, grid, self.conf.k,
-                                           self.conf.r, self._pack(), self.neural_pts, self.conf.rbf)
+                                           self.conf.r, self._pack(), self.neural_pts, self.conf.rbf, self._owner)
         else:
             pseudo = torch.zeros((), device=dev)
         far_cfg = float(self.conf.ray_sampler.far)

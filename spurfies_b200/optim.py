@@ -32,6 +32,8 @@ def cosine_lr(step: int, base_lr: float = 5.0e-4, eta_min: float = 3.0e-4, t_max
 
 
 class FusedAdam:
+    _LR_SLOTS = 64
+
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 5.0e-4, betas=(0.9, 0.999), eps: float = 1.0e-8,
                  max_norm: float = 1.0, grad_flat: Optional[torch.Tensor] = None):
         self.params: List[torch.Tensor] = [p for p in params]
@@ -52,7 +54,11 @@ class FusedAdam:
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
         self.state = torch.tensor([0.0, self.lr], dtype=torch.float32, device=dev)   # [steps taken, lr]
-        self._lr_host = torch.tensor([self.lr], dtype=torch.float32).pin_memory()
+        # ring of pinned staging slots for the asynchronous lr upload: the host may run many (graph-replayed) steps
+        # ahead of the GPU, so a single pinned word could be overwritten before its copy has been executed
+        self._lr_host = torch.full((self._LR_SLOTS,), self.lr, dtype=torch.float32).pin_memory()
+        self._lr_events = [None] * self._LR_SLOTS
+        self._lr_n = 0
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.info = torch.zeros(2, dtype=torch.float32, device=dev)
         self._ws = torch.empty(_lib.lib.spf_optim_workspace_bytes(), dtype=torch.uint8, device=dev)
@@ -83,8 +89,15 @@ class FusedAdam:
     def set_lr(self, lr: float) -> None:
         """Learning rate of the next step (host scheduler -> one 4-byte async H2D copy, outside any captured graph)."""
         self.lr = float(lr)
-        self._lr_host[0] = self.lr
-        self.state[1:2].copy_(self._lr_host, non_blocking=True)
+        i = self._lr_n % self._LR_SLOTS
+        self._lr_n += 1
+        if self._lr_events[i] is not None:
+            self._lr_events[i].synchronize()   # the copy that last used this slot has run (64 steps ago: never waits)
+        self._lr_host[i] = self.lr
+        self.state[1:2].copy_(self._lr_host[i:i + 1], non_blocking=True)
+        if self._lr_events[i] is None:
+            self._lr_events[i] = torch.cuda.Event()
+        self._lr_events[i].record()
 
     # ------------------------------------------------------------------ step
     def step(self, grad_scale: float = 1.0, zero_grad: bool = True) -> None:

@@ -11,14 +11,17 @@ from __future__ import annotations
 import torch
 
 
-def pack_sw128(W: torch.Tensor, n_pad: int | None = None) -> torch.Tensor:
+PACK_F16 = 2   # SPF_PACK_F16: forward weight images are fp16, gradient-chain images bf16 (csrc/umma.cuh)
+
+
+def pack_sw128(W: torch.Tensor, n_pad: int | None = None, dtype=torch.bfloat16) -> torch.Tensor:
     """W [N, K] (any float dtype, any device) -> uint8 image [ceil(K/64) * n_pad * 128] on the same device."""
     N, K = W.shape
     n_pad = n_pad or N
     assert n_pad % 8 == 0 and n_pad >= N
     nkb = (K + 63) // 64
-    Wb = torch.zeros(n_pad, nkb * 64, dtype=torch.bfloat16, device=W.device)
-    Wb[:N, :K] = W.detach().to(torch.bfloat16)
+    Wb = torch.zeros(n_pad, nkb * 64, dtype=dtype, device=W.device)
+    Wb[:N, :K] = W.detach().float().clamp(-65504.0, 65504.0).to(dtype)
     t = Wb.view(n_pad, nkb, 8, 8).permute(1, 0, 2, 3)                      # [kb, n, chunk, 8]
     n = torch.arange(n_pad, device=W.device)
     c = torch.arange(8, device=W.device)
@@ -28,7 +31,7 @@ def pack_sw128(W: torch.Tensor, n_pad: int | None = None) -> torch.Tensor:
 
 
 def pack_sw128_dev(out: torch.Tensor, W: torch.Tensor, N: int, K: int, transpose: bool = False, n_pad: int | None = None,
-                   col_off: int = 0, row_off_bytes: int = 0, batch: list | None = None) -> None:
+                   col_off: int = 0, row_off_bytes: int = 0, batch: list | None = None, f16: bool = False) -> None:
     """Kernel version (spf_pack_sw128) for per-step packing of trainable weights: writes the image of
     W[:, col_off:col_off+K] ([N, K]) -- or, with transpose, of W[:, col_off:col_off+N]^T where W is [K, .] -- into the
     uint8 buffer `out` starting at byte `row_off_bytes`.  W must be fp32, CUDA, with unit column stride.  With `batch`
@@ -39,11 +42,12 @@ def pack_sw128_dev(out: torch.Tensor, W: torch.Tensor, N: int, K: int, transpose
     n_pad = n_pad or N
     if batch is not None:   # collected; one launch for all of them in pack_flush
         batch.append((W.data_ptr() + 4 * col_off, out.data_ptr() + row_off_bytes, int(W.stride(0)), int(N), int(K),
-                      int(bool(transpose)), int(n_pad), W))
+                      int(bool(transpose)) | (PACK_F16 if f16 else 0), int(n_pad), W))
         return
     src = C.c_void_p(W.data_ptr() + 4 * col_off)
     dst = C.c_void_p(out.data_ptr() + row_off_bytes)
-    _lib.call("spf_pack_sw128", src, int(W.stride(0)), int(N), int(K), int(bool(transpose)), int(n_pad), dst, _lib.stream())
+    _lib.call("spf_pack_sw128", src, int(W.stride(0)), int(N), int(K), int(bool(transpose)) | (PACK_F16 if f16 else 0), int(n_pad), dst,
+              _lib.stream())
 
 
 def pack_flush(batch: list) -> None:

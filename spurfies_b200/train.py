@@ -20,6 +20,58 @@ from .model import PointVolSDF, VolSDFLoss
 from .optim import FusedAdam, cosine_lr
 
 
+def _clone_tree(v):
+    """Static copy of a (nested) input dict: tensors are cloned, dicts recursed, everything else kept."""
+    if torch.is_tensor(v):
+        return v.clone()
+    if isinstance(v, dict):
+        return {k: _clone_tree(x) for k, x in v.items()}
+    return v
+
+
+def _like_tree(v):
+    if torch.is_tensor(v):
+        return torch.empty_like(v)
+    if isinstance(v, dict):
+        return {k: _like_tree(x) for k, x in v.items()}
+    return v
+
+
+def _copy_tree(dst, src, path="") -> None:
+    """dst[k].copy_(src[k]) for every tensor of a (nested) dict.  The structure and shapes must be the captured ones:
+    a CUDA graph bakes in the device pointers, so an entry that cannot be copied into its static buffer is an error,
+    never silently skipped."""
+    for k, v in src.items():
+        if torch.is_tensor(v):
+            if k not in dst or not torch.is_tensor(dst[k]) or dst[k].shape != v.shape:
+                raise ValueError(f"graph replay: input '{path}{k}' does not match the captured step "
+                                 f"({tuple(v.shape)} vs {tuple(dst[k].shape) if k in dst and torch.is_tensor(dst[k]) else None})")
+            dst[k].copy_(v, non_blocking=True)
+        elif isinstance(v, dict):
+            if not isinstance(dst.get(k), dict):
+                raise ValueError(f"graph replay: input '{path}{k}' was not a dict when the step was captured")
+            _copy_tree(dst[k], v, path + k + ".")
+        elif v is None and dst.get(k) is not None:
+            raise ValueError(f"graph replay: input '{path}{k}' is None but the captured step had a value")
+
+
+def _to_device_tree(v, dev):
+    if torch.is_tensor(v):
+        return v.to(dev, non_blocking=True)
+    if isinstance(v, dict):
+        return {k: _to_device_tree(x, dev) for k, x in v.items()}
+    return v
+
+
+def _record_tree(v, stream) -> None:
+    if torch.is_tensor(v):
+        if v.is_cuda:
+            v.record_stream(stream)
+    elif isinstance(v, dict):
+        for x in v.values():
+            _record_tree(x, stream)
+
+
 class TrainStep:
     def __init__(self, model: PointVolSDF, lr: float = 5.0e-4, grad_clip: float = 1.0, loss: Optional[VolSDFLoss] = None,
                  world_size: int = 1, lr_schedule: bool = True, grad_compress: Optional[str] = None):
@@ -68,8 +120,15 @@ class TrainStep:
             import gc
             self.model._last = None
             gc.collect()  # drop every reference to earlier eager steps' autograd graphs (see model.forward)
-            self._static = ({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()},
-                            {k: v.clone() for k, v in gt.items()}, {k: v.clone() for k, v in rng.items()})
+            # every tensor of the inputs -- including the nested ``local_data`` dict (feature maps and cameras of the
+            # step's view, which change every step) -- gets a static device copy the graph reads from
+            dev = self.opt.flat_p.device
+            self._static = tuple(_clone_tree(_to_device_tree(d, dev)) for d in (batch, gt, rng))
+            # The warm-up steps below are real optimisation steps on one batch: snapshot everything they change
+            # (parameters, both Adam moments, the step count / lr, the gradient buffer) and restore it afterwards, so
+            # that capture() has no effect on the training trajectory.
+            opt = self.opt
+            snap = [t.clone() for t in (opt.flat_p, opt.exp_avg, opt.exp_avg_sq, opt.state, opt.flat_g)]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -77,9 +136,13 @@ class TrainStep:
                     self._eager(*self._static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            restore = lambda: [t.copy_(s_) for t, s_ in zip((opt.flat_p, opt.exp_avg, opt.exp_avg_sq, opt.state, opt.flat_g), snap)]
+            restore()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._static_out = self._eager(*self._static)
+            restore()   # (capture does not execute, but keep the invariant explicit and cheap)
+            torch.cuda.synchronize()
             self._graph = g
             return True
         except Exception as e:  # noqa: BLE001 - report and fall back to eager
@@ -92,14 +155,8 @@ class TrainStep:
             return False
 
     def replay(self, batch, gt, rng):
-        sb, sg, sr = self._static
-        for k, v in batch.items():
-            if torch.is_tensor(v):
-                sb[k].copy_(v, non_blocking=True)
-        for k, v in gt.items():
-            sg[k].copy_(v, non_blocking=True)
-        for k, v in rng.items():
-            sr[k].copy_(v, non_blocking=True)
+        for st, src in zip(self._static, (batch, gt, rng)):
+            _copy_tree(st, src)
         if getattr(self, "_copy_stream", None) is not None:
             self._free.record()      # the staging set (if that is where the inputs came from) may be refilled
         self._tick_lr()
@@ -120,18 +177,15 @@ class TrainStep:
         if self._graph is None:
             with torch.cuda.stream(cs):
                 dev = self.opt.flat_p.device
-                mv = lambda d: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in d.items()}
-                self._pending = (mv(batch), mv(gt), mv(rng))
+                self._pending = tuple(_to_device_tree(d, dev) for d in (batch, gt, rng))
                 self._ready.record(cs)
             return
         if self._stage is None:
-            self._stage = tuple({k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in d.items()} for d in self._static)
+            self._stage = tuple(_like_tree(d) for d in self._static)
         cs.wait_event(self._free)   # the previous step has moved the staging set into the static inputs
         with torch.cuda.stream(cs):
             for st, src in zip(self._stage, (batch, gt, rng)):
-                for k, v in src.items():
-                    if torch.is_tensor(v):
-                        st[k].copy_(v, non_blocking=True)
+                _copy_tree(st, src)
             self._ready.record(cs)
         self._pending = self._stage
 
@@ -142,13 +196,23 @@ class TrainStep:
         b, g, r = self._pending
         if self._graph is None:
             for d in (b, g, r):
-                for v in d.values():
-                    if torch.is_tensor(v):
-                        v.record_stream(cur)
+                _record_tree(d, cur)
             self._tick_lr()
             return self._eager(b, g, r)
         out = self.replay(b, g, r)   # device-to-device copies into the static inputs, then the graph
         return out
+
+    # ------------------------------------------------------------------ checkpoints (train.py:300-328 saves the scheduler too)
+    def state_dict(self) -> Dict:
+        return {"iter_step": int(self.iter_step), "base_lr": float(self.base_lr), "optimizer": self.opt.state_dict()}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.opt.load_state_dict(sd["optimizer"])
+        self.base_lr = float(sd.get("base_lr", self.base_lr))
+        # without a saved scheduler position, resume where the optimiser's step count says (one tick per step)
+        self.iter_step = int(sd["iter_step"]) if "iter_step" in sd else int(self.opt.state[0].item())
+        if self.lr_schedule:
+            self.opt.set_lr(cosine_lr(max(self.iter_step - 1, 0), self.base_lr))
 
     def __call__(self, batch, gt, rng=None) -> Dict[str, torch.Tensor]:
         if self._graph is not None:

@@ -26,6 +26,69 @@ def load_golden():
     return g, P
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# training-batch-scale fixture (tests/golden/make_golden_big.py): 1024 rays x 20 000 points, reference-generated
+GOLDEN_BIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_dtu20k_r1024.pt")
+BIG_N_POINTS, BIG_N_RAYS = 20000, 1024
+
+
+def image_gt(uv, seed=3):
+    """An image-like colour target: smooth in the pixel position (what a photograph is at ray-batch scale)."""
+    g = torch.Generator().manual_seed(seed)
+    u = uv[0] / torch.tensor([512.0, 384.0])
+    fr = torch.rand(3, 2, generator=g) * 4 + 1
+    ph = torch.rand(3, generator=g) * 6.28
+    return (0.5 + 0.45 * torch.sin((u[:, None, :] * fr[None]).sum(-1) * 3.0 + ph[None]))[None]
+
+
+def big_inputs():
+    """The deterministic inputs of the big fixture: scene, camera, pixels, mask target, RNG draws, colour targets."""
+    from spurfies_b200 import scenes
+    scene = scenes.dtu_like(BIG_N_POINTS, seed=24, radii=(0.3, 0.45))
+    cam = scenes.camera(0, scene["cam_radius"])
+    uv = (scenes.pixel_batch(BIG_N_RAYS, seed=7) - torch.tensor([256.0, 192.0])) * 0.45 + torch.tensor([256.0, 192.0])
+    gt = scenes.synthetic_gt(BIG_N_RAYS, 7)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(1234)   # the draws the reference makes from the global CPU generator, in its order
+    rng = {"t_rand": torch.rand(BIG_N_RAYS, 128), "u": torch.rand(BIG_N_RAYS, 64), "sampling_idx": torch.randperm(128)[:32]}
+    torch.random.set_rng_state(state)
+    return scene, cam, uv, gt, rng, {"random": gt["rgb"], "image": image_gt(uv)}
+
+
+def load_golden_big():
+    """(golden, scene, cam, uv, gt, rng, targets, P): inputs regenerated from the recipe and verified by checksum."""
+    g = torch.load(GOLDEN_BIG, weights_only=False)
+    scene, cam, uv, gt, rng, targets = big_inputs()
+    P = H.init_params(scene["pts"], scene["colors"], seed=g["recipe"]["param_seed"])
+    P.neural_feats_geometry *= g["recipe"]["geometry_latent_scale"]
+    P.neural_feats_color[:, 3:] *= g["recipe"]["color_latent_scale_from3"]
+    got = {"pts": scene["pts"], "uv": uv, "t_rand": rng["t_rand"], "u": rng["u"], "sampling_idx": rng["sampling_idx"].float(),
+           "gt_random": targets["random"], "gt_image": targets["image"], "neural_feats_color": P.neural_feats_color,
+           "F_color.0": P.F_color[0][0], "R.0": P.R[0][0], "F_geometry.0": P.F_geometry[0][0]}
+    for n, t in got.items():
+        v, want = float(t.double().abs().sum()), g["checksum"][n]
+        assert abs(v - want) <= 1e-9 * max(1.0, abs(want)), f"big golden recipe drifted for {n}: {v} vs {want}"
+    return g, scene, cam, uv, gt, rng, targets, P
+
+
+def big_grad_errors(got: dict, gold_grads: dict) -> dict:
+    """max|a-b| / max|ref| per trainable tensor against a `gold[target]["grads"]` entry.  Latent tables are compared on
+    the fixture's row subset, relative to the WHOLE reference table's max (stored), plus the relative error of the
+    column sums and of the Frobenius norm over the subset."""
+    out = {}
+    for n, r in gold_grads.items():
+        a = got[n].detach().double().cpu()
+        if isinstance(r, dict):
+            sub = a[::r["stride"]]
+            ref = r["values"].double()
+            out[n] = float((sub - ref).abs().max() / r["absmax"])
+            out[n + " (rows, fro)"] = float((sub - ref).norm() / ref.norm())
+            out[n + " (colsum)"] = float((a.sum(0) - r["colsum"].double()).abs().max() / r["colsum"].double().abs().max())
+        else:
+            out[n] = float((a - r.double()).abs().max() / r.double().abs().max())
+    return out
+
+
 def trainable(P):
     P.neural_feats_color.requires_grad_()
     P.neural_feats_geometry.requires_grad_()

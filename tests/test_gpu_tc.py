@@ -41,6 +41,11 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
+def _hf(t):
+    """fp16 rounding: the format of every FORWARD operand of the tensor-core mode (csrc/umma.cuh)."""
+    return t.to(torch.float16).float()
+
+
 def _leaky(z):
     return torch.where(z > 0, z, 0.01 * z)
 
@@ -59,9 +64,9 @@ def _pairs(slots, q, model):
 
 
 def test_geometry_field_tc_matches_bf16_emulation():
-    """The tcgen05 geometry kernel against a torch emulation that rounds to bf16 at exactly the same points (inputs,
-    weights, inter-layer activations; fp32 accumulation) -- so the LeakyReLU masks coincide and only summation order
-    differs.  (Against the fp32 kernel the per-row Jacobian differs by ~sqrt(fraction of sign flips): a piecewise-
+    """The tcgen05 geometry kernel against a torch emulation that rounds at exactly the same points (forward operands --
+    inputs, weights, inter-layer activations -- to fp16, the operands of the d sdf / d input chain to bf16; fp32
+    accumulation) -- so the LeakyReLU masks coincide and only summation order differs.  (Against the fp32 kernel the per-row Jacobian differs by ~sqrt(fraction of sign flips): a piecewise-
     linear net's gradient is discontinuous in its input, see test_geometry_field_tc_vs_fp32.)"""
     from spurfies_b200 import fields
     from spurfies_b200.fields import SlotSet, geo_sdf_raw
@@ -75,14 +80,14 @@ def test_geometry_field_tc_matches_bf16_emulation():
     fields.set_precision("fp32")
     lst, p, valid, x_pi, wn = _pairs(slots, q, model)
     W, b = pack.W, pack.b
-    hi = _bf(x_pi)
-    lo = _bf(x_pi - hi)
-    in0 = torch.cat([_bf(model.neural_feats_geometry.detach()[p]), hi, lo], -1) * valid[..., None]
-    W1e = _bf(torch.cat([W[0][:, :32], W[0][:, 32:35], W[0][:, 32:35]], 1))
+    hi = _hf(x_pi)
+    lo = _hf(x_pi - hi)
+    in0 = torch.cat([_hf(model.neural_feats_geometry.detach()[p]), hi, lo], -1) * valid[..., None]
+    W1e = _hf(torch.cat([W[0][:, :32], W[0][:, 32:35], W[0][:, 32:35]], 1))
     z1 = in0 @ W1e.t() + b[0]
-    z2 = _bf(_leaky(z1)) @ _bf(W[1]).t() + b[1]
-    z3 = _bf(_leaky(z2)) @ _bf(W[2]).t() + b[2]
-    z4 = _bf(_leaky(z3)) @ _bf(W[3]).t() + b[3]
+    z2 = _hf(_leaky(z1)) @ _hf(W[1]).t() + b[1]
+    z3 = _hf(_leaky(z2)) @ _hf(W[2]).t() + b[2]
+    z4 = _hf(_leaky(z3)) @ _hf(W[3]).t() + b[3]
     sdf_row = _leaky(z4) @ pack.v5 + pack.c5
     mk = lambda z: torch.where(z > 0, 1.0, 0.01)
     g4 = _bf(pack.v5 * mk(z4))
@@ -258,24 +263,27 @@ def test_wgrad_tc_multi(n_units, rpu):
     from spurfies_b200 import _lib
     g = torch.Generator().manual_seed(7 * n_units + rpu)
     rows = (n_units * rpu + 127) // 128 * 128
-    shapes = [(256, 256, True), (128, 112, True), (64, 32, False), (64, 16, False), (256, 256, True)]   # (lda, N, db)
-    dzs = [torch.randn(rows + 128, 256, generator=g).cuda().to(torch.bfloat16) for _ in shapes]
-    acts = [torch.randn(rows + 128, lda, generator=g).cuda().to(torch.bfloat16) for lda, _, _ in shapes]
+    # (lda, N, db, fmt): fmt bit 0 / 1 = dz / act is bf16 (else fp16).  1 = bf16 gradient x fp16 saved activation (the
+    # training step's products), 2 = the head's swapped a2^T @ dz3 product, 3 / 0 = both bf16 / both fp16
+    shapes = [(256, 256, True, 1), (128, 112, True, 1), (64, 32, False, 3), (64, 16, False, 2), (256, 256, False, 0)]
+    dt = lambda bit, fmt: torch.bfloat16 if (fmt >> bit) & 1 else torch.float16
+    dzs = [torch.randn(rows + 128, 256, generator=g).cuda().to(dt(0, f)) for _, _, _, f in shapes]
+    acts = [torch.randn(rows + 128, lda, generator=g).cuda().to(dt(1, f)) for lda, _, _, f in shapes]
     count = torch.tensor([n_units], dtype=torch.int32, device="cuda")
     arr = (_lib.WgradJob * len(shapes))()
     outs, keep = [], []
-    for i, (lda, N, want_db) in enumerate(shapes):
+    for i, (lda, N, want_db, fmt) in enumerate(shapes):
         dW = torch.zeros(256, N, device="cuda")
         db = torch.zeros(256, device="cuda") if want_db else None
         dz_t, act_t = _to_tile_layout(dzs[i], 4), _to_tile_layout(acts[i], lda // 64)
         keep += [dz_t, act_t]
         arr[i].dz, arr[i].act, arr[i].dW = dz_t.data_ptr(), act_t.data_ptr(), dW.data_ptr()
         arr[i].db = db.data_ptr() if db is not None else None
-        arr[i].lda, arr[i].N = lda, N
+        arr[i].lda, arr[i].N, arr[i].fmt = lda, N, fmt
         outs.append((dW, db))
     _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), rpu, n_units + 50, _lib.stream())
     torch.cuda.synchronize()
-    for i, (lda, N, want_db) in enumerate(shapes):
+    for i, (lda, N, want_db, fmt) in enumerate(shapes):
         ref = dzs[i][:rows].float().t() @ acts[i][:rows, :N].float()
         assert float((outs[i][0] - ref).abs().max() / ref.abs().max()) < 1e-4, i
         if want_db:

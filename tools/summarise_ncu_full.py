@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Per-launch table of the metrics that matter from an `ncu --set full` report.
-usage: python tools/summarise_ncu_full.py gpurun_out/x.ncu-rep "<command>" > profiles/rNN_ncu_full.md"""
+usage: python tools/summarise_ncu_full.py gpurun_out/x.ncu-rep "<command>" [--traffic-json profiles/ncu_traffic.json]
+       > profiles/rNN_ncu_full.md
+--traffic-json also writes, per kernel name, the DRAM bytes (read + write) of its LONGEST launch: bench.py's
+roofline.traffic reads that file (it never carries a constant of its own)."""
 import csv
+import json
+import os
 import subprocess
 import sys
 
@@ -14,7 +19,9 @@ COLS = [("gpu__time_duration.sum", "time us", 1.0), ("dram__bytes_read.sum", "DR
 
 
 def main():
-    rep, cmd = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
+    rep, cmd = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "")
+    tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
+    traffic = {}
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
     head, units, data = rows[0], rows[1], rows[2:]
@@ -43,9 +50,24 @@ def main():
                 vals.append(f"{v:.1f}")
             except (KeyError, ValueError):
                 vals.append("-")
+        if tj:
+            def num(m):
+                v = float(r[ix[m]].replace(",", ""))
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "msecond": 1e3, "us": 1.0,
+                            "usecond": 1.0, "ns": 1e-3, "nsecond": 1e-3}.get(units[ix[m]], 1.0)
+            try:
+                t_us, by = num("gpu__time_duration.sum"), num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+                if name not in traffic or t_us > traffic[name]["time_us"]:
+                    traffic[name] = {"dram_bytes": by, "time_us": t_us, "dram_read_bytes": num("dram__bytes_read.sum"),
+                                     "dram_write_bytes": num("dram__bytes_write.sum")}
+            except (KeyError, ValueError):
+                pass
         g = r[ix["Grid Size"]].strip("()").split(",")[0]
         b = r[ix["Block Size"]].strip("()").split(",")[0]
         print(f"| `{name}` | {g} x {b} | " + " | ".join(vals) + " |")
+    if tj:
+        json.dump({"file": os.path.basename(rep), "command": cmd, "note": "per kernel: the longest launch of the capture",
+                   "kernels": traffic}, open(tj, "w"), indent=1)
 
 
 if __name__ == "__main__":
