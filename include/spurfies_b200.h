@@ -374,7 +374,8 @@ int spf_wgrad_tc(const void* dz, const void* act, int32_t lda, int32_t N, const 
 typedef struct {
   const void* dz; const void* act; float* dW; float* db;
   int32_t lda, N;
-  int32_t fmt;      /* bit 0: dz is bf16 (else fp16); bit 1: act is bf16 (else fp16).  db needs a bf16 dz. */
+  int32_t fmt;      /* bit 0: dz is bf16 (else fp16); bit 1: act is bf16 (else fp16).  An fp16 operand is converted to
+                     * bf16 in shared memory before the MMAs (tcgen05 kind::f16 needs A and B in the same format). */
   int32_t reserved;
 } spf_wgrad_job;
 int spf_wgrad_tc_multi(const spf_wgrad_job* jobs /* HOST array */, int32_t n_jobs, const int32_t* count,

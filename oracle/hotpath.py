@@ -446,6 +446,7 @@ def render_forward(p: Params, grid: OracleGrid, uv, pose, intrinsics, cfg: Sampl
         pts_rendered = o + dd * dist_map[:, None]
         sdf_rendered = point_sdf(p, grid, pts_rendered, compact=True)
         pseudo_loss = F.l1_loss(sdf_rendered, torch.zeros_like(sdf_rendered), reduction="mean")
+        out["pseudo_count"] = int(sdf_rendered.shape[0])   # the mean's denominator (data-parallel tests)
         color_filler = torch.zeros(Rv, S, 3)
         color_filler[vm] = colors
         rgb_values = torch.sum(weights_values.unsqueeze(-1) * color_filler, 1)

@@ -2,6 +2,7 @@
 // cp.async ring; tile-layout operands via TMA bulk copies), weight packing and the tcgen05 building-block self test.
 // The per-pair fields and the per-sample radiance head live in mlp_tc2.cu on the CTA-pair tile engine.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "umma.cuh"
 
 using namespace tc;
@@ -162,6 +163,7 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
   const uint32_t sbase = smem_u32(smem);
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int act_panels = (N + 63) >> 6;
+  const bool conv_dz = false, conv_act = false;   // single-job entry point: both operands bf16
   const uint32_t idesc = idesc_bf16_mn(128, N);
   float bsum = 0.0f;
 
@@ -184,6 +186,27 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
     const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
     mbar_wait(bar_full + st, ph);
     const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    if (conv_dz || conv_act) {
+#pragma unroll 1
+      for (int op = 0; op < 2; ++op) {
+        if (!(op == 0 ? conv_dz : conv_act)) continue;
+        uint8_t* base = smem + st * WG_STAGE_BYTES + op * 32768;
+        const int nchunk = (op == 0 ? 4 : act_panels) * 512;   // 16-byte chunks of the operand's stage region
+        for (int c = tid; c < nchunk; c += TC_THREADS) {
+          uint4 u = *reinterpret_cast<uint4*>(base + c * 16);
+          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
+            const float2 f = __half22float2(h);
+            w[e] = pack_bf16(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(base + c * 16) = u;
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the MMAs (async proxy) and ordered before the refill
+      __syncthreads();
+    }
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -275,7 +298,14 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
   const int my_tiles = (ntiles - bid + nb - 1) / nb;
   const int N = J.N;
   const int act_panels = (N + 63) >> 6;
-  const uint32_t idesc = idesc_f16k_mn(128, N, J.fmt);   // dZ (A) and the saved activation (B) may differ in format
+  // tcgen05.mma kind::f16 wants A and B in the SAME 16-bit format (a bf16 x fp16 instruction descriptor is an illegal
+  // instruction on the B200).  Gradient tiles are bf16 and the saved forward activations fp16, so the fp16 operand of
+  // a stage is converted to bf16 IN PLACE in shared memory (elementwise, so the swizzle does not matter) by all 256
+  // threads before the MMAs of that stage are issued: ~110 instructions per thread per 64-row tile, against a
+  // ~3000-cycle HBM budget per tile.  Rounding fp16 -> bf16 here is a plain 2^-9 rounding of a wgrad operand; the
+  // LeakyReLU sign decisions were taken in the forward pass on the fp16 values.
+  const uint32_t idesc = idesc_bf16_mn(128, N);
+  const bool conv_dz = !(J.fmt & 1), conv_act = !(J.fmt & 2);
   float bsum = 0.0f;
 
   auto load_tile = [&](int it) {   // one thread
@@ -297,6 +327,27 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
     const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
     mbar_wait(bar_full + st, ph);
     const uint32_t sdz = sbase + st * WG_STAGE_BYTES, sact = sdz + 32768;
+    if (conv_dz || conv_act) {
+#pragma unroll 1
+      for (int op = 0; op < 2; ++op) {
+        if (!(op == 0 ? conv_dz : conv_act)) continue;
+        uint8_t* base = smem + st * WG_STAGE_BYTES + op * 32768;
+        const int nchunk = (op == 0 ? 4 : act_panels) * 512;   // 16-byte chunks of the operand's stage region
+        for (int c = tid; c < nchunk; c += TC_THREADS) {
+          uint4 u = *reinterpret_cast<uint4*>(base + c * 16);
+          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
+            const float2 f = __half22float2(h);
+            w[e] = pack_bf16(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(base + c * 16) = u;
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the MMAs (async proxy) and ordered before the refill
+      __syncthreads();
+    }
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -373,7 +424,6 @@ extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, con
     if (c < 1) c = 1;
     if (q == n_jobs - 1 || used + c > sms - (n_jobs - 1 - q)) c = sms - (n_jobs - 1 - q) - used;
     const spf_wgrad_job& J = jobs[q];
-    if (J.db && !(J.fmt & 1)) return SPF_ERR_UNSUPPORTED;   // the bias-gradient column sums read dZ as bf16
     d.j[q] = {(const uint8_t*)J.dz, (const uint8_t*)J.act, J.dW, J.db, J.lda >> 6, J.N, used, c, J.fmt & 3};
     used += c;
   }

@@ -48,10 +48,10 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
     ch.L[1] = {W.w2p, 4, 16, 256, FMT_F16};
     ch.L[2] = {W.w3p, 4, 16, 256, FMT_F16};
     ch.L[3] = {W.w4p, 4, 16, 256, FMT_F16};
-    ch.L[4] = {W.w4tp, 4, 16, 256, FMT_BF16};   // d sdf / d input chain: bf16 operands
-    ch.L[5] = {W.w3tp, 4, 16, 256, FMT_BF16};
-    ch.L[6] = {W.w2tp, 4, 16, 256, FMT_BF16};
-    ch.L[7] = {W.w1tp, 4, 16, 48, FMT_BF16};
+    ch.L[4] = {W.w4tp, 4, 16, 256, FMT_F16};    // d sdf / d input chain: the network's Jacobian (O(weights) magnitudes,
+    ch.L[5] = {W.w3tp, 4, 16, 256, FMT_F16};    // no 1/R loss scaling), so fp16 is range-safe here too and keeps 3 more
+    ch.L[6] = {W.w2tp, 4, 16, 256, FMT_F16};    // bits per layer than bf16
+    ch.L[7] = {W.w1tp, 4, 16, 48, FMT_F16};
     ch.n = WITH_J ? 8 : 4;
   }
   for (int i = tid; i < 256; i += THREADS) {
@@ -169,8 +169,8 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
               dot = fmaf(fmaxf(z0, LEAKY * z0), vq.x, dot); dot = fmaf(fmaxf(z1, LEAKY * z1), vq.y, dot);
               dot = fmaf(fmaxf(z2, LEAKY * z2), vq.z, dot); dot = fmaf(fmaxf(z3, LEAKY * z3), vq.w, dot);
               if (WITH_J) {   // g4 = v5 * lrelu'(z4)
-                pk[2 * q] = pack_bf16(z0 > 0.0f ? vq.x : LEAKY * vq.x, z1 > 0.0f ? vq.y : LEAKY * vq.y);
-                pk[2 * q + 1] = pack_bf16(z2 > 0.0f ? vq.z : LEAKY * vq.z, z3 > 0.0f ? vq.w : LEAKY * vq.w);
+                pk[2 * q] = pack_f16(z0 > 0.0f ? vq.x : LEAKY * vq.x, z1 > 0.0f ? vq.y : LEAKY * vq.y);
+                pk[2 * q + 1] = pack_f16(z2 > 0.0f ? vq.z : LEAKY * vq.z, z3 > 0.0f ? vq.w : LEAKY * vq.w);
               }
             }
           }
@@ -212,7 +212,7 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
             for (int i = 0; i < 8; ++i) {
               const float m0 = (sb & (2u << (2 * i))) ? LEAKY : 1.0f;
               const float m1 = (sb & (0x20000u << (2 * i))) ? LEAKY : 1.0f;
-              pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+              pk[i] = pack_f16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
             }
             const int c0 = half * 128 + c * 16;
             uint8_t* dstA = sA + (c0 >> 6) * 16384;

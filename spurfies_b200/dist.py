@@ -36,6 +36,22 @@ def shard_rays(batch: dict, rank: int, world: int, ray_keys=("uv",), dim: int = 
     return out
 
 
+def global_count_scales(local_counts: torch.Tensor, world: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Loss terms that are MEANS over a data-dependent count (valid samples, hit rays, crossing rays) must be normalised
+    by the GLOBAL count for a ray-sharded step to equal the one-big-batch step (sum of numerators / global
+    counts; reference means: pointneus_disent.py:765-780 ``F.l1_loss(..., reduction="mean")`` over all hit rays,
+    loss.py:34-40 over all valid samples, feat_utils.py:446-451 over all crossing rays).  Given this rank's counts
+    [k], returns the factors  local * world / global  that turn each rank-local mean into this rank's share of the global
+    mean AFTER the gradient average over ranks (sum_r share_r / world == global mean).  One tiny all-reduce, no host
+    sync, CUDA-graph capturable.  A term nobody contributes to (global count 0) keeps factor 1."""
+    c = local_counts.detach().to(torch.float32)
+    if world <= 1:
+        return torch.ones_like(c)
+    tot = c.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return torch.where(tot > 0, c * float(world) / tot.clamp(min=1.0), torch.ones_like(c))
+
+
 def flat_offsets(params: Iterable[torch.Tensor], align: int = 1) -> Tuple[List[int], int]:
     """Element offsets of each tensor inside a flat buffer whose segments start on multiples of `align` elements
     (align = 4: 16-byte boundaries for the fused optimiser's 128-bit accesses) and the padded total."""

@@ -140,11 +140,11 @@ class GeoPack:
                 self.f32 = s
                 # tensor-core images (mlp_tc2.cu): x - p enters twice (fp16 hi + lo) against the same weights
                 W1ext = torch.cat([W[0][:, :32], W[0][:, 32:35], W[0][:, 32:35]], dim=1)
-                f16 = torch.float16   # forward operands are fp16, the d sdf / d input chain's bf16 (csrc/umma.cuh)
+                f16 = torch.float16   # fp16 operands for the forward layers and the d sdf / d input chain (csrc/umma.cuh)
                 self.tc_imgs = [pack_sw128(W1ext, dtype=f16), pack_sw128(W[1], dtype=f16), pack_sw128(W[2], dtype=f16),
                                 pack_sw128(W[3], dtype=f16),
-                                pack_sw128(W[3].t()), pack_sw128(W[2].t()), pack_sw128(W[1].t()),
-                                pack_sw128(W[0].t(), n_pad=48)]
+                                pack_sw128(W[3].t(), dtype=f16), pack_sw128(W[2].t(), dtype=f16),
+                                pack_sw128(W[1].t(), dtype=f16), pack_sw128(W[0].t(), n_pad=48, dtype=f16)]
                 t = GeoWeightsTC()
                 (t.w1p, t.w2p, t.w3p, t.w4p, t.w4tp, t.w3tp, t.w2tp, t.w1tp) = (i.data_ptr() for i in self.tc_imgs)
                 t.b1, t.b2, t.b3, t.b4 = (b[i].data_ptr() for i in range(4))
@@ -560,7 +560,7 @@ class PseudoPointLoss(torch.autograd.Function):
     x = cam + dist * dir and d sdf / d x).  Replaces ~40 torch launches of mask / where / sum / sign glue per step."""
 
     @staticmethod
-    def forward(ctx, feat_g, dist, cam_loc, ray_dirs, nvalid, grid, k, r, pack, pts, rbf, owner=""):
+    def forward(ctx, feat_g, dist, cam_loc, ray_dirs, nvalid, grid, k, r, pack, pts, rbf, owner="", aux=None):
         dev = dist.device
         R = dist.shape[0]
         x = torch.empty(R, 3, dtype=torch.float32, device=dev)
@@ -576,6 +576,8 @@ class PseudoPointLoss(torch.autograd.Function):
         ctx.slots, ctx.jw, ctx.u = slots, jw, (u_sdf, u_dist)
         ctx.feat_shape = feat_g.shape
         ctx.direct = _direct_grad(feat_g)
+        if aux is not None:   # the mean's denominator, for the data-parallel global-count normalisation (dist.py)
+            aux["pseudo_count"] = ((nvalid > 0) & (slots.pidx[:, 0] >= 0)).sum()
         return value.reshape(())
 
     @staticmethod
@@ -592,7 +594,7 @@ class PseudoPointLoss(torch.autograd.Function):
             call("spf_sdf_bwd", ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K, ptr(ctx.jw),
                  ptr((u_sdf * g).contiguous()), ptr(target), stream())
         d_dist = u_dist * g if u_dist is not None else None
-        return gfeat, d_dist, None, None, None, None, None, None, None, None, None, None
+        return gfeat, d_dist, None, None, None, None, None, None, None, None, None, None, None
 
 
 class TVRegul(torch.autograd.Function):

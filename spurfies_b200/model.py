@@ -256,6 +256,7 @@ class PointVolSDF(nn.Module):
         self.ray_sampler = ErrorBoundSampler_pn(self.scene_bounding_sphere, **conf.get_config("ray_sampler"))
         self._geo_pack = GeoPack()
         self._self_knn = None
+        self._dp = (1, None)   # (world size, process group) of the ray-sharded data parallelism, see set_data_parallel
         PointVolSDF._instances += 1
         self._owner = f"m{PointVolSDF._instances}."   # prefix of this model's arena buffers (fields.Arena)
         self.to(device)
@@ -273,6 +274,13 @@ class PointVolSDF(nn.Module):
             fc[:, :3] = colors.float().to(fc.device) * 2.0 / 255.0 - 1.0
         self.neural_feats_color = nn.Parameter(fc)
         self.neural_feats_geometry = nn.Parameter(fg)
+
+    def set_data_parallel(self, world_size: int, group=None) -> None:
+        """Ray-sharded data parallelism (new functionality): with world_size > 1 the training forward
+        all-reduces the denominators of its count-normalised loss terms (pseudo-point, local, eikonal) so that the
+        gradient averaged over ranks is the gradient of the one-big-batch step.  The ray shards must be equally
+        sized for the per-ray means (rgb, mask) to combine exactly."""
+        self._dp = (int(world_size), group)
 
     # ------------------------------------------------------------------ helpers
     def _grid(self) -> VoxelGrid:
@@ -393,16 +401,33 @@ class PointVolSDF(nn.Module):
         # feature-consistency loss at the first back-facing zero crossing (pointneus_disent.py:727-763, DTU 3-view only)
         local_data = input.get("local_data", None)
         local_loss = torch.zeros((), device=dev)
+        world, group = self._dp
+        dp = world > 1 and self.training
+        counts = {}
         if local_data is not None and self.training:
             feats = local_feature_args(local_data, dev)
             local_loss, d_surface, cross = LocalLoss.apply(sdf, t, cam_loc, ray_dirs, feats, R, S)
             self._last_surface = (d_surface, cross)
+            if dp:
+                counts["local"] = (cross >= 0).sum()
         # pseudo points (pointneus_disent.py:765-780): expected-depth point per hit ray, SDF should vanish there
         if aux_losses:
+            aux = {} if dp else None
             pseudo = PseudoPointLoss.apply(self.neural_feats_geometry, dist, cam_loc, ray_dirs, nvalid, grid, self.conf.k,
-                                           self.conf.r, self._pack(), self.neural_pts, self.conf.rbf, self._owner)
+                                           self.conf.r, self._pack(), self.neural_pts, self.conf.rbf, self._owner, aux)
+            if dp:
+                counts["pseudo"] = aux["pseudo_count"]
         else:
             pseudo = torch.zeros((), device=dev)
+        eik_scale = None
+        if dp:
+            # global-count normalisation of the count-normalised means (one 12-byte all-reduce, no host sync)
+            from .dist import global_count_scales
+            zero_c = torch.zeros((), dtype=torch.int64, device=dev)
+            loc = torch.stack([counts.get("pseudo", zero_c).to(torch.int64), counts.get("local", zero_c).to(torch.int64),
+                               slots.count.reshape(()).to(torch.int64)])
+            sc = global_count_scales(loc, world, group)
+            pseudo, local_loss, eik_scale = pseudo * sc[0], local_loss * sc[1], sc[2]
         far_cfg = float(self.conf.ray_sampler.far)
         depth_vals = torch.where(ray_mask[:, None], t * depth_scale[:, None], torch.full_like(t, far_cfg))
         output = {
@@ -417,6 +442,8 @@ class PointVolSDF(nn.Module):
         }
         if self.white_bkgd:  # pointneus_disent.py:856-861 (computed but never written back there either)
             pass
+        if eik_scale is not None:
+            output["eikonal_scale"] = eik_scale
         if not self.training:
             output["normal_map"] = normal
         else:
@@ -459,6 +486,8 @@ class VolSDFLoss(nn.Module):
             out["eikonal_loss"] = (((g.norm(2, dim=1) - 1) ** 2) * m).sum() / m.sum().clamp(min=1)
         else:
             out["eikonal_loss"] = zero
+        if "eikonal_scale" in model_outputs:   # data parallel: this rank's share of the global mean (PointVolSDF.forward)
+            out["eikonal_loss"] = out["eikonal_loss"] * model_outputs["eikonal_scale"]
         out["tv_loss"] = model_outputs["tv_loss"] if ("tv_loss" in model_outputs and self.tv_weight > 0) else zero
         if "weights" in model_outputs:
             wsum = model_outputs["weights"].sum(-1, keepdim=True)
@@ -492,6 +521,13 @@ class VolSDFLoss(nn.Module):
         loss, terms = _FusedLoss.apply(model_outputs["rgb_values"], model_outputs["weights"],
                                        tv if tv is not None else zero, local if local is not None else zero,
                                        pseudo if pseudo is not None else zero, rgb_gt, mask2, g, m, wts)
+        es = model_outputs.get("eikonal_scale")
+        if es is not None and g is not None:   # data parallel: the eikonal mean over the GLOBAL valid-sample count (value only:
+            eik = terms[2]                     # the term has no gradient path)
+            loss = loss + self.eikonal_weight * (es - 1.0) * eik
+            terms = terms.clone()
+            terms[2] = eik * es
+            terms[0] = loss.detach()
         self.iter_step += 1
         return {"loss": loss, "rgb_loss": terms[1], "eikonal_loss": terms[2], "tv_loss": terms[3], "mask_loss": terms[4],
                 "local_loss": terms[5], "pseudo_loss": terms[6]}

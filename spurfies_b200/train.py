@@ -84,6 +84,7 @@ class TrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.grad_clip = grad_clip
         self.world_size = world_size
+        model.set_data_parallel(world_size)   # count-normalised loss terms use global counts (PointVolSDF.forward)
         self.base_lr, self.lr_schedule, self.iter_step = lr, lr_schedule, 0
         n_half = 0
         if grad_compress is not None:

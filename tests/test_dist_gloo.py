@@ -148,10 +148,16 @@ def _oracle_setup():
     return H, P, cam, uv, rng, gt
 
 
-def _per_ray_loss(H, P, grid, cam, uv, rng, gt_rgb, gt_mask):
+def _per_ray_loss(H, P, grid, cam, uv, rng, gt_rgb, gt_mask, world=1):
+    """rgb + mask (means over the rays: equal shards combine exactly) + the pseudo-point term, a mean over the HIT rays
+    whose pseudo point has a neighbour -- a data-dependent count that differs between shards, normalised globally with
+    the same helper PointVolSDF.forward uses (spurfies_b200/dist.py::global_count_scales)."""
+    from spurfies_b200.dist import global_count_scales
     out = H.render_forward(P, grid, uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), True, 1, rng, with_tv=False)
     lo = H.volsdf_loss(out, gt_rgb, gt_mask)
-    return lo["rgb_loss"] + lo["mask_loss"]      # the terms whose denominators are the ray count
+    cnt = torch.tensor([float(out.get("pseudo_count", 0))])
+    scale = global_count_scales(cnt, world)[0]
+    return lo["rgb_loss"] + lo["mask_loss"] + 0.5 * lo["pseudo_loss"] * scale, int(cnt[0])
 
 
 def _worker_sharded(rank, world, port, q):
@@ -161,12 +167,12 @@ def _worker_sharded(rank, world, port, q):
     R = uv.shape[1]
     lo, hi = shard_range(R, rank, world)
     rng_r = {"t_rand": rng["t_rand"][lo:hi], "u": rng["u"][lo:hi], "sampling_idx": rng["sampling_idx"]}
-    loss = _per_ray_loss(H, P, P.make_grid(), cam, shard_rays({"uv": uv}, rank, world)["uv"], rng_r,
-                         gt["rgb"][:, lo:hi], gt["mask"][0, lo:hi, 0])
+    loss, cnt = _per_ray_loss(H, P, P.make_grid(), cam, shard_rays({"uv": uv}, rank, world)["uv"], rng_r,
+                              gt["rgb"][:, lo:hi], gt["mask"][0, lo:hi, 0], world)
     loss.backward()
     params = P.trainable()
     FlatGradReducer(params, world).reduce()
-    q.put((rank, [p.grad.detach().numpy().copy() for p in params]))  # by value (no fd passing)
+    q.put((rank, ([p.grad.detach().numpy().copy() for p in params], cnt)))  # by value (no fd passing)
     dist.destroy_process_group()
 
 
@@ -181,11 +187,13 @@ def test_sharded_rays_equal_one_big_batch_world2():
     for p in procs:
         p.join(60)
     H, P, cam, uv, rng, gt = _oracle_setup()
-    loss = _per_ray_loss(H, P, P.make_grid(), cam, uv, rng, gt["rgb"], gt["mask"][0, :, 0])
+    loss, cnt = _per_ray_loss(H, P, P.make_grid(), cam, uv, rng, gt["rgb"], gt["mask"][0, :, 0])
     loss.backward()
     want = [p.grad for p in P.trainable()]
     nonzero = 0
-    for g0, g1, w in zip(got[0], got[1], want):
+    # the shards see different hit counts (otherwise the test would not exercise the global normalisation)
+    assert got[0][1] + got[1][1] == cnt and got[0][1] != got[1][1], (got[0][1], got[1][1], cnt)
+    for g0, g1, w in zip(got[0][0], got[1][0], want):
         g0, g1 = torch.from_numpy(g0), torch.from_numpy(g1)
         assert torch.equal(g0, g1)                                    # every rank holds the identical reduced gradient
         scale = float(w.abs().max())

@@ -190,16 +190,12 @@ def test_fresh_scene_against_oracle():
 
 
 def test_bf16_mode_training_step_within_2e2_of_reference():
-    """Tensor-core (bf16) mode against the reference-generated golden step.
-
-    Rendered outputs, loss and d beta: within the north star's 2e-2 (max|a-b| / max|ref|) of the REFERENCE.
-    Parameter gradients of the trainable MLPs: a LeakyReLU net's gradient is discontinuous in its pre-activations, so
-    rounding the matmul operands to bf16 flips the sign of the ~0.4 % of units that sit within bf16 rounding of zero,
-    and each flip moves that unit's whole contribution.  On this 48-ray step with a random colour target the weight
-    gradients are sums with heavy cancellation, and the flips alone put ANY bf16-operand evaluation 2.5e-2 .. 4.7e-2
-    from the fp32 reference (measured with the oracle's bf16 arithmetic model on CPU, oracle/hotpath.py
-    BF16_OPERANDS).  So they are checked (a) within 2e-2 of that arithmetic model -- same roundings, same flips, only
-    the summation order differs -- and (b) within 8e-2 of the fp32 reference."""
+    """Tensor-core mode (fp16 forward operands, bf16 gradient operands) against the reference-generated 48-ray golden
+    step: rendered outputs, loss, d beta and all 14 weight / bias gradients within the north star's 2e-2
+    (max|a-b| / max|ref|) of the REFERENCE, directly -- no arithmetic model in between.  (With bf16 forward operands the
+    weight gradients sat at 2.4e-2 .. 5.4e-2: ~0.4 % of the LeakyReLU units lie within bf16 rounding of zero and each
+    sign flip moves that unit's whole contribution; fp16 operands cut the flips 8x at the same tensor throughput.)
+    The training-batch-scale version of this test is tests/test_gpu_hotpath_big.py."""
     from spurfies_b200.model import PointVolSDF, VolSDFLoss, default_conf
     g, P = load_golden()
     model = PointVolSDF(default_conf(), "24", "dtu", neural_points=g["scene"]["pts"], neural_colors=g["scene"]["colors"],
@@ -217,28 +213,16 @@ def test_bf16_mode_training_step_within_2e2_of_reference():
     errs["loss"] = abs(float(lo["loss"]) - float(g["train_loss"]["loss"])) / float(g["train_loss"]["loss"])
     got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
     errs["d density.beta"] = rel_err(got["density.beta"], g["train_grads"]["density.beta"])
-    print("bf16 mode vs reference golden:", {k: f"{v:.2e}" for k, v in errs.items()})
+    print("tc mode vs reference golden:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert all(v < 2e-2 for v in errs.values()), errs
-    # (a) the oracle evaluated with the mode's arithmetic model (CPU, a few seconds)
-    _, P2 = load_golden()
-    Pt = trainable(P2)
-    H.BF16_OPERANDS = True
-    try:
-        ro = H.render_forward(Pt, Pt.make_grid(), g["uv"], g["pose"], g["intrinsics"], H.SamplerCfg(), True, 1, g["rng"])
-        H.volsdf_loss(ro, g["gt"]["rgb"], g["gt"]["mask"][0, :, 0])["loss"].backward()
-    finally:
-        H.BF16_OPERANDS = False
-    model_grads = {}
-    for nm, layers in (("F_color", Pt.F_color), ("R", Pt.R)):
-        for i, (W, b) in enumerate(layers):
-            model_grads[f"{nm}.{2 * i}.weight"], model_grads[f"{nm}.{2 * i}.bias"] = W.grad, b.grad
-    e_model = {n: rel_err(got[n], r) for n, r in model_grads.items()}
-    e_ref = {n: rel_err(got[n], g["train_grads"][n]) for n in model_grads}
-    print("bf16 mode weight gradients vs bf16 arithmetic model:", {k: f"{v:.2e}" for k, v in e_model.items()})
-    print("bf16 mode weight gradients vs fp32 reference      :", {k: f"{v:.2e}" for k, v in e_ref.items()})
-    assert all(v < 2e-2 for v in e_model.values()), e_model
-    assert all(v < 8e-2 for v in e_ref.values()), e_ref
-    # per-point latent gradients come from a handful of pairs each: bound their aggregate error instead
+    names = [n for n in g["train_grads"] if n.startswith(("F_color.", "R."))]
+    e_ref = {n: rel_err(got[n], g["train_grads"][n]) for n in names}
+    print("tc mode weight gradients vs fp32 reference:", {k: f"{v:.2e}" for k, v in e_ref.items()})
+    assert len(names) == 14 and all(v < 2e-2 for v in e_ref.values()), e_ref
+    # per-point latent gradients come from a handful of pairs each on this 48-ray step: aggregate error (the max-norm
+    # is reported and bounded at batch scale in test_gpu_hotpath_big.py)
     for n in ("neural_feats_color", "neural_feats_geometry"):
         a, r = got[n].double().cpu(), g["train_grads"][n].double()
-        assert float((a - r).norm() / r.norm()) < 1e-1, (n, float((a - r).norm() / r.norm()))
+        fro = float((a - r).norm() / r.norm())
+        print(f"tc mode d {n}: fro {fro:.2e} max {rel_err(got[n], g['train_grads'][n]):.2e}")
+        assert fro < 5e-2, (n, fro)

@@ -64,9 +64,8 @@ def _pairs(slots, q, model):
 
 
 def test_geometry_field_tc_matches_bf16_emulation():
-    """The tcgen05 geometry kernel against a torch emulation that rounds at exactly the same points (forward operands --
-    inputs, weights, inter-layer activations -- to fp16, the operands of the d sdf / d input chain to bf16; fp32
-    accumulation) -- so the LeakyReLU masks coincide and only summation order differs.  (Against the fp32 kernel the per-row Jacobian differs by ~sqrt(fraction of sign flips): a piecewise-
+    """The tcgen05 geometry kernel against a torch emulation that rounds at exactly the same points (every operand --
+    inputs, weights, inter-layer activations, the rows of the d sdf / d input chain -- to fp16; fp32 accumulation) -- so the LeakyReLU masks coincide and only summation order differs.  (Against the fp32 kernel the per-row Jacobian differs by ~sqrt(fraction of sign flips): a piecewise-
     linear net's gradient is discontinuous in its input, see test_geometry_field_tc_vs_fp32.)"""
     from spurfies_b200 import fields
     from spurfies_b200.fields import SlotSet, geo_sdf_raw
@@ -90,11 +89,11 @@ def test_geometry_field_tc_matches_bf16_emulation():
     z4 = _hf(_leaky(z3)) @ _hf(W[3]).t() + b[3]
     sdf_row = _leaky(z4) @ pack.v5 + pack.c5
     mk = lambda z: torch.where(z > 0, 1.0, 0.01)
-    g4 = _bf(pack.v5 * mk(z4))
-    g3 = _bf((g4 @ _bf(W[3])) * mk(z3))
-    g2 = _bf((g3 @ _bf(W[2])) * mk(z2))
-    g1 = _bf((g2 @ _bf(W[1])) * mk(z1))
-    J = g1 @ _bf(W[0])                                  # [V,8,35]
+    g4 = _hf(pack.v5 * mk(z4))
+    g3 = _hf((g4 @ _hf(W[3])) * mk(z3))
+    g2 = _hf((g3 @ _hf(W[2])) * mk(z2))
+    g1 = _hf((g2 @ _hf(W[1])) * mk(z1))
+    J = g1 @ _hf(W[0])                                  # [V,8,35]
     ref_sdf = (wn * sdf_row).sum(-1)
     ref_grad = (wn[..., None] * J[..., 32:35]).sum(1)
     ref_jw = (wn[..., None] * J[..., :32]).reshape(-1, 32)
@@ -265,7 +264,7 @@ def test_wgrad_tc_multi(n_units, rpu):
     rows = (n_units * rpu + 127) // 128 * 128
     # (lda, N, db, fmt): fmt bit 0 / 1 = dz / act is bf16 (else fp16).  1 = bf16 gradient x fp16 saved activation (the
     # training step's products), 2 = the head's swapped a2^T @ dz3 product, 3 / 0 = both bf16 / both fp16
-    shapes = [(256, 256, True, 1), (128, 112, True, 1), (64, 32, False, 3), (64, 16, False, 2), (256, 256, False, 0)]
+    shapes = [(256, 256, True, 1), (128, 112, True, 1), (64, 32, False, 3), (64, 16, False, 2), (256, 256, True, 0)]
     dt = lambda bit, fmt: torch.bfloat16 if (fmt >> bit) & 1 else torch.float16
     dzs = [torch.randn(rows + 128, 256, generator=g).cuda().to(dt(0, f)) for _, _, _, f in shapes]
     acts = [torch.randn(rows + 128, lda, generator=g).cuda().to(dt(1, f)) for lda, _, _, f in shapes]
@@ -284,8 +283,9 @@ def test_wgrad_tc_multi(n_units, rpu):
     _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), rpu, n_units + 50, _lib.stream())
     torch.cuda.synchronize()
     for i, (lda, N, want_db, fmt) in enumerate(shapes):
-        ref = dzs[i][:rows].float().t() @ acts[i][:rows, :N].float()
+        bfr = lambda t: t.to(torch.bfloat16).float()   # an fp16 operand is rounded to bf16 before the MMA
+        ref = bfr(dzs[i][:rows]).t() @ bfr(acts[i][:rows, :N])
         assert float((outs[i][0] - ref).abs().max() / ref.abs().max()) < 1e-4, i
         if want_db:
-            refb = dzs[i][:rows].float().sum(0)
+            refb = bfr(dzs[i][:rows]).sum(0)
             assert float((outs[i][1] - refb).abs().max() / refb.abs().max()) < 1e-4, i
