@@ -20,6 +20,7 @@ using namespace tc;
 #define WG_STAGE_BYTES 65536
 #define WG_STAGES 3
 #define WG_SMEM (WG_STAGES * WG_STAGE_BYTES + 256)
+#define WGM_THREADS (TC_THREADS + 32)   // k_wgrad_multi: 8 compute warps + 1 producer warp
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_wgrad_tc(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ act, int lda, int N,
@@ -192,16 +193,22 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
         if (!(op == 0 ? conv_dz : conv_act)) continue;
         uint8_t* base = smem + st * WG_STAGE_BYTES + op * 32768;
         const int nchunk = (op == 0 ? 4 : act_panels) * 512;   // 16-byte chunks of the operand's stage region
-        for (int c = tid; c < nchunk; c += TC_THREADS) {
-          uint4 u = *reinterpret_cast<uint4*>(base + c * 16);
-          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+        // four chunks per thread and pass, all loads issued before the first conversion (nchunk is a multiple of 1024)
+#pragma unroll 1
+        for (int c0 = tid; c0 < nchunk; c0 += 4 * TC_THREADS) {
+          uint4 u[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
-            const float2 f = __half22float2(h);
-            w[e] = pack_bf16(f.x, f.y);
+          for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<uint4*>(base + (c0 + q * TC_THREADS) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+              w[e] = pack_bf16(f.x, f.y);
+            }
+            *reinterpret_cast<uint4*>(base + (c0 + q * TC_THREADS) * 16) = u[q];
           }
-          *reinterpret_cast<uint4*>(base + c * 16) = u;
         }
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the MMAs (async proxy) and ordered before the refill
@@ -269,7 +276,7 @@ k_wgrad_tiled(const uint8_t* __restrict__ dz, const uint8_t* __restrict__ act, i
 struct WgJobDev { const uint8_t* dz; const uint8_t* act; float* dW; float* db; int act_nkb, N, cta0, ncta, fmt; };
 struct WgJobsDev { WgJobDev j[SPF_WGRAD_MAX_JOBS]; int n; };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WGM_THREADS, 1)
 k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -320,8 +327,16 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
     for (int kb = 0; kb < act_panels; ++kb) bulk_g2s(sact + kb * 8192, gact + kb * 16384, 8192, bar_full + st);
   };
 
-  if (tid == 32)
-    for (int it = 0; it < WG_STAGES && it < my_tiles; ++it) load_tile(it);
+  if (warp == 8) {
+    // producer warp: refills a stage as soon as its MMAs have retired and all 8 compute warps have left it.  Decoupled
+    // from the compute warps (they synchronise among themselves on a named barrier), so waiting for an MMA to retire
+    // never holds up the conversion / bias sums of the following tiles.
+    if (lane == 0)
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it >= WG_STAGES) mbar_wait(bar_empty + it % WG_STAGES, (uint32_t)(((it / WG_STAGES) - 1) & 1));
+        load_tile(it);
+      }
+  } else
   for (int it = 0; it < my_tiles; ++it) {
     const int st = it % WG_STAGES;
     const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
@@ -333,20 +348,26 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
         if (!(op == 0 ? conv_dz : conv_act)) continue;
         uint8_t* base = smem + st * WG_STAGE_BYTES + op * 32768;
         const int nchunk = (op == 0 ? 4 : act_panels) * 512;   // 16-byte chunks of the operand's stage region
-        for (int c = tid; c < nchunk; c += TC_THREADS) {
-          uint4 u = *reinterpret_cast<uint4*>(base + c * 16);
-          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+        // four chunks per thread and pass, all loads issued before the first conversion (nchunk is a multiple of 1024)
+#pragma unroll 1
+        for (int c0 = tid; c0 < nchunk; c0 += 4 * TC_THREADS) {
+          uint4 u[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
-            const float2 f = __half22float2(h);
-            w[e] = pack_bf16(f.x, f.y);
+          for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<uint4*>(base + (c0 + q * TC_THREADS) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+              w[e] = pack_bf16(f.x, f.y);
+            }
+            *reinterpret_cast<uint4*>(base + (c0 + q * TC_THREADS) * 16) = u[q];
           }
-          *reinterpret_cast<uint4*>(base + c * 16) = u;
         }
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the MMAs (async proxy) and ordered before the refill
-      __syncthreads();
+      named_bar_sync(1, TC_THREADS);
     }
     if (warp == 0) {
       tc_fence_after();
@@ -372,10 +393,6 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_local(bar_empty + st);
-    if (tid == 32 && it + WG_STAGES < my_tiles) {
-      mbar_wait(bar_empty + st, ph);   // MMAs of tile `it` retired and every warp has read the stage
-      load_tile(it + WG_STAGES);
-    }
   }
   if (warp == 0) {
     if (elect_one()) mma_commit(bar_done);
@@ -383,8 +400,8 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
   }
   mbar_wait(bar_done, 0);
   tc_fence_after();
-  if (J.db) atomicAdd(J.db + tid, bsum);
-  {
+  if (J.db && warp < 8) atomicAdd(J.db + tid, bsum);
+  if (warp < 8) {
     const int out_row = 128 * (warp >> 2) + 32 * (warp & 3) + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 256;
     for (int c0 = 0; c0 < N; c0 += 32) {
@@ -428,7 +445,7 @@ extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, con
     used += c;
   }
   SPF_CUDA(cudaFuncSetAttribute(k_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
-  k_wgrad_multi<<<used, TC_THREADS, WG_SMEM, (cudaStream_t)stream_>>>(d, count, rows_per_unit);
+  k_wgrad_multi<<<used, WGM_THREADS, WG_SMEM, (cudaStream_t)stream_>>>(d, count, rows_per_unit);
   SPF_CHECK_LAUNCH("k_wgrad_multi");
   return SPF_OK;
 }

@@ -424,9 +424,9 @@ class PointVolSDF(nn.Module):
             # global-count normalisation of the count-normalised means (one 12-byte all-reduce, no host sync)
             from .dist import global_count_scales
             zero_c = torch.zeros((), dtype=torch.int64, device=dev)
-            loc = torch.stack([counts.get("pseudo", zero_c).to(torch.int64), counts.get("local", zero_c).to(torch.int64),
-                               slots.count.reshape(()).to(torch.int64)])
-            sc = global_count_scales(loc, world, group)
+            local_counts = torch.stack([counts.get("pseudo", zero_c).to(torch.int64),
+                                        counts.get("local", zero_c).to(torch.int64), slots.count.reshape(()).to(torch.int64)])
+            sc = global_count_scales(local_counts, world, group)
             pseudo, local_loss, eik_scale = pseudo * sc[0], local_loss * sc[1], sc[2]
         far_cfg = float(self.conf.ray_sampler.far)
         depth_vals = torch.where(ray_mask[:, None], t * depth_scale[:, None], torch.full_like(t, far_cfg))

@@ -29,6 +29,9 @@ def main():
     R = 512
     cam = scenes.camera(0, sc["cam_radius"])
     uv = (scenes.pixel_batch(R, 3) - torch.tensor([256.0, 192.0])) * 0.8 + torch.tensor([256.0, 192.0])  # some rays miss
+    # rays ordered by distance from the image centre: the first shard hits the object with (almost) every ray, the last
+    # one misses with most -> the count-normalised loss terms see very different denominators on the ranks
+    uv = uv[:, torch.argsort((uv[0] - torch.tensor([256.0, 192.0])).norm(dim=-1))]
     gt, rng = scenes.synthetic_gt(R, 3), scenes.rng_inputs(R, 3)
     ld = scenes.local_data(0, sc["cam_radius"], feat_res=(128, 96))
 
