@@ -155,6 +155,14 @@ int spf_head_bwd_f32(const spf_head_weights_f32* W, const int32_t* list, const i
                      const float* d_rgb /*[n,3] by slot*/, const float* rgb, const float* a1, const float* a2,
                      float* d_hbar, float* dzf, float* dz1, float* dz2, float* dz3, void* stream);
 
+/* exact-mode weight gradient (the reference's nn.Linear backward, pointneus_disent.py:76-84, 100-107, as plain fp32 FFMA:
+ * no library GEMM, no host synchronisation): dW [M,N] += dZ[:, :M]^T @ A[:, :N] and (db != NULL) db [M] += column sums of
+ * dZ over the first count[0] * rows_per_unit rows of dZ (row stride ldz).  Row i of dZ pairs with row i of A (row stride
+ * lda) or, with idx != NULL, with row idx[i] / idx_div.  dW / db are ACCUMULATED (zero them first). */
+int spf_wgrad_f32(const float* dz, int32_t ldz, int32_t M, const float* act, int32_t lda, int32_t N,
+                  const int32_t* idx /* optional */, int32_t idx_div, const int32_t* count, int32_t rows_per_unit,
+                  int64_t n_max, float* dW, float* db, void* stream);
+
 /* ---- a10 + a11: Laplace density + alpha compositing (density.py:21-30; pointneus_disent.py:894-908, 765-795)
  * Dense per-ray layout [R,Smax]; a slot is valid iff pidx[slot*K] >= 0.  ray_nvalid[r]==0 -> the ray is
  * "not hit" and gets the reference's fill values (pointneus_disent.py:817-854). */
@@ -186,8 +194,20 @@ int spf_sampler_iter(const float* z, const float* sdf, int32_t R, int32_t M, con
                      int32_t beta_iters, float bound_coef, float add_tiny, int32_t first_iter, float* beta_io,
                      int32_t final, int32_t N, const float* u /*[R,N] or NULL*/, const float* u_lin /*[N]*/,
                      float near, float far, const int32_t* extra_idx /*[n_extra]*/, int32_t n_extra,
-                     const float* cam_loc, const float* ray_dirs, float* out_z /*final: [R,N+2+n_extra]; else [R,N]*/,
+                     const float* cam_loc, const float* ray_dirs, float* out_z /*final: [R,N+2+n_extra], else [R,N]*/,
                      float* out_points /*[R,cols,3]*/, int32_t* flag_not_converged, void* stream);
+/* The same launch under DEVICE-side control of Algorithm 1's outer loop (ray_sampler.py:466-474: "while not converged and
+ * iterations left"), for the multi-iteration eval schedule without a host round trip per iteration.  state[0] = "not
+ * converged" flag of the current iteration (cleared by the caller, set by the probe), state[1] = "converged earlier, final
+ * draw made" (maintained by the caller: state[1] |= !state[0] after each non-final iteration).
+ * pred 1 (final == 0): probe; if state[1] the new samples are parked outside every grid instead (no further SDF work).
+ * pred 2 (final != 0): final draw only if !state[1] && !state[0] (this iteration converged).
+ * pred 3 (final != 0): final draw unless state[1] (last allowed iteration). */
+int spf_sampler_iter_pred(const float* z, const float* sdf, int32_t R, int32_t M, const float* beta_dev, float eps,
+                          int32_t beta_iters, float bound_coef, float add_tiny, int32_t first_iter, float* beta_io,
+                          int32_t final_, int32_t N, const float* u, const float* u_lin, float near_, float far_,
+                          const int32_t* extra_idx, int32_t n_extra, const float* cam_loc, const float* ray_dirs,
+                          float* out_z, float* out_points, int32_t* state /*[2]*/, int32_t pred, void* stream);
 /* merge sorted z [R,M] (+sdf) with new sorted samples [R,N] (+sdf) -> [R,M+N] (ray_sampler.py:405-415, 533) */
 int spf_sampler_merge(const float* z, const float* sdf, int32_t M, const float* zs, const float* sdf_s, int32_t N,
                       int32_t R, float* z_out, float* sdf_out, void* stream);

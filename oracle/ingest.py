@@ -1,10 +1,15 @@
 """TEST INFRASTRUCTURE ONLY (never imported by spurfies_b200/): CPU restatement of the reference's neural-point
 voxel down-sampling, spurfies/model/utils.py:6-59 (`construct_vox_points_closest`, `voxelize`).
 
-The reference uses torch_scatter's scatter_mean / scatter_min (absent here, and CUDA-atomic, hence not bit-reproducible
-run to run: the centroid's last bits and the tie-breaks of scatter_min depend on the atomics' order), so utils.py cannot
-be imported to generate fixtures: *parity unpinned* beyond this restatement.  scatter_mean -> index_add / count,
-scatter_min -> amin reduce + first index attaining it; everything else is the same torch ops in the same order."""
+The reference uses torch_scatter's scatter_mean / scatter_min (absent in this image; on CUDA they run on float atomics,
+so the centroid's last bits and the tie-breaks of scatter_min are not reproducible run to run even upstream).
+PINNED: tests/golden/ingest.pt holds the outputs of the reference's own utils.py functions, imported from
+/root/reference with torch_scatter replaced by a pure-torch shim of its documented CPU semantics
+(tests/golden/make_golden_ingest.py); tests/test_oracle_ingest.py checks this restatement against it (voxel set and
+order exact, kept point per voxel identical, centroid within one fp32 ulp of the fp32-summed reference), and
+tests/test_gpu_ingest.py checks the kernels against the same fixture.  scatter_mean -> index_add / count (here in
+fp64, rounded once), scatter_min -> amin reduce + first index attaining it; everything else is the same torch ops in
+the same order."""
 import torch
 
 

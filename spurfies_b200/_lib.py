@@ -112,6 +112,9 @@ _SIGS = {
     "spf_sampler_coarse": [_P, _P, _F, _F, _P, _P, _I, _I, _P, _P, _P],
     "spf_sampler_iter": [_P, _P, _I, _I, _P, _F, _I, _F, _F, _I, _P, _I, _I, _P, _P, _F, _F, _P, _I, _P, _P, _P, _P,
                          _P, _P],
+    "spf_sampler_iter_pred": [_P, _P, _I, _I, _P, _F, _I, _F, _F, _I, _P, _I, _I, _P, _P, _F, _F, _P, _I, _P, _P, _P, _P,
+                              _P, _I, _P],
+    "spf_wgrad_f32": [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _L, _P, _P, _P],
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],

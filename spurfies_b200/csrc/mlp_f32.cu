@@ -595,3 +595,92 @@ extern "C" int spf_head_bwd_f32(const spf_head_weights_f32* W, const int32_t* li
   SPF_CHECK_LAUNCH("k_head_bwd_f32");
   return SPF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// exact-mode weight gradient: dW[M][N] += dZ[:, :M]^T @ A[:, :N], db[M] += column sums of dZ, over the first
+// count * rows_per_unit compact rows (device-side count: no host synchronisation, CUDA-graph capturable).  Plain fp32
+// FFMA, split-K over row partitions with an fp32 atomic merge -- the reference's nn.Linear backward
+// (pointneus_disent.py:76-84, 100-107) without a library GEMM.  A's rows may be addressed through an index list
+// (row i of dZ pairs with row idx[i] / idx_div of A): the radiance head's hbar (by slot) and PE3(dir) (by ray) operands.
+// CTA = 64 x 64 output tile x one row partition; 256 threads, 4 x 4 register micro-tiles, 32-row shared-memory stages.
+// ------------------------------------------------------------------------------------------------
+#define WGF_ROWS 32
+__global__ void __launch_bounds__(256)
+k_wgrad_f32(const float* __restrict__ dz, int ldz, int M, const float* __restrict__ act, int lda, int N,
+            const int* __restrict__ idx, int idx_div, const int* __restrict__ count, int rows_per_unit, int parts,
+            float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ __align__(16) float sA[WGF_ROWS][64];
+  __shared__ __align__(16) float sB[WGF_ROWS][64];
+  __shared__ int sI[WGF_ROWS];
+  const long long rows = (long long)(*count) * rows_per_unit;
+  const int tiles_n = (N + 63) >> 6;
+  const int tm = (int)(blockIdx.y / tiles_n), tn = (int)(blockIdx.y % tiles_n);
+  long long chunk = (rows + parts - 1) / parts;
+  chunk = (chunk + WGF_ROWS - 1) / WGF_ROWS * WGF_ROWS;
+  const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+  if (r0 >= r1) return;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float bsum = 0.0f;
+  const int m0 = tm * 64, n0 = tn * 64;
+  for (long long r = r0; r < r1; r += WGF_ROWS) {
+    const int nr = (int)min((long long)WGF_ROWS, r1 - r);
+    __syncthreads();
+    if (tid < WGF_ROWS) sI[tid] = (idx && tid < nr) ? idx[r + tid] / idx_div : 0;
+    __syncthreads();
+    for (int e = tid; e < WGF_ROWS * 64; e += 256) {
+      const int k = e >> 6, c = e & 63;
+      float a = 0.0f, b = 0.0f;
+      if (k < nr) {
+        if (m0 + c < M) a = dz[(size_t)(r + k) * ldz + m0 + c];
+        if (n0 + c < N) b = act[(size_t)(idx ? (long long)sI[k] : r + k) * lda + n0 + c];
+      }
+      sA[k][c] = a;
+      sB[k][c] = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < WGF_ROWS; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (db && tn == 0 && tid < 64)
+      for (int k = 0; k < WGF_ROWS; ++k) bsum += sA[k][tid];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) atomicAdd(dW + (size_t)m * N + n, acc[i][j]);
+    }
+  if (db && tn == 0 && tid < 64 && m0 + tid < M) atomicAdd(db + m0 + tid, bsum);
+}
+
+extern "C" int spf_wgrad_f32(const float* dz, int32_t ldz, int32_t M, const float* act, int32_t lda, int32_t N,
+                             const int32_t* idx, int32_t idx_div, const int32_t* count, int32_t rows_per_unit,
+                             int64_t n_max, float* dW, float* db, void* stream_) {
+  if (!dz || !act || !count || !dW || M < 1 || N < 1 || ldz < M || lda < N || rows_per_unit < 1) return SPF_ERR_INVALID;
+  if (idx && idx_div < 1) return SPF_ERR_INVALID;
+  if (n_max <= 0) return SPF_OK;
+  const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  const long long max_rows = (long long)n_max * rows_per_unit;
+  long long parts = (4LL * spf_num_sms() + tiles - 1) / tiles;           // ~4 CTAs per SM in total
+  const long long max_parts = (max_rows + 4 * WGF_ROWS - 1) / (4 * WGF_ROWS);   // at least 128 rows per partition
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  dim3 grid((unsigned)parts, (unsigned)tiles);
+  k_wgrad_f32<<<grid, 256, 0, (cudaStream_t)stream_>>>(dz, ldz, M, act, lda, N, idx, idx_div, count, rows_per_unit,
+                                                        (int)parts, dW, db);
+  SPF_CHECK_LAUNCH("k_wgrad_f32");
+  return SPF_OK;
+}

@@ -383,10 +383,26 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
                                const float* __restrict__ u, const float* __restrict__ u_lin, float near_, float far_,
                                const int* __restrict__ extra_idx, int n_extra, const float* __restrict__ cam_loc,
                                const float* __restrict__ dirs, float* __restrict__ out_z, float* __restrict__ out_pts,
-                               int* __restrict__ flag) {
+                               int* __restrict__ flag, const int* __restrict__ state, int pred) {
   extern __shared__ float smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (pred && r < R) {
+    // device-side control flow of Algorithm 1's outer loop (ray_sampler.py:466-474) for the multi-iteration (eval)
+    // schedule: state[0] = "some ray's beta is still above beta0" (set by this iteration's probe launch), state[1] =
+    // "converged in an earlier iteration, the final draw has been made".  No host round trip decides what runs.
+    const int not_conv = state[0], done = state[1];
+    if (pred == 1 && done) {   // probe after convergence: park the new samples outside every grid (the SDF pass on
+      for (int j = lane; j < N; j += 32) {   // them then finds no neighbour and does no MLP work)
+        out_z[(size_t)r * N + j] = far_;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) out_pts[((size_t)r * N + j) * 3 + a] = 1.0e9f;
+      }
+      return;
+    }
+    if (pred == 2 && (done || not_conv)) return;   // final draw only in the iteration that converged
+    if (pred == 3 && done) return;                 // last allowed iteration: final draw unless already made
+  }
   const int stride = M + 1;
   float* sz = smem + (size_t)wid * 6 * stride;   // z
   float* sd = sz + stride;                        // sdf
@@ -555,7 +571,33 @@ extern "C" int spf_sampler_iter(const float* z, const float* sdf, int32_t R, int
              "sampler_iter smem attr");
   k_sampler_iter<<<(R + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream_>>>(
       z, sdf, R, M, beta_dev, eps, beta_iters, bound_coef, add_tiny, first_iter, beta_io, final_, N, u, u_lin, near_,
-      far_, extra_idx, n_extra, cam_loc, ray_dirs, out_z, out_points, flag_not_converged);
+      far_, extra_idx, n_extra, cam_loc, ray_dirs, out_z, out_points, flag_not_converged, nullptr, 0);
+  SPF_CHECK_LAUNCH("k_sampler_iter");
+  return SPF_OK;
+}
+
+extern "C" int spf_sampler_iter_pred(const float* z, const float* sdf, int32_t R, int32_t M, const float* beta_dev,
+                                     float eps, int32_t beta_iters, float bound_coef, float add_tiny, int32_t first_iter,
+                                     float* beta_io, int32_t final_, int32_t N, const float* u, const float* u_lin,
+                                     float near_, float far_, const int32_t* extra_idx, int32_t n_extra,
+                                     const float* cam_loc, const float* ray_dirs, float* out_z, float* out_points,
+                                     int32_t* state, int32_t pred, void* stream_) {
+  if (!z || !sdf || !beta_dev || !beta_io || !cam_loc || !ray_dirs || !out_z || !out_points || !state) return SPF_ERR_INVALID;
+  if (!u && !u_lin) return SPF_ERR_INVALID;
+  if (M < 2 || N < 1 || pred < 1 || pred > 3) return SPF_ERR_INVALID;
+  if ((pred == 1) != (final_ == 0)) return SPF_ERR_INVALID;
+  if (final_ && (N + 2 + n_extra > M)) return SPF_ERR_UNSUPPORTED;
+  if (n_extra > 0 && !extra_idx) return SPF_ERR_INVALID;
+  if (R <= 0) return SPF_OK;
+  const int wpb = 4;
+  size_t smem = (size_t)wpb * 6 * (M + 1) * sizeof(float);
+  if (smem > 200 * 1024) return SPF_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    SPF_CUDA(cudaFuncSetAttribute(k_sampler_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "sampler_iter smem attr");
+  k_sampler_iter<<<(R + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream_>>>(
+      z, sdf, R, M, beta_dev, eps, beta_iters, bound_coef, add_tiny, first_iter, beta_io, final_, N, u, u_lin, near_,
+      far_, extra_idx, n_extra, cam_loc, ray_dirs, out_z, out_points, state, state, pred);
   SPF_CHECK_LAUNCH("k_sampler_iter");
   return SPF_OK;
 }

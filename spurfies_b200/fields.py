@@ -1,9 +1,9 @@
 """Host-side wrappers (torch.autograd.Function) around the field / compositing kernels of libspurfies_b200.so.
 
 PyTorch is used for device memory, streams and autograd bookkeeping only; every tensor op on the hot path is a
-hand-written kernel reached through the C ABI (include/spurfies_b200.h).  The only library GEMMs are the plain
-weight-gradient products dW = dZ^T @ A of the EXACT (fp32) mode (cuBLAS through torch.matmul); the bf16 mode uses the
-split-K tcgen05 kernel (spf_wgrad_tc_multi).
+hand-written kernel reached through the C ABI (include/spurfies_b200.h).  There is no library GEMM: the weight-gradient
+products dW = dZ^T @ A run in the split-K tcgen05 kernel (spf_wgrad_tc_multi) in the tensor-core mode and in the split-K
+fp32 FFMA kernel (spf_wgrad_f32) in the exact mode.
 
 Layout: a *slot* is one query position (ray sample or point).  ``pidx`` [n, K] holds its neighbours sorted by
 (d^2, id), -1 padded.  Valid slots (>= 1 neighbour) are compacted on the device into ``list`` / ``count``; per-slot
@@ -374,12 +374,21 @@ class ColorField(torch.autograd.Function):
                 [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool,
                 targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])])
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
-        else:    # exact mode: plain fp32 library GEMMs over the compact pair rows (needs V on the host)
-            r = slots.V * slots.K
-            dW3, db3 = dz3[:r].t() @ h2[:r], dz3[:r].sum(0)
-            dW2, db2 = dz2[:r].t() @ h1[:r], dz2[:r].sum(0)
-            dW1, db1 = (dz1[:r].t() @ in0[:r])[:, :103], dz1[:r].sum(0)
+        else:    # exact mode: fp32 FFMA split-K kernel over the compact pair rows (device-side row count, no library GEMM)
+            dW3, db3 = _wgrad_f32(dz3, h2, 256, slots, slots.K)
+            dW2, db2 = _wgrad_f32(dz2, h1, 256, slots, slots.K)
+            dW1, db1 = _wgrad_f32(dz1, in0, 103, slots, slots.K)
         return (None if ctx.direct is not None else gfeat), dW1, db1, dW2, db2, dW3, db3, None, None, None, None
+
+
+def _wgrad_f32(dz, act, N, slots, rows_per_unit, want_db=True, M=256, idx=None, idx_div=1):
+    """dW [M,N] (+ db [M]) of the exact mode through spf_wgrad_f32: fp32 FFMA split-K, row count read on the device."""
+    dev = dz.device
+    dW = torch.zeros(M, N, dtype=torch.float32, device=dev)
+    db = torch.zeros(M, dtype=torch.float32, device=dev) if want_db else None
+    call("spf_wgrad_f32", ptr(dz), int(dz.stride(0)), int(M), ptr(act), int(act.stride(0)), int(N), ptr(idx), int(idx_div),
+         ptr(slots.count), int(rows_per_unit), slots.n, ptr(dW), ptr(db), stream())
+    return dW, db
 
 
 def positional_encoding(x: torch.Tensor, multires: int) -> torch.Tensor:
@@ -498,13 +507,14 @@ class RadianceHead(torch.autograd.Function):
         dz3 = Arena.get(tg + ".hdz3", (rows, 4), torch.float32, dev)
         call("spf_head_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
              ptr(a1), ptr(a2), ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3), stream())
-        V = slots.V
-        lst = slots.list[:V].long()
-        dW4, db4 = dzf[:V].t() @ hb[lst], dzf[:V].sum(0)
-        cat = torch.cat([positional_encoding(dirs[lst // ctx.Smax], 3), f[:V]], -1)
-        dR1, drb1 = dz1[:V].t() @ cat, dz1[:V].sum(0)
-        dR2, drb2 = dz2[:V].t() @ a1[:V], dz2[:V].sum(0)
-        dR3, drb3 = dz3[:V, :3].t() @ a2[:V], dz3[:V, :3].sum(0)
+        # exact mode: the same fp32 FFMA split-K kernel; hbar (by slot) and PE3(dir) (by ray) are read through the list
+        dW4, db4 = _wgrad_f32(dzf, hb, 256, slots, 1, idx=slots.list)
+        pe = positional_encoding(dirs, 3).contiguous()                                # [R, 21], per ray
+        dR1pe, drb1 = _wgrad_f32(dz1, pe, 21, slots, 1, idx=slots.list, idx_div=ctx.Smax)
+        dR1f, _ = _wgrad_f32(dz1, f, 256, slots, 1, want_db=False)
+        dR1 = torch.cat([dR1pe, dR1f], dim=1)
+        dR2, drb2 = _wgrad_f32(dz2, a1, 256, slots, 1)
+        dR3, drb3 = _wgrad_f32(dz3, a2, 256, slots, 1, M=3)
         return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, drb3, None, None, None
 
 

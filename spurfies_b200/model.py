@@ -134,14 +134,39 @@ class ErrorBoundSampler_pn:
              ptr(ray_dirs), R, M, ptr(z), ptr(pts), stream())
         beta0 = model.density.get_beta().detach().reshape(1).float().contiguous()
         beta_io = torch.empty(R, dtype=torch.float32, device=dev)
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        # device-side loop state of Algorithm 1 (ray_sampler.py:466-474): [0] = "some ray's beta still above beta0" in the
+        # current iteration, [1] = "converged in an earlier iteration".  The reference decides with a host sync per
+        # iteration (`beta.max() > beta0`, :468); here every launch of the multi-iteration (eval) schedule is predicated
+        # on this state instead (spf_sampler_iter_pred), so a full-image render has no host round trip.
+        state = torch.zeros(2, dtype=torch.int32, device=dev)
         n_extra = self.N_samples_extra
         cols = self.N_samples + 2 + n_extra
-        total_iters, not_converge = 0, True
+        total_iters = 0
         sdf = None
         new_pts, new_z = pts, z
-        z_out = None
-        while not_converge and total_iters < max_total_iters:
+        z_out = p_out = None
+
+        def final_draw(M, pred):
+            nonlocal z_out, p_out
+            u = None
+            if training:
+                u = (rng["u"] if rng is not None else torch.rand(R, self.N_samples)).to(dev, non_blocking=True).contiguous()
+                sidx = rng["sampling_idx"] if rng is not None else torch.randperm(M)[:n_extra]
+            else:
+                sidx = torch.linspace(0, M - 1, n_extra).long()
+            sidx = sidx.to(dev, dtype=torch.int32).contiguous()
+            if z_out is None:
+                z_out = torch.empty(R, cols, dtype=torch.float32, device=dev)
+                p_out = torch.empty(R, cols, 3, dtype=torch.float32, device=dev)
+            args = (ptr(z), ptr(sdf.contiguous()), R, M, ptr(beta0), float(self.eps), int(self.beta_iters), cst["bound_coef"],
+                    float(self.add_tiny), int(total_iters == 1), ptr(beta_io), 1, self.N_samples, ptr(u), ptr(cst["u_final"]),
+                    float(self.near), float(self.far), ptr(sidx), n_extra, ptr(o), ptr(ray_dirs), ptr(z_out), ptr(p_out))
+            if pred == 0:
+                call("spf_sampler_iter", *args, ptr(state), stream())
+            else:
+                call("spf_sampler_iter_pred", *args, ptr(state), pred, stream())
+
+        while total_iters < max_total_iters:
             with torch.no_grad():
                 s_new = model.sdf_importance(new_pts.view(-1, 3)).view(R, -1)
             if sdf is None:
@@ -155,41 +180,26 @@ class ErrorBoundSampler_pn:
                 z, sdf = z2, sdf2
             M = z.shape[1]
             total_iters += 1
-            last_allowed = total_iters >= max_total_iters
-            if last_allowed:
-                final = True  # no need to know `not_converge`: this is the last sampling either way
-            else:
-                # the reference decides with a host sync (`beta.max() > beta0`, ray_sampler.py:468); so do we,
-                # but only on the multi-iteration (eval) schedule.  Run the line search once to get beta.
-                flag.zero_()
-                probe_z = torch.empty(R, self.N_samples_eval, dtype=torch.float32, device=dev)
-                probe_p = torch.empty(R, self.N_samples_eval, 3, dtype=torch.float32, device=dev)
-                beta_probe = beta_io.clone()
-                call("spf_sampler_iter", ptr(z), ptr(sdf.contiguous()), R, M, ptr(beta0), float(self.eps),
-                     int(self.beta_iters), cst["bound_coef"], float(self.add_tiny), int(total_iters == 1),
-                     ptr(beta_probe), 0, self.N_samples_eval, None, ptr(cst["u_eval"]), float(self.near),
-                     float(self.far), None, 0, ptr(o), ptr(ray_dirs), ptr(probe_z), ptr(probe_p), ptr(flag), stream())
-                not_converge = bool(flag.item())
-                final = not not_converge
-                if not final:
-                    beta_io, new_z, new_pts = beta_probe, probe_z, probe_p
-                    continue
-            # final draw
-            u = None
-            if training:
-                u = (rng["u"] if rng is not None else torch.rand(R, self.N_samples)).to(dev, non_blocking=True).contiguous()
-                sidx = rng["sampling_idx"] if rng is not None else torch.randperm(M)[:n_extra]
-            else:
-                sidx = torch.linspace(0, M - 1, n_extra).long()
-            sidx = sidx.to(dev, dtype=torch.int32).contiguous()
-            z_out = torch.empty(R, cols, dtype=torch.float32, device=dev)
-            p_out = torch.empty(R, cols, 3, dtype=torch.float32, device=dev)
-            call("spf_sampler_iter", ptr(z), ptr(sdf.contiguous()), R, M, ptr(beta0), float(self.eps),
-                 int(self.beta_iters), cst["bound_coef"], float(self.add_tiny), int(total_iters == 1), ptr(beta_io), 1,
-                 self.N_samples, ptr(u), ptr(cst["u_final"]), float(self.near), float(self.far), ptr(sidx), n_extra,
-                 ptr(o), ptr(ray_dirs), ptr(z_out), ptr(p_out), ptr(flag), stream())
+            if total_iters >= max_total_iters:
+                # the last allowed iteration samples either way (ray_sampler.py:466); single-iteration (training)
+                # schedule: a plain launch
+                final_draw(M, 0 if max_total_iters == 1 else 3)
+                break
+            # probe: line search for beta, error-bound opacity, N_samples_eval new samples per ray; sets state[0] if
+            # any ray is still above beta0
+            state[0:1].zero_()
+            probe_z = torch.empty(R, self.N_samples_eval, dtype=torch.float32, device=dev)
+            probe_p = torch.empty(R, self.N_samples_eval, 3, dtype=torch.float32, device=dev)
+            beta_probe = beta_io.clone()
+            call("spf_sampler_iter_pred", ptr(z), ptr(sdf.contiguous()), R, M, ptr(beta0), float(self.eps),
+                 int(self.beta_iters), cst["bound_coef"], float(self.add_tiny), int(total_iters == 1),
+                 ptr(beta_probe), 0, self.N_samples_eval, None, ptr(cst["u_eval"]), float(self.near),
+                 float(self.far), None, 0, ptr(o), ptr(ray_dirs), ptr(probe_z), ptr(probe_p), ptr(state), 1, stream())
+            final_draw(M, 2)                                                  # runs only if this iteration converged
+            state[1:2].bitwise_or_((state[0:1] == 0).to(torch.int32))         # converged now or earlier
+            beta_io, new_z, new_pts = beta_probe, probe_z, probe_p
+        if z_out is not None:
             self.last_points = p_out
-            not_converge = False
         if z_out is None:  # max_total_iters == 0: the reference would fail on `samples`; return the coarse samples
             z_out, self.last_points = z, pts
         if rng is not None and "eik_idx" not in rng:

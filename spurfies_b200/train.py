@@ -111,12 +111,10 @@ class TrainStep:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def capture(self, batch, gt, rng) -> bool:
-        """Capture forward + loss + backward + (all-reduce) + clip + Adam into one CUDA graph.  Possible because the
-        bf16 step has no host synchronisation (slot counts stay on the device) and every big buffer is persistent.
+        """Capture forward + loss + backward + (all-reduce) + clip + Adam into one CUDA graph.  Possible in both
+        precision modes because the step has no host synchronisation (slot counts stay on the device) and every big
+        buffer is persistent.
         Inputs are copied into static tensors before each replay.  Returns False (and stays eager) if capture fails."""
-        if self.model.precision != "bf16":
-            self.graph_error = "exact (fp32) mode sizes its library wgrad GEMMs on the host"
-            return False
         try:
             import gc
             self.model._last = None

@@ -55,6 +55,27 @@ def test_sampler_matches_reference(setup):
     assert float(err.median()) < 2e-4 and float((err < 1e-3).float().mean()) > 0.9, err
 
 
+def test_eval_sampler_converges_on_the_device(setup):
+    """The eval schedule's outer loop (ray_sampler.py:466-474) runs under device-side predication (no host sync per
+    iteration).  With a huge error tolerance every ray converges in iteration 1: the final draw must be made there, the
+    remaining iterations must leave it alone, and the result must equal the single-iteration schedule's."""
+    g, P, model = setup
+    R = g["uv"].shape[1]
+    dirs, cam = g["ray_dirs"].cuda(), g["cam_loc"].cuda().expand(R, 3).contiguous()
+    model.eval()
+    s = model.ray_sampler
+    eps = s.eps
+    try:
+        s.eps = 1.0e6
+        z5, _ = s.get_z_vals(dirs, cam, model, -1, 1)
+        z1, _ = s.get_z_vals(dirs, cam, model, 1, 1)
+    finally:
+        s.eps = eps
+    assert z5.shape == z1.shape and torch.equal(z5, z1)
+    z_normal, _ = s.get_z_vals(dirs, cam, model, -1, 1)
+    assert not torch.equal(z_normal, z1)     # with the real tolerance the schedule does iterate
+
+
 def test_train_forward_backward_matches_reference(setup):
     from spurfies_b200.model import VolSDFLoss
     g, P, model = setup
