@@ -339,11 +339,16 @@ def other_rooflines(prof, prof_steps, pairs, model, pk):
     def per_step(name):
         return prof[name]["ms"] / prof_steps * 1e-3 if name in prof else None
 
-    def add(name, work, unit, peak, note):
+    def add(name, work, unit, peak, note, resident=None):
+        """resident="L2": the kernel's working set lives in the 126 MB L2 (ncu: DRAM < 1 %), so its algorithmic GB/s is
+        NOT a fraction of the HBM peak -- reported without `frac` and with the bound that actually limits it."""
         t = per_step(name)
         if t:
             a = work / t / (1e9 if unit == "GB/s" else 1e12)
-            out[name] = {"achieved": a, "unit": unit, "peak": peak, "frac": a / peak, "ms_per_step": t * 1e3, "work": note}
+            out[name] = {"achieved": a, "unit": unit, "peak": None if resident else peak, "frac": None if resident else a / peak,
+                         "ms_per_step": t * 1e3, "work": note}
+            if resident:
+                out[name]["resident"] = resident
 
     hbm, tc = pk["hbm_gbs"], pk["bf16_tflops_sustained"]
     # colour field: fwd 2*(103*256 + 2*256^2) FLOP/pair; dgrad 2*(2*256^2 + 256*64); wgrad 2*256*(256+256+103)
@@ -360,13 +365,18 @@ def other_rooflines(prof, prof_steps, pairs, model, pk):
     # C_q counted on the REFERENCE geometry (27 voxels of edge 0.075) from the grid's own cell table
     cq = getattr(model, "_bench_cq", None)
     if cq is not None:
-        add("spf_knn_slots", cq["queries"] * (12 + 216 + 32) + 16.0 * cq["candidates"], "GB/s", hbm,
-            "%d masked-in queries, mean C_q %.0f (reference 27-voxel candidate set)" % (cq["queries"], cq["candidates"] / max(cq["queries"], 1)))
+        scanned = cq.get("scanned", cq["candidates"])
+        add("spf_knn_slots", cq["queries"] * (12 + 216 + 32) + 16.0 * scanned, "GB/s", hbm,
+            "%d masked-in queries; bytes actually scanned: mean %.0f candidates x 16 B in the 27 search cells (the reference's "
+            "27 voxels hold %.0f); the 1.6 MB point table is L2-resident (ncu r02: DRAM 0.2 %%) and the kernel is issue-bound on "
+            "the warp top-K insertion (SM busy 79 %%), so neither HBM nor L2 bandwidth is its roof"
+            % (cq["queries"], scanned / max(cq["queries"], 1), cq["candidates"] / max(cq["queries"], 1)), resident="L2")
     # compositing: 28 B in + 4 B out per slot, + 28 B per ray
     R, S = model._last["t"].shape
     add("spf_composite_fwd", R * S * 32.0 + R * 28.0, "GB/s", hbm, "32 B/slot + 28 B/ray")
     # gather backward (geometry latents): per valid pair 128 B of Jacobian row read + 128 B read-modify-write of the latent row
-    add("spf_sdf_bwd", pairs * 384.0, "GB/s", hbm, "384 B/pair (jw row + RMW of the latent gradient row)")
+    add("spf_sdf_bwd", pairs * 384.0, "GB/s", hbm, "384 B/pair (128 B jw row streamed from HBM + 256 B read-modify-write of the "
+        "latent-gradient row, which stays in L2: the 12.8 MB table is re-touched ~12x per step)", resident="L2 (gradient table)")
     # sampler (1 iteration, train schedule): 128 x 8 B in + 64 x 4 B draws + 98 x 16 B out per ray
     add("spf_sampler_iter", R * (128 * 8 + 64 * 4 + 98 * 16.0), "GB/s", hbm, "2 848 B/ray; latency / SFU bound (11 error-bound evaluations per ray)")
     # TV regulariser: per point 8 neighbour rows gathered + 8 scattered (128 B each) + its own
@@ -379,8 +389,9 @@ def other_rooflines(prof, prof_steps, pairs, model, pk):
 
 
 def knn_candidate_stats(model):
-    """Sum over the last step's masked-in fine-pass queries of the number of points in their 27 reference voxels
-    (bench bookkeeping in torch, outside every timed region)."""
+    """For the last step's masked-in fine-pass queries: the number of points in their 27 REFERENCE voxels (edge 0.075:
+    the candidate set of knnquery.cu:263-277, SURVEY 8(d)'s algorithmic C_q) and in the 27 SEARCH cells the kernel
+    actually scans (edge >= radius).  Bench bookkeeping in torch, outside every timed region."""
     grid = model._voxel_grid_neural
     g = grid.handle
     loc = model._last.get("loc")
@@ -388,20 +399,27 @@ def knn_candidate_stats(model):
         return None
     q = loc[model._last["slot_sample"] >= 0]   # slots that passed the dilated-occupancy mask
     shift = torch.tensor(list(g.shift), device=q.device)
-    vs = torch.tensor(list(g.vsize), device=q.device)
-    dim = torch.tensor(list(g.dim), device=q.device)
-    c = torch.floor((q - shift) / vs).long()
-    cs = grid._cell_start.long()
-    total = torch.zeros((), dtype=torch.long, device=q.device)
-    for dx in (-1, 0, 1):
-        for dy in (-1, 0, 1):
-            cx, cy = c[:, 0] + dx, c[:, 1] + dy
-            ok = (cx >= 0) & (cx < dim[0]) & (cy >= 0) & (cy < dim[1])
-            z0 = (c[:, 2] - 1).clamp(0, int(dim[2]) - 1)
-            z1 = (c[:, 2] + 1).clamp(0, int(dim[2]) - 1)
-            base = cx.clamp(0, int(dim[0]) - 1) * (dim[1] * dim[2]) + cy.clamp(0, int(dim[1]) - 1) * dim[2]
-            total += ((cs[base + z1 + 1] - cs[base + z0]) * ok).sum()
-    return {"queries": int(q.shape[0]), "candidates": int(total)}
+
+    def count(cs, vs, dims):
+        vs = torch.tensor(list(vs), device=q.device)
+        dim = torch.tensor(list(dims), device=q.device)
+        c = torch.floor((q - shift) / vs).long()
+        cs = cs.long()
+        total = torch.zeros((), dtype=torch.long, device=q.device)
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                cx, cy = c[:, 0] + dx, c[:, 1] + dy
+                ok = (cx >= 0) & (cx < dim[0]) & (cy >= 0) & (cy < dim[1])
+                z0 = (c[:, 2] - 1).clamp(0, int(dim[2]) - 1)
+                z1 = (c[:, 2] + 1).clamp(0, int(dim[2]) - 1)
+                base = cx.clamp(0, int(dim[0]) - 1) * (dim[1] * dim[2]) + cy.clamp(0, int(dim[1]) - 1) * dim[2]
+                total += ((cs[base + z1 + 1] - cs[base + z0]) * ok).sum()
+        return int(total)
+
+    out = {"queries": int(q.shape[0]), "candidates": count(grid._cell_start, g.vsize, g.dim)}
+    if getattr(grid, "_search_radius", None) is not None:
+        out["scanned"] = count(grid._search_cell_start, [g.search_cell] * 3, g.search_dim)
+    return out
 
 
 def cpu_baseline(sample_rays=1024, repeats=3, threads=None, budget_s=None):
@@ -473,6 +491,36 @@ def run_reference(args):
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
+
+
+class PairCounter:
+    """Counts the pair rows every geometry-field launch processes (device-side counts, summed once at the end) by
+    wrapping fields.geo_sdf_raw for ONE untimed pass: the numerator of the eval / mesh workloads' tensor roofline."""
+    FWD = 2 * (35 * 256 + 3 * 256 * 256 + 256)       # executed FLOPs per pair row, forward only (F_geometry.8 + T folded)
+
+    def __enter__(self):
+        from spurfies_b200 import fields, mesh, model
+        self.mods = [m for m in (fields, mesh, model) if hasattr(m, "geo_sdf_raw")]
+        self.orig = fields.geo_sdf_raw
+        self.counts, self.flops = [], []
+
+        def wrapped(pack, slots, x, pts, feat_g, rbf, want_grad, want_jw, *a, **k):
+            self.counts.append(slots.count.clone())
+            self.flops.append(self.FWD * (2 if (want_grad or want_jw) else 1))
+            return self.orig(pack, slots, x, pts, feat_g, rbf, want_grad, want_jw, *a, **k)
+        for m in self.mods:
+            m.geo_sdf_raw = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            m.geo_sdf_raw = self.orig
+
+    def totals(self):
+        if not self.counts:
+            return 0.0, 0.0
+        c = torch.stack(self.counts).reshape(-1).double().cpu() * 8.0      # pair rows per launch
+        return float(c.sum()), float((c * torch.tensor(self.flops, dtype=torch.float64)).sum())
 
 
 def run_inference(args):
@@ -553,6 +601,10 @@ def run_inference(args):
     ms = e0.elapsed_time(e1)
     prof = _lib.profile_collect()
     _lib.profile_reset(False)
+    with PairCounter() as pc:      # one untimed pass: pair rows / executed FLOPs of the geometry-field launches of a pass
+        one(0)
+    torch.cuda.synchronize()
+    pair_rows, geo_flops = pc.totals()
     # end to end: inputs from pinned host memory, the step's result copied back to pinned host memory
     host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if torch.is_tensor(v)}
     barrier()
@@ -586,6 +638,37 @@ def run_inference(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk,
                 "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        pk = peaks()
+        kms = line["kernels_ms_per_step"]
+        per_rank = 1.0 / world     # this rank's share of the units (every rank runs the same kernels on its slice)
+        dom = "spf_sdf_fwd_tc" if args.precision == "bf16" else "spf_sdf_fwd_f32"
+        if dom in kms and geo_flops > 0:
+            a = geo_flops / (kms[dom] * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": dom + " (all launches of one pass on rank 0: coarse / sampler / fine)",
+                                "achieved": a, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                "frac": a / pk["bf16_tflops_sustained"], "traffic": None, "ms_per_step": kms[dom],
+                                "pair_rows_per_step": pair_rows, "peak_source": pk["source"] + " bf16 sustained",
+                                "note": "EXECUTED FLOPs (411 648 per pair row forward, x2 with the d sdf / d input chain) over "
+                                        "every pair row of the pass / summed launch time; no ncu capture of this workload -> "
+                                        "traffic null"}
+        other = {}
+
+        def add(name, nbytes, note):
+            if name in kms and kms[name] > 0:
+                g = nbytes / (kms[name] * 1e-3) / 1e9
+                other[name] = {"achieved": g, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": g / pk["hbm_gbs"],
+                               "ms_per_step": kms[name], "work": note}
+        if args.workload == "eval":
+            Rr, S = total * per_rank, 80
+            add("spf_composite_fwd", Rr * S * 32.0 + Rr * 28.0, "32 B/slot + 28 B/ray over %d rays" % Rr)
+            # eval schedule: probe launches read z, sdf [R, M] for M = 128..512 and write 128 x 16 B, plus the final draws
+            add("spf_sampler_iter", Rr * (sum(m * 8.0 for m in (128, 256, 384, 512, 640)) + 4 * 128 * 16.0 + 98 * 16.0),
+                "z, sdf in (M = 128..640) + new samples out, summed over the <= 5 iterations; latency / SFU bound")
+            add("spf_knn_points", Rr * 128 * 5 * (12 + 32.0), "12 B query + 32 B indices per probe point (the candidate scan is L2-resident)")
+        else:
+            add("spf_grid_points_mask", total * per_rank * 4.0 + pair_rows / 8.0 * 16.0, "4 B/grid point (the volume) + 16 B per kept point")
+            add("spf_scatter_f32", pair_rows / 8.0 * 12.0, "12 B per kept point")
+        line["rooflines_other"] = other
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
