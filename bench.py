@@ -323,10 +323,86 @@ def run_ours(args):
         "kernel_timing": ("CUDA events around each C-ABI call, eager re-run of %d of the timed steps (graph replay cannot be "
                           "instrumented)" % prof_steps) if graphed else "CUDA events around each C-ABI call inside the timed region",
     }
+    if args.reference_gpu:
+        try:
+            line["reference_gpu"] = reference_gpu(device, rays_gpu, sc, wl)
+        except Exception as e:  # noqa: BLE001 - a baseline that cannot run is reported, never fatal
+            line["reference_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if args.cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=3, budget_s=40.0)
     print(json.dumps(line))
     shutdown()
+
+
+def reference_gpu(device, rays, sc, wl, steps=3):
+    """The reference's GPU path on THIS GPU, same scene / batch / schedule (BASELINE.md section 2's stronger baseline):
+    its own CUDA kernels (oracle/_ref, compiled unmodified) under the restated torch graph (oracle/hotpath.py, pinned to
+    the reference's Python at 1e-5) -- fp32 cuBLAS MLPs, index_add_, three grid rebuilds and the tv_regul self-kNN per
+    step, exactly the work the reference's PointVolSDF.forward + backward does.  Also its kNN query alone next to ours on
+    identical sample positions.  Test infrastructure timed as a baseline; the product path never touches it."""
+    from oracle import gpu_ref as G
+    from oracle import hotpath as H
+    from spurfies_b200 import scenes
+    if G.load_reference_ext() is None:
+        return {"unavailable": "oracle/_ref/knnquery_cuda*.so not built"}
+    torch.cuda.empty_cache()
+    P = H.init_params(sc["pts"], sc["colors"], seed=0)
+    P.neural_feats_geometry *= 8.0
+    P.neural_feats_color[:, 3:] *= 500.0
+    if wl["scene"] != "dtu":
+        P.grid_args = dict(P.grid_args, ranges=(-2, -2, -2, 2, 2, 2))
+    P = G.params_to(P, device)
+    for t in P.trainable():
+        t.requires_grad_()
+    cu = lambda d: {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+    cam = cu(scenes.camera(0, sc["cam_radius"], RES))
+    grid = G.make_grid("reference", P)
+
+    def inputs(seed):
+        return (scenes.pixel_batch(rays, seed, RES).to(device), cu(scenes.rng_inputs(rays, seed)), cu(scenes.synthetic_gt(rays, seed)))
+
+    def step(seed):
+        uv, rng, gt = inputs(seed)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out, lo = G.training_step(P, grid, uv, cam, rng, gt)
+        e1.record()
+        torch.cuda.synchronize()
+        for t in P.trainable():
+            t.grad = None
+        return e0.elapsed_time(e1), out
+    step(1)                                                     # warm-up (cuBLAS handles, allocator)
+    times = []
+    for i in range(steps):
+        ms, out = step(100 + i)
+        times.append(ms)
+    ms_step = statistics.median(times)
+    # kNN alone on the last step's fine sample positions: the reference's set_pointset + query vs the product's
+    z = out["z_vals"].detach()
+    d, o = H.camera_rays(inputs(100 + steps - 1)[0], cam["pose"], cam["intrinsics"])
+    raypos = (o[:, None, :] + z[..., None] * d[0][:, None, :]).contiguous()
+    prod = G.make_grid("product", P)
+
+    def time_query(g, n=5):
+        g.query_dense(raypos, 8, 2.0, 80)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            g.query_dense(raypos, 8, 2.0, 80)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    t_ref, t_prod = time_query(grid), time_query(prod)
+    del grid, prod, out
+    torch.cuda.empty_cache()
+    return {"value": rays / (ms_step * 1e-3), "unit": "rays/s", "ms_per_step": ms_step, "steps_timed": len(times),
+            "kind": "reference CUDA kernels (oracle/_ref, unmodified) + restated torch graph on the same GPU, fp32, eager, no optimiser step",
+            "rays_per_step": rays,
+            "knn_query_ms": {"reference_set_pointset_plus_query": t_ref, "product_VoxelGrid_same_api": t_prod,
+                             "note": "identical [R,98,3] sample positions through the same public API (set_pointset + query, "
+                                     "utils.py:90-113 glue included); the product caches the grid on (data_ptr, version)"}}
 
 
 def other_rooflines(prof, prof_steps, pairs, model, pk):
@@ -689,6 +765,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core field kernels (2e-2 tolerance); fp32: exact SIMT kernels (1e-4)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-reference-gpu", dest="reference_gpu", action="store_false",
+                    help="skip timing the reference's GPU path (its compiled kernels + restated torch graph) on this GPU")
     ap.add_argument("--grad-compress", default=None, choices=["bf16"],
                     help="experimental, N > 1: all-reduce the latent-table gradients as bf16 (default: exact fp32 exchange)")
     ap.add_argument("--workload", default="train", choices=["train", "garden", "eval", "mesh"],
@@ -703,6 +781,7 @@ def main():
     else:
         if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.workload != "train":
             args.cpu_baseline = False   # the CPU baseline is reported at N = 1 only, on the headline workload
+            args.reference_gpu = False
         if args.workload in ("train", "garden"):
             run_ours(args)
         else:

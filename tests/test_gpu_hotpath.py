@@ -51,8 +51,11 @@ def test_sampler_matches_reference(setup):
     model.eval()
     z, _ = model.ray_sampler.get_z_vals(dirs, cam, model, -1, 1)
     assert z.shape == g["z_eval"].shape
+    # eval schedule (<= 5 iterations, deterministic draws): measured max 1.9e-6 of z in [0.5, 6] -- the same distance the
+    # reference's own sampler graph shows between GPU and CPU (tests/test_gpu_reference_path.py)
     err = (z.cpu() - g["z_eval"]).abs().max(-1).values
-    assert float(err.median()) < 2e-4 and float((err < 1e-3).float().mean()) > 0.9, err
+    print(f"eval sampler vs reference golden: per-ray max |dz| median {float(err.median()):.1e} max {float(err.max()):.1e}")
+    assert float(err.median()) < 1e-5 and float(err.max()) < 1e-4, err
 
 
 def test_eval_sampler_converges_on_the_device(setup):
@@ -168,10 +171,13 @@ def test_eval_forward_matches_reference(setup):
     with torch.no_grad():
         out = model(inp, fast=-1)
     ref = g["eval_out"]
+    errs = {}
     for k in ("rgb_values", "depth_values", "weights", "normal_map"):
         assert out[k].shape == ref[k].shape
-        e = rel_err(out[k], ref[k])
-        assert e < 2e-2, (k, e)  # the eval sampler is a 5-iteration chain of root searches: see test_sampler
+        errs[k] = rel_err(out[k], ref[k])
+    print("eval forward (fp32 mode) vs reference golden:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert all(errs[k] < 1e-4 for k in ("rgb_values", "depth_values", "weights")), errs
+    assert errs["normal_map"] < 1e-3, errs   # weighted sum of per-sample unit normals (d sdf / d x of a piecewise-linear net)
 
 
 def test_fresh_scene_against_oracle():

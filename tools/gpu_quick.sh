@@ -10,7 +10,7 @@ fi
 echo "pytest rc=$?" >> $O/${T}_pytest.log
 grep -E "passed|failed|FAILED|ERROR|rc=|tc vs|emulation|bf16 mode" $O/${T}_pytest.log | cut -c1-600 | tail -30
 if [ "${SKIP_BENCH:-0}" != "1" ]; then
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/${T}_bench.log 2> $O/${T}_bench.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-reference-gpu > $O/${T}_bench.log 2> $O/${T}_bench.err
   python - <<PY
 import json
 for line in open("$O/${T}_bench.log"):

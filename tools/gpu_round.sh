@@ -17,9 +17,9 @@ if [ "${SKIP_REF:-0}" != "1" ]; then
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${T}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cuda-graph --no-cpu-baseline > $O/${T}_bench_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cuda-graph --no-cpu-baseline --no-reference-gpu > $O/${T}_bench_ncu.log 2>&1
   echo "ncu launches rc=$?"; wc -l $O/${T}_launches.csv
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-k_sdf_tc2|k_knn_slots|k_knn_points|k_color_fwd_tc2|k_color_bwd_tc2|k_wgrad|k_composite_fwd|k_sampler_iter|k_head_fwd_tc2|k_head_bwd_tc2|k_sdf_bwd}" -s ${NCU_SKIP:-66} -c ${NCU_COUNT:-22} -f -o $O/${T}_top \
-    python bench.py --steps 2 --warmup 3 --no-cuda-graph --no-cpu-baseline > $O/${T}_bench_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cuda-graph --no-cpu-baseline --no-reference-gpu > $O/${T}_bench_ncu_full.log 2>&1
   echo "ncu full rc=$?"; ls -la $O/${T}_top.ncu-rep
 fi
