@@ -336,12 +336,13 @@ int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* list, const i
                      float* hbar, void* in0, void* h1, void* h2, uint32_t* m3, float* wn,
                      void* hb /* optional out: bf16 copy of hbar by COMPACT slot (position in list), tile layout */,
                      void* stream);
-/* as spf_color_bwd_f32; dz1..3 are bf16 [rows,256] in the TILE layout; h1 / h2 are not read (the sign words in m3 are) */
+/* as spf_color_bwd_f32; dz1..3 are fp16 [rows,256] in the TILE layout, scaled by S = gscale[0]; h1 / h2 are not read (the
+ * sign words in m3 are); feat_c_grad receives the unscaled gradient */
 int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                      const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                      const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
-                     const void* d_hb /* optional: d_hbar as bf16 by COMPACT slot, tile layout (then d_hbar may be NULL) */,
-                     void* stream);
+                     const void* d_hb /* optional: S * d_hbar as fp16 by COMPACT slot, tile layout (then d_hbar may be NULL) */,
+                     const float* gscale /* device [S, 1/S], see spf_head_bwd_tc */, void* stream);
 typedef struct {
   const uint8_t* w4p;    /* pack(F_color.6.weight) */
   const uint8_t* r1fp;   /* pack(R.0.weight[:, 21:277])  (the PE3(dir) columns enter through zpe) */
@@ -363,7 +364,11 @@ int spf_head_fwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int
 int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                     const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar, void* dzf,
                     void* dz1, void* dz2, void* dz3, float* drb3,
-                    void* d_hb /* optional out: d_hbar as bf16 by compact sample row, tile layout, INSTEAD of d_hbar */,
+                    void* d_hb /* optional out: S * d_hbar as fp16 by compact sample row, tile layout, INSTEAD of d_hbar */,
+                    const float* gscale /* device [S, 1/S].  The gradient chain (dZ tiles, d_hb) is fp16 scaled by a power of
+                                           two S picked per step from the largest upstream gradient (16 / max|d_rgb| rounded
+                                           down to a power of two) so that it sits in fp16's normal range; fp32 outputs
+                                           (d_hbar, drb3) are unscaled again. */,
                     void* stream);
 /* 16-bit 128B-swizzled k-block-major image of W [N][K] (row stride ld, fp32) or of its transpose (then W is [K][N]);
  * out holds ceil(K/64) * n_pad * 128 bytes.  `transpose` is a flag word: bit 0 = transpose, SPF_PACK_F16 = write fp16
@@ -399,7 +404,10 @@ typedef struct {
   int32_t reserved;
 } spf_wgrad_job;
 int spf_wgrad_tc_multi(const spf_wgrad_job* jobs /* HOST array */, int32_t n_jobs, const int32_t* count,
-                       int32_t rows_per_unit, int64_t n_max, void* stream);
+                       int32_t rows_per_unit, int64_t n_max,
+                       const float* gscale /* optional device [S, 1/S]: the gradient tiles carry the step's power-of-two
+                                              scale S (see spf_head_bwd_tc); dW / db are multiplied by 1/S */,
+                       void* stream);
 /* building-block self test: out[128][N] = A[128][K] (bf16 row-major) @ W^T with W given as a packed image */
 int spf_tc_gemm_test(const void* A, const void* Wpacked, int32_t N, int32_t K, float* out, void* stream);
 

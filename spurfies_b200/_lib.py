@@ -132,14 +132,14 @@ _SIGS = {
     "spf_tc_gemm_test": [_P, _P, _I, _I, _P, _P],
     "spf_sdf_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P],
     "spf_wgrad_tc": [_P, _P, _I, _I, _P, _I, _L, _I, _P, _P, _P],
-    "spf_wgrad_tc_multi": [_P, _I, _P, _I, _L, _P],
+    "spf_wgrad_tc_multi": [_P, _I, _P, _I, _L, _P, _P],
     "spf_head_fwd_tc": [_P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
-    "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spf_head_bwd_tc": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spf_pack_sw128": [_P, _I, _I, _I, _I, _I, _P, _P],
     "spf_pack_sw128_batch": [_P, _I, _P],
     "spf_head_zpe": [_P, _P, _I, _P, _I, _P, _P],
     "spf_color_fwd_tc": [_P, _P, _P, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P],
-    "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spf_color_bwd_tc": [_P, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 for _n, _a in _SIGS.items():
     _f = getattr(lib, _n)

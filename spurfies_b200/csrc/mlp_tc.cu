@@ -277,7 +277,7 @@ struct WgJobDev { const uint8_t* dz; const uint8_t* act; float* dW; float* db; i
 struct WgJobsDev { WgJobDev j[SPF_WGRAD_MAX_JOBS]; int n; };
 
 __global__ void __launch_bounds__(WGM_THREADS, 1)
-k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) {
+k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit, const float* __restrict__ gscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* bar_empty = bar_full + WG_STAGES;
@@ -311,8 +311,13 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
   // threads before the MMAs of that stage are issued: ~110 instructions per thread per 64-row tile, against a
   // ~3000-cycle HBM budget per tile.  Rounding fp16 -> bf16 here is a plain 2^-9 rounding of a wgrad operand; the
   // LeakyReLU sign decisions were taken in the forward pass on the fp16 values.
-  const uint32_t idesc = idesc_bf16_mn(128, N);
-  const bool conv_dz = !(J.fmt & 1), conv_act = !(J.fmt & 2);
+  // fmt 0: both fp16 (the training step: scaled-fp16 gradient tiles x fp16 saved activations) and fmt 3: both bf16 go
+  // straight to the tensor cores; a mixed pair has its fp16 operand converted to bf16 in shared memory first
+  const bool both_f16 = (J.fmt & 3) == 0;
+  const uint32_t idesc = idesc_f16k_mn(128, N, both_f16 ? FMT_F16 : FMT_BF16);
+  const bool conv_dz = !both_f16 && !(J.fmt & 1), conv_act = !both_f16 && !(J.fmt & 2);
+  const bool dz_f16 = both_f16;             // format of dZ in shared memory when the bias sums read it
+  const float inv_s = gscale ? gscale[1] : 1.0f;   // the gradient tiles carry the step's power-of-two scale S
   float bsum = 0.0f;
 
   auto load_tile = [&](int it) {   // one thread
@@ -387,8 +392,8 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
       const int c = (tid & 63) >> 3, e = tid & 7;
 #pragma unroll 8
       for (int k = 0; k < 64; ++k) {
-        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(pdz + k * 128 + ((c ^ (k & 7)) << 4) + e * 2);
-        bsum += __bfloat162float(v);
+        const unsigned short raw = *reinterpret_cast<const unsigned short*>(pdz + k * 128 + ((c ^ (k & 7)) << 4) + e * 2);
+        bsum += dz_f16 ? __half2float(__ushort_as_half(raw)) : __uint_as_float((unsigned)raw << 16);
       }
     }
     __syncwarp();
@@ -400,7 +405,7 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
   }
   mbar_wait(bar_done, 0);
   tc_fence_after();
-  if (J.db && warp < 8) atomicAdd(J.db + tid, bsum);
+  if (J.db && warp < 8) atomicAdd(J.db + tid, inv_s * bsum);
   if (warp < 8) {
     const int out_row = 128 * (warp >> 2) + 32 * (warp & 3) + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 256;
@@ -411,7 +416,7 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
       float* dst = J.dW + (size_t)out_row * N + c0;
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
-        if (c0 + 4 * j4 < N) atomicAdd(reinterpret_cast<float4*>(dst) + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+        if (c0 + 4 * j4 < N) atomicAdd(reinterpret_cast<float4*>(dst) + j4, make_float4(inv_s * v[4 * j4], inv_s * v[4 * j4 + 1], inv_s * v[4 * j4 + 2], inv_s * v[4 * j4 + 3]));
     }
   }
   tc_fence_before();
@@ -420,7 +425,7 @@ k_wgrad_multi(WgJobsDev jobs, const int* __restrict__ count, int rows_per_unit) 
 }
 
 extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, const int32_t* count, int32_t rows_per_unit,
-                                  int64_t n_max, void* stream_) {
+                                  int64_t n_max, const float* gscale, void* stream_) {
   if (!jobs || !count || n_jobs < 1 || n_jobs > SPF_WGRAD_MAX_JOBS || rows_per_unit < 1) return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
   WgJobsDev d;
@@ -445,7 +450,7 @@ extern "C" int spf_wgrad_tc_multi(const spf_wgrad_job* jobs, int32_t n_jobs, con
     used += c;
   }
   SPF_CUDA(cudaFuncSetAttribute(k_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM), "wgrad attr");
-  k_wgrad_multi<<<used, WGM_THREADS, WG_SMEM, (cudaStream_t)stream_>>>(d, count, rows_per_unit);
+  k_wgrad_multi<<<used, WGM_THREADS, WG_SMEM, (cudaStream_t)stream_>>>(d, count, rows_per_unit, gscale);
   SPF_CHECK_LAUNCH("k_wgrad_multi");
   return SPF_OK;
 }

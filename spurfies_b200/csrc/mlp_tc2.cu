@@ -509,12 +509,27 @@ extern "C" int spf_color_fwd_tc(const spf_color_weights_tc* W, const int32_t* li
 // ------------------------------------------------------------------------------------------------
 // colour field backward (dgrad chain).  dz rows are written (bf16) for the wgrad GEMMs; d latent is scatter-added.
 // ------------------------------------------------------------------------------------------------
+// Gradient tiles (dZ) are fp16 scaled by a per-step power of two S (gscale[0]; gscale[1] = 1 / S) chosen on the device
+// from the largest upstream gradient so that the chain sits in fp16's normal range (|dZ| ~ 16 at the top: 2^12 of
+// headroom for growth through the layers, 2^28 of range below): same tensor throughput as bf16, three more mantissa
+// bits, and the same 16-bit format as the saved forward activations -- tcgen05 kind::f16 needs A and B in ONE format, so
+// the weight-gradient MMAs consume both as stored.  Everything that leaves the chain (d latent, dW, db) is multiplied by
+// 1 / S in fp32; powers of two make that exact.
 __device__ __forceinline__ void mask_pack16(const float* vv, uint32_t sb, float scale, uint32_t* pk) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float m0 = (sb & (2u << (2 * i))) ? LEAKY * scale : scale;
     const float m1 = (sb & (0x20000u << (2 * i))) ? LEAKY * scale : scale;
-    pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+    pk[i] = pack_f16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+  }
+}
+__device__ __forceinline__ void unpack_f16x8(const uint32_t* w32, float* vv) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(w32[i]));
+    vv[2 * i] = lo;
+    vv[2 * i + 1] = hi;
   }
 }
 
@@ -522,21 +537,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int* __restrict__ count,
                 const int* __restrict__ pidx, const float* __restrict__ d_hbar, const uint32_t* __restrict__ msign,
                 const float* __restrict__ wn_in, __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2,
-                __nv_bfloat16* __restrict__ dz3, float* __restrict__ gfeat, const uint8_t* __restrict__ d_hb_c) {
+                __nv_bfloat16* __restrict__ dz3, float* __restrict__ gfeat, const uint8_t* __restrict__ d_hb_c,
+                const float* __restrict__ gscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = carve_bars(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int V = *count;
+  const float gS = gscale[0], gInvS = gscale[1];
   const int ntiles = (V + 15) / 16;
   const int nsuper = (ntiles + 3) / 4;
   const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   if (tid == 0) {
-    ch.L[0] = {W.w3tp, 4, 16, 256, FMT_BF16};
-    ch.L[1] = {W.w2tp, 4, 16, 256, FMT_BF16};
-    ch.L[2] = {W.w1ftp, 4, 16, 64, FMT_BF16};
+    ch.L[0] = {W.w3tp, 4, 16, 256, FMT_F16};
+    ch.L[1] = {W.w2tp, 4, 16, 256, FMT_F16};
+    ch.L[2] = {W.w1ftp, 4, 16, 64, FMT_F16};
     ch.n = 3;
   }
   const uint32_t tmem = setup(smem, B);
@@ -579,17 +596,12 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
               a[0] = *reinterpret_cast<const uint4*>(srcc + (c0 >> 6) * 16384 + sw128_off(hrow, (c0 & 63) >> 3));
               a[1] = *reinterpret_cast<const uint4*>(srcc + (c0 >> 6) * 16384 + sw128_off(hrow, ((c0 & 63) >> 3) + 1));
             }
-            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(a);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              vv[2 * i] = __uint_as_float(w32[i] << 16);
-              vv[2 * i + 1] = __uint_as_float(w32[i] & 0xffff0000u);
-            }
+            unpack_f16x8(reinterpret_cast<const uint32_t*>(a), vv);   // the head left it scaled by S already
           } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 d = sl >= 0 ? src[c * 4 + q] : make_float4(0, 0, 0, 0);
-              vv[4 * q] = d.x; vv[4 * q + 1] = d.y; vv[4 * q + 2] = d.z; vv[4 * q + 3] = d.w;
+              vv[4 * q] = gS * d.x; vv[4 * q + 1] = gS * d.y; vv[4 * q + 2] = gS * d.z; vv[4 * q + 3] = gS * d.w;
             }
           }
           const uint32_t sb = (c & 1) ? (mwa[c >> 1] << 1) : mwa[c >> 1];
@@ -648,7 +660,8 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
         if (p >= 0) {
           float4* dst = reinterpret_cast<float4*>(gfeat + (size_t)p * 64 + half * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) atomicAdd(dst + j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          for (int j4 = 0; j4 < 8; ++j4)
+            atomicAdd(dst + j4, make_float4(gInvS * v[4 * j4], gInvS * v[4 * j4 + 1], gInvS * v[4 * j4 + 2], gInvS * v[4 * j4 + 3]));
         }
       }
       tc_fence_before();
@@ -662,15 +675,15 @@ k_color_bwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
 extern "C" int spf_color_bwd_tc(const spf_color_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                 const int32_t* pidx, int32_t K, const float* d_hbar, const void* h1, const void* h2,
                                 const uint32_t* m3, const float* wn, void* dz1, void* dz2, void* dz3, float* feat_c_grad,
-                                const void* d_hb, void* stream_) {
-  if (!W || !list || !count || !pidx || (!d_hbar && !d_hb) || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad)
+                                const void* d_hb, const float* gscale, void* stream_) {
+  if (!W || !list || !count || !pidx || (!d_hbar && !d_hb) || !m3 || !wn || !dz1 || !dz2 || !dz3 || !feat_c_grad || !gscale)
     return SPF_ERR_INVALID;
   if (K != 8) return SPF_ERR_UNSUPPORTED;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_color_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "colorb_tc2 attr");
   k_color_bwd_tc2<<<pair_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
       *W, list, count, pidx, d_hbar, m3, wn, (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, feat_c_grad,
-      (const uint8_t*)d_hb);
+      (const uint8_t*)d_hb, gscale);
   SPF_CHECK_LAUNCH("k_color_bwd_tc2");
   return SPF_OK;
 }
@@ -902,22 +915,23 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
                const float* __restrict__ d_rgb, const float* __restrict__ rgb, const uint8_t* __restrict__ a1_s,
                const uint8_t* __restrict__ a2_s, float* __restrict__ d_hbar, __nv_bfloat16* __restrict__ dzf,
                __nv_bfloat16* __restrict__ dz1, __nv_bfloat16* __restrict__ dz2, __nv_bfloat16* __restrict__ dz3,
-               float* __restrict__ drb3, __nv_bfloat16* __restrict__ d_hb_c) {
+               float* __restrict__ drb3, __nv_bfloat16* __restrict__ d_hb_c, const float* __restrict__ gscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = carve_bars(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int V = *count;
+  const float gS = gscale[0], gInvS = gscale[1];
   const int ntiles = (V + 127) / 128;
   const int nsuper = (ntiles + 3) / 4;
   const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int n_iter = cid < nsuper ? (nsuper - cid + ncl - 1) / ncl : 0;
   Chain& ch = *reinterpret_cast<Chain*>(smem + OFF_CHAIN);
   if (tid == 0) {
-    ch.L[0] = {W.r3tp, 1, 1, 256, FMT_BF16};
-    ch.L[1] = {W.r2tp, 4, 16, 256, FMT_BF16};
-    ch.L[2] = {W.r1ftp, 4, 16, 256, FMT_BF16};
-    ch.L[3] = {W.w4tp, 4, 16, 256, FMT_BF16};
+    ch.L[0] = {W.r3tp, 1, 1, 256, FMT_F16};
+    ch.L[1] = {W.r2tp, 4, 16, 256, FMT_F16};
+    ch.L[2] = {W.r1ftp, 4, 16, 256, FMT_F16};
+    ch.L[3] = {W.w4tp, 4, 16, 256, FMT_F16};
     ch.n = 4;
   }
   const uint32_t tmem = setup(smem, B);
@@ -944,9 +958,9 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         float g[3] = {0.f, 0.f, 0.f};
         if (slot >= 0) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) { const float y = rgb[3 * (size_t)slot + c]; g[c] = d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
+          for (int c = 0; c < 3; ++c) { const float y = rgb[3 * (size_t)slot + c]; g[c] = gS * d_rgb[3 * (size_t)slot + c] * y * (1.0f - y); }
         }
-        const uint4 gz = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], 0.f), 0u, 0u);
+        const uint4 gz = make_uint4(pack_f16(g[0], g[1]), pack_f16(g[2], 0.f), 0u, 0u);   // dZ of R.4, scaled by S (see mask_pack16)
         if (tile_ok) {   // operand of the R.4 wgrad: tile layout with one k-block (64 columns, 16 used)
           uint8_t* zdst = reinterpret_cast<uint8_t*>(dz3) + (size_t)tile * 16384;
           *reinterpret_cast<uint4*>(zdst + sw128_off(row, 0)) = gz;
@@ -954,7 +968,7 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
         }
         if (drb3 && tile_ok) {                                                     // bias gradient of R.4
           const float s0 = warp_sum(g[0]), s1 = warp_sum(g[1]), s2 = warp_sum(g[2]);
-          if (lane == 0) { atomicAdd(drb3, s0); atomicAdd(drb3 + 1, s1); atomicAdd(drb3 + 2, s2); }
+          if (lane == 0) { atomicAdd(drb3, gInvS * s0); atomicAdd(drb3 + 1, gInvS * s1); atomicAdd(drb3 + 2, gInvS * s2); }
         }
         *reinterpret_cast<uint4*>(sA + sw128_off(row, 0)) = gz;                    // K = 16: chunks 0, 1 of k-block 0
         *reinterpret_cast<uint4*>(sA + sw128_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
@@ -1005,7 +1019,7 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           for (int i = 0; i < 8; ++i) {
             const float m0 = (pb & (1u << (2 * i))) ? 1.0f : LEAKY;
             const float m1 = (pb & (2u << (2 * i))) ? 1.0f : LEAKY;
-            pk[i] = pack_bf16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
+            pk[i] = pack_f16(vv[2 * i] * m0, vv[2 * i + 1] * m1);
           }
           uint8_t* dstA = sA + kb * 16384;
           *reinterpret_cast<uint4*>(dstA + sw128_off(row, ch0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1030,13 +1044,14 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
             const int c0 = half * 128 + c * 16;
             uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(vv[2 * i], vv[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) pk[i] = pack_f16(vv[2 * i], vv[2 * i + 1]);   // stays scaled by S for the colour backward
             uint8_t* dstA = sA + (c0 >> 6) * 16384;
             *reinterpret_cast<uint4*>(dstA + sw128_off(row, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dstA + sw128_off(row, ((c0 & 63) >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           } else if (slot >= 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[c * 4 + q] = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+            for (int q = 0; q < 4; ++q)
+              dst[c * 4 + q] = make_float4(gInvS * vv[4 * q], gInvS * vv[4 * q + 1], gInvS * vv[4 * q + 2], gInvS * vv[4 * q + 3]);
           }
         }
       }
@@ -1057,14 +1072,15 @@ k_head_bwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
 
 extern "C" int spf_head_bwd_tc(const spf_head_weights_tc* W, const int32_t* list, const int32_t* count, int64_t n_max,
                                const float* d_rgb, const float* rgb, const void* a1, const void* a2, float* d_hbar,
-                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* d_hb, void* stream_) {
-  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || (!d_hbar && !d_hb) || !dzf || !dz1 || !dz2 || !dz3)
+                               void* dzf, void* dz1, void* dz2, void* dz3, float* drb3, void* d_hb, const float* gscale,
+                               void* stream_) {
+  if (!W || !list || !count || !d_rgb || !rgb || !a1 || !a2 || (!d_hbar && !d_hb) || !dzf || !dz1 || !dz2 || !dz3 || !gscale)
     return SPF_ERR_INVALID;
   if (n_max <= 0) return SPF_OK;
   SPF_CUDA(cudaFuncSetAttribute(k_head_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "headb_tc2 attr");
   k_head_bwd_tc2<<<sample_grid(n_max), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(
       *W, list, count, d_rgb, rgb, (const uint8_t*)a1, (const uint8_t*)a2, d_hbar, (__nv_bfloat16*)dzf,
-      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3, (__nv_bfloat16*)d_hb);
+      (__nv_bfloat16*)dz1, (__nv_bfloat16*)dz2, (__nv_bfloat16*)dz3, drb3, (__nv_bfloat16*)d_hb, gscale);
   SPF_CHECK_LAUNCH("k_head_bwd_tc2");
   return SPF_OK;
 }

@@ -248,10 +248,10 @@ def _color_struct_tc(W, b, owner=""):
     imgs = [w1p]
     for nm, w, tr in (("c.w2p", W[1], False), ("c.w3p", W[2], False), ("c.w3tp", W[2], True), ("c.w2tp", W[1], True)):
         im = _img(owner + nm, dev, 131072)
-        pack_sw128_dev(im, w, 256, 256, transpose=tr, batch=jobs, f16=not tr)   # forward fp16, dgrad (transposed) bf16
+        pack_sw128_dev(im, w, 256, 256, transpose=tr, batch=jobs, f16=True)   # every operand of the tensor-core mode is fp16
         imgs.append(im)
     w1ftp = _img(owner + "c.w1ftp", dev, 32768)
-    pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39, batch=jobs)     # (W1[:, 39:103])^T : [64][256]
+    pack_sw128_dev(w1ftp, W[0], 64, 256, transpose=True, col_off=39, batch=jobs, f16=True)     # (W1[:, 39:103])^T : [64][256]
     imgs.append(w1ftp)
     pack_flush(jobs)   # one launch
     s = ColorWeightsTC()
@@ -278,16 +278,25 @@ class _ZeroPool:
         return out
 
 
-def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None):
+def grad_scale(upstream: torch.Tensor, target: float = 16.0) -> torch.Tensor:
+    """Device tensor [S, 1/S] for the tensor-core mode's fp16 gradient chain: S = the power of two that brings the largest
+    upstream gradient entry just below `target` (2^12 of fp16 headroom above for growth through the layers, 2^28 of range
+    below), computed on the device (no host sync, CUDA-graph capturable).  Powers of two make scaling / unscaling exact."""
+    amax = upstream.detach().abs().amax().to(torch.float32).clamp(min=1.0e-30)
+    e = torch.floor(torch.log2(target / amax)).clamp(-100.0, 100.0)
+    return torch.stack([torch.exp2(e), torch.exp2(-e)]).contiguous()
+
+
+def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None, gscale=None):
     """[(dz, act, lda, N, want_db[, fmt])] -> [(dW [256,N], db [256] or None)]: all products in ONE spf_wgrad_tc_multi launch
-    (every operand in the tile layout, lda a multiple of 64); no host sync.  fmt (default 1): bit 0 = dz is bf16, bit 1 =
-    act is bf16 -- normally dz is a bf16 gradient tile and act an fp16 saved forward activation.  ``targets[i] = (dW_grad, db_grad)`` (either may be
+    (every operand in the tile layout, lda a multiple of 64); no host sync.  fmt (default 0 = both fp16): bit 0 = dz is
+    bf16, bit 1 = act is bf16.  `gscale` = the step's [S, 1/S] (grad_scale): the gradient tiles carry S, the outputs do not.  ``targets[i] = (dW_grad, db_grad)`` (either may be
     None) makes job i accumulate straight into those gradient buffers (see _direct_grad); None is then returned for them."""
     arr = (_lib.WgradJob * len(jobs))()
     out = []
     for i, job in enumerate(jobs):
         dz, act, lda, N, want_db = job[:5]
-        arr[i].fmt = job[5] if len(job) > 5 else 1
+        arr[i].fmt = job[5] if len(job) > 5 else 0
         tW, tb = targets[i] if targets is not None else (None, None)
         dW = tW if tW is not None else pool.take(256, N)
         db = (tb if tb is not None else pool.take(256)) if want_db else None
@@ -295,7 +304,8 @@ def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None):
         arr[i].db = db.data_ptr() if db is not None else None
         arr[i].lda, arr[i].N = int(lda), int(N)
         out.append((None if tW is not None else dW, None if (tb is not None or db is None) else db))
-    call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(jobs), ptr(slots.count), int(rows_per_unit), slots.n, stream())
+    call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(jobs), ptr(slots.count), int(rows_per_unit), slots.n,
+         ptr(gscale), stream())
     return out
 
 
@@ -348,7 +358,7 @@ class ColorField(torch.autograd.Function):
         s, keep, W, b, in0, h1, h2, m3, wn = ctx.saved_t
         dev = d_hbar.device
         rows = slots.rows_alloc(slots.K)
-        adt = torch.bfloat16 if tcm else torch.float32
+        adt = torch.float16 if tcm else torch.float32
         tg = slots.tag
         dz1 = Arena.get(tg + ".dz1", (rows, 256), adt, dev)
         dz2 = Arena.get(tg + ".dz2", (rows, 256), adt, dev)
@@ -359,9 +369,12 @@ class ColorField(torch.autograd.Function):
             # RadianceHead.backward); `d_hbar` is then only the placeholder autograd carried here
             cached = getattr(slots, "d_hb_compact", None)
             compact = cached is not None and cached[1] == d_hbar.data_ptr()
+            # the gradient chain is fp16 scaled by the step's power of two S: the head's (its compact gradient already
+            # carries it) or, for a stand-alone call, one derived from this upstream gradient
+            gscale = cached[2] if compact else grad_scale(d_hbar)
             call("spf_color_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
                  None if compact else ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2),
-                 ptr(dz3), ptr(gfeat), ptr(cached[0]) if compact else None, stream())
+                 ptr(dz3), ptr(gfeat), ptr(cached[0]) if compact else None, ptr(gscale), stream())
             slots.d_hb_compact = None
         else:
             call("spf_color_bwd_f32", C.byref(s), ptr(slots.list), ptr(slots.count), slots.n, ptr(slots.pidx), slots.K,
@@ -372,7 +385,7 @@ class ColorField(torch.autograd.Function):
             tw = ctx.direct_w   # W1's gradient needs its columns permuted back: through the pool; the rest may go direct
             (dW3, db3), (dW2, db2), (dW1p, db1) = _wgrad_multi(
                 [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool,
-                targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])])
+                targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])], gscale=gscale)
             dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
         else:    # exact mode: fp32 FFMA split-K kernel over the compact pair rows (device-side row count, no library GEMM)
             dW3, db3 = _wgrad_f32(dz3, h2, 256, slots, slots.K)
@@ -421,7 +434,7 @@ class RadianceHead(torch.autograd.Function):
                                                ("h.r3tp", W[3], 256, 3, True, 256, 0), ("h.r2tp", W[2], 256, 256, True, 256, 0),
                                                ("h.r1ftp", W[1], 256, 256, True, 256, 21), ("h.w4tp", W[0], 256, 256, True, 256, 0)):
                 im = _img(slots.owner + nm, dev, image_bytes(npad, K_))
-                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co, batch=jobs, f16=not tr)
+                pack_sw128_dev(im, w, N_, K_, transpose=tr, n_pad=npad, col_off=co, batch=jobs, f16=True)
                 imgs.append(im)
             pack_flush(jobs)
             s = HeadWeightsTC()
@@ -475,14 +488,14 @@ class RadianceHead(torch.autograd.Function):
         n = slots.n
         tg = slots.tag
         rows = slots.rows_alloc(1)
-        adt = torch.bfloat16 if tcm else torch.float32
+        adt = torch.float16 if tcm else torch.float32
         d_hbar = Arena.get(tg + ".d_hbar", (n, 256), torch.float32, dev)  # consumed only at valid slots
         dzf = Arena.get(tg + ".hdzf", (rows, 256), adt, dev)
         dz1 = Arena.get(tg + ".hdz1", (rows, 256), adt, dev)
         dz2 = Arena.get(tg + ".hdz2", (rows, 256), adt, dev)
         if tcm:
             hb, pe = hb
-            dz3 = Arena.get(tg + ".hdz3b", (rows, 64), torch.bfloat16, dev)   # tile layout, one k-block (3 columns used)
+            dz3 = Arena.get(tg + ".hdz3b", (rows, 64), torch.float16, dev)   # tile layout, one k-block (3 columns used)
             pool = _ZeroPool(3 * 256 * 256 + 256 * 32 + 256 * 16 + 3 * 256 + 4, dev)
             tw = ctx.direct_w   # R.0 (concatenated) and R.4 (transposed) go through the pool; the rest may go direct
             drb3 = tw[7] if tw[7] is not None else pool.take(3)
@@ -490,17 +503,18 @@ class RadianceHead(torch.autograd.Function):
             # travel to ColorField.backward as bf16 by compact sample row in the tile layout (one coalesced bulk store per
             # tile here, half the bytes there); the fp32 `d_hbar` returned to autograd is then an unwritten placeholder
             d_hbc = None
+            gscale = grad_scale(d_rgb)   # [S, 1/S]: the fp16 gradient chain of this step (csrc/mlp_tc2.cu: mask_pack16)
             if ctx.from_color and getattr(slots, "single_consumer", False):
-                d_hbc = Arena.get(tg + ".d_hbc", (rows, 256), torch.bfloat16, dev)
-                slots.d_hb_compact = (d_hbc, d_hbar.data_ptr())
+                d_hbc = Arena.get(tg + ".d_hbc", (rows, 256), torch.float16, dev)
+                slots.d_hb_compact = (d_hbc, d_hbar.data_ptr(), gscale)
             call("spf_head_bwd_tc", C.byref(s), ptr(slots.list), ptr(slots.count), n, ptr(d_rgb.contiguous()), ptr(rgb),
                  ptr(a1), ptr(a2), None if d_hbc is not None else ptr(d_hbar), ptr(dzf), ptr(dz1), ptr(dz2), ptr(dz3),
-                 ptr(drb3), ptr(d_hbc), stream())
+                 ptr(drb3), ptr(d_hbc), ptr(gscale), stream())
             # every operand is in the tile layout (pe and dz3 with a single k-block)
             (dW4, db4), (dR1f, drb1), (dR1pe, _), (dR2, drb2), (dR3t, _) = _wgrad_multi(
                 [(dzf, hb, 256, 256, True), (dz1, f, 256, 256, True), (dz1, pe, 64, 32, False), (dz2, a1, 256, 256, True),
-                 (a2, dz3, 64, 16, False, 2)], slots, 1, pool,            # (a2^T @ dz3) = dR3^T, [256,16]: A fp16, B bf16
-                targets=[(tw[0], tw[1]), (None, tw[3]), (None, None), (tw[4], tw[5]), (None, None)])
+                 (a2, dz3, 64, 16, False)], slots, 1, pool,               # (a2^T @ dz3) = dR3^T, [256,16]
+                targets=[(tw[0], tw[1]), (None, tw[3]), (None, None), (tw[4], tw[5]), (None, None)], gscale=gscale)
             dR1 = torch.cat([dR1pe[:, :21], dR1f], dim=1)
             dR3 = dR3t[:, :3].t().contiguous()
             return d_hbar, dW4, db4, dR1, drb1, dR2, drb2, dR3, (None if tw[7] is not None else drb3), None, None, None

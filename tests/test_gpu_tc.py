@@ -262,8 +262,8 @@ def test_wgrad_tc_multi(n_units, rpu):
     from spurfies_b200 import _lib
     g = torch.Generator().manual_seed(7 * n_units + rpu)
     rows = (n_units * rpu + 127) // 128 * 128
-    # (lda, N, db, fmt): fmt bit 0 / 1 = dz / act is bf16 (else fp16).  1 = bf16 gradient x fp16 saved activation (the
-    # training step's products), 2 = the head's swapped a2^T @ dz3 product, 3 / 0 = both bf16 / both fp16
+    # (lda, N, db, fmt): fmt bit 0 / 1 = dz / act is bf16 (else fp16).  0 = both fp16 (the training step's products:
+    # scaled-fp16 gradient tiles x fp16 saved activations), 3 = both bf16, 1 / 2 = mixed (converted in shared memory)
     shapes = [(256, 256, True, 1), (128, 112, True, 1), (64, 32, False, 3), (64, 16, False, 2), (256, 256, True, 0)]
     dt = lambda bit, fmt: torch.bfloat16 if (fmt >> bit) & 1 else torch.float16
     dzs = [torch.randn(rows + 128, 256, generator=g).cuda().to(dt(0, f)) for _, _, _, f in shapes]
@@ -280,12 +280,15 @@ def test_wgrad_tc_multi(n_units, rpu):
         arr[i].db = db.data_ptr() if db is not None else None
         arr[i].lda, arr[i].N, arr[i].fmt = lda, N, fmt
         outs.append((dW, db))
-    _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), rpu, n_units + 50, _lib.stream())
+    gscale = torch.tensor([4.0, 0.25], device="cuda")   # the gradient operand carries S = 4: outputs are multiplied by 1/S
+    _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), rpu, n_units + 50, _lib.ptr(gscale),
+              _lib.stream())
     torch.cuda.synchronize()
     for i, (lda, N, want_db, fmt) in enumerate(shapes):
-        bfr = lambda t: t.to(torch.bfloat16).float()   # an fp16 operand is rounded to bf16 before the MMA
-        ref = bfr(dzs[i][:rows]).t() @ bfr(acts[i][:rows, :N])
+        # a mixed pair has its fp16 operand rounded to bf16 before the MMA; fp16 x fp16 and bf16 x bf16 run as stored
+        bfr = (lambda t: t.to(torch.bfloat16).float()) if fmt in (1, 2) else (lambda t: t.float())
+        ref = 0.25 * (bfr(dzs[i][:rows]).t() @ bfr(acts[i][:rows, :N]))
         assert float((outs[i][0] - ref).abs().max() / ref.abs().max()) < 1e-4, i
         if want_db:
-            refb = bfr(dzs[i][:rows]).sum(0)
+            refb = 0.25 * bfr(dzs[i][:rows]).sum(0)
             assert float((outs[i][1] - refb).abs().max() / refb.abs().max()) < 1e-4, i

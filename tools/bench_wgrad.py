@@ -14,10 +14,11 @@ rows = rows // 128 * 128
 units = rows // 8
 shapes = [(256, 256), (256, 256), (128, 112)]
 g = torch.Generator(device="cuda").manual_seed(0)
-dz = [torch.randn(rows + 128, 256, device="cuda", generator=g).to(torch.bfloat16) for _ in shapes]
+dz_src = [torch.randn(rows + 128, 256, device="cuda", generator=g) for _ in shapes]
 count = torch.tensor([units], dtype=torch.int32, device="cuda")
-for name, fmt, dt in (("bf16 x bf16", 3, torch.bfloat16), ("bf16 x fp16 (in-kernel conversion)", 1, torch.float16)):
+for name, fmt, dt in (("bf16 x bf16", 3, torch.bfloat16), ("bf16 x fp16 (in-kernel conversion)", 1, torch.float16), ("fp16 x fp16", 0, torch.float16)):
     act = [torch.randn(rows + 128, lda, device="cuda", generator=g).to(dt) for lda, _ in shapes]
+    dz = [d.to(torch.float16 if fmt == 0 else torch.bfloat16) for d in dz_src]
     arr = (_lib.WgradJob * len(shapes))()
     outs = []
     for i, (lda, N) in enumerate(shapes):
@@ -25,7 +26,7 @@ for name, fmt, dt in (("bf16 x bf16", 3, torch.bfloat16), ("bf16 x fp16 (in-kern
         outs.append((dW, db))
         arr[i].dz, arr[i].act, arr[i].dW, arr[i].db = dz[i].data_ptr(), act[i].data_ptr(), dW.data_ptr(), db.data_ptr()
         arr[i].lda, arr[i].N, arr[i].fmt = lda, N, fmt
-    run = lambda: _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), 8, units, _lib.stream())
+    run = lambda: _lib.call("spf_wgrad_tc_multi", C.cast(arr, C.c_void_p), len(shapes), _lib.ptr(count), 8, units, None, _lib.stream())
     for _ in range(3):
         run()
     torch.cuda.synchronize()
