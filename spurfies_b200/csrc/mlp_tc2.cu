@@ -149,10 +149,9 @@ k_sdf_tc2(spf_geo_weights_tc W, const int* __restrict__ list, const int* __restr
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bq = bias4[c * 4 + q];
-              float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
-              z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
-              pk[2 * q] = pack_f16(z0, z1);
-              pk[2 * q + 1] = pack_f16(z2, z3);
+              const float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
+              pk[2 * q] = leaky_f16x2(pack_f16(z0, z1), LEAKY_H2);      // sign(h) == sign(z): the sign bits below are exact
+              pk[2 * q + 1] = leaky_f16x2(pack_f16(z2, z3), LEAKY_H2);
               if (WITH_J) {
                 sb = (sb >> 2) | (pk[2 * q] & 0x80008000u);
                 sb = (sb >> 2) | (pk[2 * q + 1] & 0x80008000u);
@@ -425,6 +424,8 @@ k_color_fwd_tc2(spf_color_weights_tc W, const int* __restrict__ list, const int*
           for (int q = 0; q < 4; ++q) {
             const float4 bq = bias4[c * 4 + q];
             float z0 = vv[4 * q] + bq.x, z1 = vv[4 * q + 1] + bq.y, z2 = vv[4 * q + 2] + bq.z, z3 = vv[4 * q + 3] + bq.w;
+            // (LeakyReLU on the packed fp16 pair, as in the geometry / head kernels, was measured here and rejected: this
+            // kernel also needs the fp32 values in its last layer, and the extra code path cost registers: 0.588 -> 0.632 ms)
             z0 = fmaxf(z0, LEAKY * z0); z1 = fmaxf(z1, LEAKY * z1); z2 = fmaxf(z2, LEAKY * z2); z3 = fmaxf(z3, LEAKY * z3);
             vv[4 * q] = z0; vv[4 * q + 1] = z1; vv[4 * q + 2] = z2; vv[4 * q + 3] = z3;
             pk[2 * q] = pack_f16(z0, z1);
@@ -835,7 +836,7 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
       for (int l = 0; l < 3; ++l) {
         const float4* bias4 = l == 1 ? zrow4 : reinterpret_cast<const float4*>(s_bias + (l == 0 ? 0 : 256) + half * 128);
         __nv_bfloat16* dst = l == 0 ? f_s : (l == 1 ? a1_s : a2_s);
-        const float slope = l == 0 ? 1.0f : LEAKY;   // F_color.6 has no activation
+        const uint32_t slope2 = l == 0 ? ONE_H2 : LEAKY_H2;   // F_color.6 has no activation
         wait_acc(B, t, acc_par);
         if ((tid & 255) == 0) TL(6, t, l);
         drain_store(t);
@@ -853,10 +854,9 @@ k_head_fwd_tc2(spf_head_weights_tc W, const int* __restrict__ list, const int* _
           uint32_t pk[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float z0 = vv[4 * q] + bq[q].x, z1 = vv[4 * q + 1] + bq[q].y, z2 = vv[4 * q + 2] + bq[q].z, z3 = vv[4 * q + 3] + bq[q].w;
-            z0 = fmaxf(z0, slope * z0); z1 = fmaxf(z1, slope * z1); z2 = fmaxf(z2, slope * z2); z3 = fmaxf(z3, slope * z3);
-            pk[2 * q] = pack_f16(z0, z1);
-            pk[2 * q + 1] = pack_f16(z2, z3);
+            const float z0 = vv[4 * q] + bq[q].x, z1 = vv[4 * q + 1] + bq[q].y, z2 = vv[4 * q + 2] + bq[q].z, z3 = vv[4 * q + 3] + bq[q].w;
+            pk[2 * q] = leaky_f16x2(pack_f16(z0, z1), slope2);
+            pk[2 * q + 1] = leaky_f16x2(pack_f16(z2, z3), slope2);
           }
           const int c0 = half * 128 + c * 16;
           uint8_t* dstA = sA + (c0 >> 6) * 16384;

@@ -237,6 +237,18 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// LeakyReLU on a packed fp16 pair: max(h, slope * h) as two f16x2 instructions for two elements (the fp32 form costs two
+// per element).  Applied AFTER the fp32 bias add and the rounding to fp16, so the sign of every pre-activation -- the
+// only thing the backward's masks depend on -- is exactly the fp32 one; the negative branch is rounded twice (2^-12
+// relative of a value that is already 100x smaller).  slope2 = the slope as a packed fp16 pair (0.01 -> 0x211F211F).
+__device__ __forceinline__ uint32_t leaky_f16x2(uint32_t h, uint32_t slope2) {
+  uint32_t m, r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(slope2));
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h), "r"(m));
+  return r;
+}
+constexpr uint32_t LEAKY_H2 = 0x211F211Fu;   // 0.01 (0.010002) as fp16 x 2
+constexpr uint32_t ONE_H2 = 0x3C003C00u;     // 1.0 as fp16 x 2 (a linear layer through the same code path)
 __device__ __forceinline__ float f16_round(float a) {   // the value pack_f16 stores, back in fp32
   unsigned short h;
   asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(a));
