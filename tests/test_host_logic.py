@@ -81,5 +81,6 @@ def test_pack_jobs_struct_matches_the_header():
     import ctypes as C
     from spurfies_b200 import _lib
     assert C.sizeof(_lib.PackJob) == 2 * C.sizeof(C.c_void_p) + 6 * 4
-    assert C.sizeof(_lib.WgradJob) == 4 * C.sizeof(C.c_void_p) + 2 * 4
+    assert C.sizeof(_lib.WgradJob) == 4 * C.sizeof(C.c_void_p) + 4 * 4          # lda, N, fmt, reserved
     assert _lib.PackJob.out.offset == 8 and _lib.PackJob.ld.offset == 16 and _lib.WgradJob.lda.offset == 32
+    assert _lib.WgradJob.fmt.offset == 40
