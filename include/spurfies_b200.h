@@ -217,6 +217,11 @@ int spf_sampler_merge(const float* z, const float* sdf, int32_t M, const float* 
 int spf_tv_fwd_bwd(const float* pts, const float* feat_g /*[N,32]*/, const int32_t* self_pidx /*[N,K]*/,
                    int32_t N, int32_t K, float* value /*[1]*/, float* grad /*[N,32] or NULL (accumulated)*/,
                    float grad_scale, void* stream);
+/* the same over the points [first, first + count) only, value and gradient multiplied by `scale`: a data-parallel rank
+ * computes its 1/W slice of the (ray-independent) regulariser with scale = W, so that the gradient average over the
+ * ranks is the full term (the reference recomputes all of it on its single GPU every step, utils.py:221-281) */
+int spf_tv_fwd_bwd_range(const float* pts, const float* feat_g, const int32_t* self_pidx, int32_t N, int32_t K,
+                         int32_t first, int32_t count, float* value, float* grad, float scale, void* stream);
 
 /* ---- a14: VolSDFLoss (spurfies/model/loss.py:51-100), forward and gradients in two launches ----------------------
  * terms[8] = {loss, rgb_loss, eikonal_loss, tv_loss, mask_loss, local_loss, pseudo_loss, #valid samples};

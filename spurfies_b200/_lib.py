@@ -117,6 +117,7 @@ _SIGS = {
     "spf_wgrad_f32": [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _L, _P, _P, _P],
     "spf_sampler_merge": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
     "spf_tv_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _F, _P],
+    "spf_tv_fwd_bwd_range": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P],
     "spf_camera_rays": [_P, _P, _P, _I, _P, _P, _P, _P],
     "spf_ray_points": [_P, _P, _P, _I, _P, _P],
     "spf_pseudo_loss": [_P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],

@@ -644,11 +644,14 @@ extern "C" int spf_sampler_merge(const float* z, const float* sdf, int32_t M, co
 // one lane per latent channel (C_g = 32).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_tv(const float* __restrict__ pts, const float* __restrict__ feat, const int* __restrict__ nbr, int N,
-                     int K, float* __restrict__ value, float* __restrict__ grad, float grad_scale) {
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                     int K, int first, int count, float* __restrict__ value, float* __restrict__ grad, float grad_scale) {
+  // points [first, first + count) of the N: a data-parallel rank takes one slice of the (ray-independent) regulariser
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int i = first + li;
   int lane = threadIdx.x & 31;
   float tv_i = 0.0f;
-  if (i < N) {
+  const bool active = li < count && i < N;
+  if (active) {
     // utils.py:236-253: pad with self, drop self when other neighbours exist
     int my = lane < K ? nbr[(size_t)i * K + lane] : -1;
     bool has = __any_sync(SPF_FULL, my >= 0);
@@ -680,25 +683,30 @@ __global__ void k_tv(const float* __restrict__ pts, const float* __restrict__ fe
     if (grad && gi != 0.0f) atomicAdd(&grad[(size_t)i * 32 + lane], gi);
   }
   __shared__ float s_v[8];
-  if (lane == 0) s_v[threadIdx.x >> 5] = (i < N) ? tv_i : 0.0f;
+  if (lane == 0) s_v[threadIdx.x >> 5] = active ? tv_i : 0.0f;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.0f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_v[w];
-    atomicAdd(value, t / (float)N);
+    atomicAdd(value, grad_scale * t / (float)N);
   }
+}
+
+extern "C" int spf_tv_fwd_bwd_range(const float* pts, const float* feat_g, const int32_t* self_pidx, int32_t N, int32_t K,
+                                    int32_t first, int32_t count, float* value, float* grad, float scale, void* stream_) {
+  if (!pts || !feat_g || !self_pidx || !value || first < 0 || count < 0) return SPF_ERR_INVALID;
+  if (K > 32) return SPF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPF_CUDA(cudaMemsetAsync(value, 0, sizeof(float), st), "tv memset");
+  if (N <= 0 || count == 0) return SPF_OK;
+  k_tv<<<(count + 7) / 8, 256, 0, st>>>(pts, feat_g, self_pidx, N, K, first, count, value, grad, scale);
+  SPF_CHECK_LAUNCH("k_tv");
+  return SPF_OK;
 }
 
 extern "C" int spf_tv_fwd_bwd(const float* pts, const float* feat_g, const int32_t* self_pidx, int32_t N, int32_t K,
                               float* value, float* grad, float grad_scale, void* stream_) {
-  if (!pts || !feat_g || !self_pidx || !value) return SPF_ERR_INVALID;
-  if (K > 32) return SPF_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream_;
-  SPF_CUDA(cudaMemsetAsync(value, 0, sizeof(float), st), "tv memset");
-  if (N <= 0) return SPF_OK;
-  k_tv<<<(N + 7) / 8, 256, 0, st>>>(pts, feat_g, self_pidx, N, K, value, grad, grad_scale);
-  SPF_CHECK_LAUNCH("k_tv");
-  return SPF_OK;
+  return spf_tv_fwd_bwd_range(pts, feat_g, self_pidx, N, K, 0, N, value, grad, grad_scale, stream_);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -625,13 +625,15 @@ class TVRegul(torch.autograd.Function):
     """tv_regul (utils.py:221-281) on the cached self-kNN lists of the (static) neural points."""
 
     @staticmethod
-    def forward(ctx, feat_g, pts, self_pidx):
+    def forward(ctx, feat_g, pts, self_pidx, first=0, count=None, scale=1.0):
+        """`first` / `count` / `scale`: a data-parallel rank evaluates its slice of the points with scale = world size
+        (value and gradient), so that the average over the ranks is the full regulariser."""
         N, K = self_pidx.shape
         dev = feat_g.device
         value = torch.zeros(1, dtype=torch.float32, device=dev)
         grad = torch.zeros_like(feat_g, dtype=torch.float32) if ctx.needs_input_grad[0] else None
-        call("spf_tv_fwd_bwd", ptr(pts), ptr(feat_g.detach().contiguous()), ptr(self_pidx), N, K, ptr(value), ptr(grad),
-             1.0, stream())
+        call("spf_tv_fwd_bwd_range", ptr(pts), ptr(feat_g.detach().contiguous()), ptr(self_pidx), N, K, int(first),
+             int(N if count is None else count), ptr(value), ptr(grad), float(scale), stream())
         ctx.grad = grad
         ctx.direct = _direct_grad(feat_g) if grad is not None else None
         return value.reshape(())
@@ -640,8 +642,8 @@ class TVRegul(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.direct is not None:
             ctx.direct.addcmul_(ctx.grad, g)   # one pass: grad buffer += unit gradient * upstream scalar
-            return None, None, None
-        return (ctx.grad * g if ctx.grad is not None else None), None, None
+            return None, None, None, None, None, None
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ f4: local loss

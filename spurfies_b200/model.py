@@ -360,6 +360,14 @@ class PointVolSDF(nn.Module):
         key = (self.neural_pts.data_ptr(), self.neural_pts._version)
         if self._self_knn is None or self._self_knn[0] != key:
             self._self_knn = (key, self._grid().query_points(self.neural_pts, self.conf.k, self.conf.r))
+        world, group = self._dp
+        if world > 1 and self.training:
+            # ray-independent term: every rank evaluates 1/world of the points, scaled by world, so that the gradient
+            # average over the ranks is the whole regulariser (each rank reports its share x world as the term's value)
+            import torch.distributed as dist
+            from .dist import shard_range
+            lo, hi = shard_range(self.neural_pts.shape[0], dist.get_rank(group), world)
+            return TVRegul.apply(self.neural_feats_geometry, self.neural_pts, self._self_knn[1], lo, hi - lo, float(world))
         return TVRegul.apply(self.neural_feats_geometry, self.neural_pts, self._self_knn[1])
 
     # ------------------------------------------------------------------ forward (pointneus_disent.py:614-892)

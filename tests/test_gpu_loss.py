@@ -59,3 +59,31 @@ def _torch_path(loss_mod, out, gt):
     o["loss"] = (loss_mod.rgb_weight * o["rgb_loss"] + loss_mod.eikonal_weight * o["eikonal_loss"] + loss_mod.tv_weight * o["tv_loss"]
                  + loss_mod.local_weight * o["local_loss"] + loss_mod.pseudo_weight * o["pseudo_loss"] + o["mask_loss"])
     return o
+
+
+@pytest.mark.parametrize("world", [2, 8, 3])
+def test_tv_point_slices_average_to_the_whole_regulariser(world):
+    """spf_tv_fwd_bwd_range: a data-parallel rank evaluates 1/world of the points scaled by world; the AVERAGE over the
+    ranks (what the gradient all-reduce + 1/world computes) is the whole tv_regul (utils.py:221-281)."""
+    from spurfies_b200 import scenes
+    from spurfies_b200.dist import shard_range
+    from spurfies_b200.fields import TVRegul
+    from spurfies_b200.model import PointVolSDF, default_conf
+    sc = scenes.dtu_like(6000, seed=5, radii=(0.35, 0.5))
+    model = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"]).cuda()
+    pts = model.neural_pts
+    nbr = model._grid().query_points(pts, model.conf.k, model.conf.r)
+    feat = torch.randn(pts.shape[0], 32, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_()
+    whole = TVRegul.apply(feat, pts, nbr)
+    whole.backward()
+    g_whole, feat.grad = feat.grad.clone(), None
+    val, g = 0.0, torch.zeros_like(g_whole)
+    for r in range(world):
+        lo, hi = shard_range(pts.shape[0], r, world)
+        v = TVRegul.apply(feat, pts, nbr, lo, hi - lo, float(world))
+        v.backward()
+        val += float(v) / world
+        g += feat.grad / world
+        feat.grad = None
+    assert abs(val - float(whole)) <= 1e-5 * abs(float(whole))
+    assert float((g - g_whole).abs().max()) <= 1e-5 * float(g_whole.abs().max())
