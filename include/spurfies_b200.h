@@ -55,6 +55,10 @@ typedef struct {
   int32_t search_dim[3];
   const int32_t* search_cell_start;  /* [sx*sy*sz + 1] */
   const float* search_sorted;        /* [n_in_grid][4] grouped by search cell */
+  /* 0: ray-slot queries use the thread-per-query kernel (K <= 8), 1: the cloud has very dense voxels (the caller saw
+   * max points per voxel > 256 in the build statistics) -- a thread would scan thousands of candidates with divergent
+   * loads, so the warp-per-query kernel (coalesced 32-candidate steps) is used for ray slots too.  Same results. */
+  int32_t dense_cloud;
 } spf_grid;
 
 const char* spf_version(void);
@@ -80,6 +84,10 @@ int spf_mask_slots(const spf_grid* g, const float* raypos /*[R,D,3]*/, int32_t R
  * ray_nvalid[r] = number of slots of ray r with >= 1 neighbour (knnquery.py:272-280). */
 int spf_knn_slots(const spf_grid* g, const float* sample_loc, const int32_t* n_slots, int32_t R, int32_t Smax,
                   int32_t K, float radius2, int32_t* pidx /*[R,Smax,K]*/, int32_t* ray_nvalid /*[R]*/, void* stream);
+/* Kernel choice for a3 (same results either way, tests compare them): 0 = automatic -- one THREAD per query for ray
+ * slots when K <= 8 and radius2 > 0 (the hot path), one warp per query otherwise; 1 = always one warp per query;
+ * 2 = one thread per query wherever K <= 8 and radius2 > 0 (point queries too). */
+int spf_knn_set_algo(int32_t algo);
 /* a2+a3 fused for point queries (D = 1, Smax = 1: sdf_importance / get_sdf_eval / pseudo_sdf / tv_regul). */
 int spf_knn_points(const spf_grid* g, const float* q /*[Q,3]*/, int64_t Q, int32_t K, float radius2,
                    int32_t* pidx /*[Q,K]*/, void* stream);

@@ -29,7 +29,7 @@ class SpfGrid(C.Structure):
     _fields_ = [("shift", C.c_float * 3), ("vsize", C.c_float * 3), ("dim", C.c_int32 * 3), ("ks", C.c_int32 * 3),
                 ("n_points", C.c_int32), ("n_cells", C.c_int32), ("cell_start", C.c_void_p), ("sorted", C.c_void_p),
                 ("hit", C.c_void_p), ("search_cell", C.c_float), ("search_dim", C.c_int32 * 3),
-                ("search_cell_start", C.c_void_p), ("search_sorted", C.c_void_p)]
+                ("search_cell_start", C.c_void_p), ("search_sorted", C.c_void_p), ("dense_cloud", C.c_int32)]
 
 
 class GeoWeightsF32(C.Structure):
@@ -98,6 +98,7 @@ _SIGS = {
     "spf_mask_slots": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "spf_knn_slots": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "spf_knn_points": [_P, _P, _L, _I, _F, _P, _P],
+    "spf_knn_set_algo": [_I],
     "spf_mask_points": [_P, _P, _L, _P, _P],
     "spf_compact_valid": [_P, _L, _I, _P, _P, _P, _Z, _P],
     "spf_ray_prep": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -146,6 +147,9 @@ for _n, _a in _SIGS.items():
     _f = getattr(lib, _n)
     _f.restype = C.c_int
     _f.argtypes = _a
+
+if os.environ.get("SPF_KNN_ALGO"):   # development knob: A/B the kNN kernel families under bench.py (spf_knn_set_algo)
+    lib.spf_knn_set_algo(int(os.environ["SPF_KNN_ALGO"]))
 
 EXPORTED = ["spf_version", "spf_last_cuda_error", "spf_grid_workspace_bytes", "spf_compact_workspace_bytes",
             "spf_optim_workspace_bytes", "spf_voxelize_workspace_bytes", "spf_loss_workspace_bytes", *_SIGS]

@@ -267,6 +267,193 @@ static inline GridDev to_dev_query(const spf_grid* g, float radius2) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// THREAD-per-query kNN (K <= 8, radius > 0: every call of the hot path).  The warp-per-query scan above spends its issue
+// slots on the serial top-K insertion (six shuffles per surviving candidate, ~25 insertions per query on a DTU-shaped
+// cloud where ~66 of the ~250 scanned candidates lie inside the radius) and on 9 mostly half-empty 32-lane steps.  Here a
+// lane owns a query:
+//   * the lanes of a warp are consecutive slots of a ray (or consecutive query points), so they walk the same few cell
+//     columns and their candidate loads hit the same L1 lines;
+//   * a candidate costs the distance arithmetic, ONE compare against a running limit (min(radius^2, d2 of the current
+//     K-th best)) and an unconditional 8-byte store of its key into the lane's shared-memory list, whose fill count
+//     advances only if the candidate passed: no divergent branch per candidate;
+//   * the sorted top-K lives in registers; lists are merged into it ("drain") only when some lane's list is nearly full
+//     and once at the end -- warp-synchronously, so the branchy insertion network runs ~2-4 times x list length per
+//     warp instead of once per survivor per query, and every drain tightens the limit;
+//   * a block first compacts its valid queries (slots below the ray's count / points inside the dilated occupancy), so
+//     warps are dense.
+// The result is the K smallest by (d2, id), as before: the selection is a total order, so it cannot depend on the scan
+// order -- bit-identical to knn_warp (tests/test_gpu_knn.py compares both with the oracle and with each other).
+// ------------------------------------------------------------------------------------------------
+#define KT_THREADS 128
+#define KT_CAP 24
+#define KT_UNROLL 4
+#define KT_KR 8
+
+__device__ __forceinline__ void kt_insert(unsigned long long (&key)[KT_KR], unsigned long long k) {
+#pragma unroll
+  for (int j = KT_KR - 1; j > 0; --j) {
+    const bool g1 = key[j - 1] > k, g0 = key[j] > k;
+    key[j] = g1 ? key[j - 1] : (g0 ? k : key[j]);
+  }
+  if (key[0] > k) key[0] = k;
+}
+
+// all 32 lanes: merge each lane's list into its sorted keys, empty the lists, tighten the limits
+__device__ __forceinline__ void kt_drain(unsigned long long (&key)[KT_KR], const unsigned long long* list, int& n, float& lim) {
+  const int nmax = __reduce_max_sync(SPF_FULL, n);
+  for (int i = 0; i < nmax; ++i) {
+    const unsigned long long k = i < n ? list[i * KT_THREADS] : KEY_NONE;
+    if (k < key[KT_KR - 1]) kt_insert(key, k);
+  }
+  n = 0;
+  // a candidate farther than the current 8th best cannot enter (equal distance can: the point id decides, in kt_insert)
+  if (key[KT_KR - 1] != KEY_NONE) lim = __uint_as_float((unsigned)(key[KT_KR - 1] >> 32));
+}
+
+// Called by all 32 lanes of a warp (inactive lanes scan nothing).  list = this lane's column of the block's list array.
+__device__ __forceinline__ void knn_thread(const GridDev& g, bool active, float qx, float qy, float qz, float r2,
+                                           unsigned long long* list, unsigned long long (&key)[KT_KR]) {
+  const bool fine = g.use_search != 0;
+  const float vx = fine ? g.fcell : g.vx, vy = fine ? g.fcell : g.vy, vz = fine ? g.fcell : g.vz;
+  const int dx = fine ? g.fdx : g.dx, dy = fine ? g.fdy : g.dy, dz = fine ? g.fdz : g.dz;
+  const int* __restrict__ cstart = fine ? g.fcell_start : g.cell_start;
+  const float4* __restrict__ cand = fine ? g.fsorted : g.sorted;
+  const int fx = (int)floorf(__fdiv_rn(__fsub_rn(qx, g.sx), vx));
+  const int fy = (int)floorf(__fdiv_rn(__fsub_rn(qy, g.sy), vy));
+  const int fz = (int)floorf(__fdiv_rn(__fsub_rn(qz, g.sz), vz));
+  const int L = fine ? 1 : (g.kx + 1) / 2 - 1;  // the reference uses kernel_size[0] on all axes (knnquery.cu:263)
+#pragma unroll
+  for (int j = 0; j < KT_KR; ++j) key[j] = KEY_NONE;
+  const int z0 = max(0, fz - L), z1 = min(dz - 1, fz + L);
+  if (z0 > z1) active = false;
+  int n = 0;
+  float lim = r2;
+  const float INF = __int_as_float(0x7f800000);
+  for (int ox = -L; ox <= L; ++ox)
+    for (int oy = -L; oy <= L; ++oy) {
+      const int cx = fx + ox, cy = fy + oy;
+      int beg = 1, len = 0;   // an empty segment reads element 0 (index beg + (-1)) and discards it
+      if (active && cx >= 0 && cx < dx && cy >= 0 && cy < dy) {
+        const int base = cx * (dy * dz) + cy * dz;
+        const int b = cstart[base + z0], e = cstart[base + z1 + 1];
+        if (e > b) { beg = b; len = e - b; }
+      }
+      const int maxlen = __reduce_max_sync(SPF_FULL, len);
+      const int last = len - 1;
+      for (int o = 0; o < maxlen; o += KT_UNROLL) {
+        float4 c[KT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) c[u] = cand[beg + min(o + u, last)];   // past the segment: re-reads, discarded
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+          const float xv = __fsub_rn(c[u].x, qx), yv = __fsub_rn(c[u].y, qy), zv = __fsub_rn(c[u].z, qz);
+          // knnquery.cu:281 as nvcc contracts it: FMUL y*y ; FFMA x,x ; FFMA z,z
+          const float d2 = __fmaf_rn(zv, zv, __fmaf_rn(xv, xv, __fmul_rn(yv, yv)));
+          *reinterpret_cast<uint2*>(list + n * KT_THREADS) = make_uint2((unsigned)__float_as_int(c[u].w), __float_as_uint(d2));
+          // knnquery.cu:282 (radius) and the running K-th-best bound in one compare
+          n += (d2 <= lim && o + u <= last) ? 1 : 0;
+        }
+        if (__any_sync(SPF_FULL, n > KT_CAP - KT_UNROLL)) kt_drain(key, list, n, lim);
+      }
+    }
+  kt_drain(key, list, n, lim);
+}
+
+// block-level compaction of the valid work items: returns the flat id this thread processes (-1: none).  All threads call.
+__device__ __forceinline__ int kt_compact(bool valid, int flat) {
+  __shared__ int s_item[KT_THREADS];
+  __shared__ int s_wsum[KT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned m = __ballot_sync(SPF_FULL, valid);
+  if (lane == 0) s_wsum[wid] = __popc(m);
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < KT_THREADS / 32; ++w) {
+    const int c = s_wsum[w];
+    if (w < wid) off += c;
+    total += c;
+  }
+  if (valid) s_item[off + __popc(m & ((1u << lane) - 1))] = flat;
+  __syncthreads();
+  return tid < total ? s_item[tid] : -1;
+}
+
+__global__ void __launch_bounds__(KT_THREADS) k_knn_slots_t(GridDev g, const float* __restrict__ sample_loc,
+                                                            const int* __restrict__ n_slots, int R, int Smax, int K, float r2,
+                                                            int* __restrict__ pidx, int* __restrict__ ray_nvalid) {
+  __shared__ unsigned long long s_list[KT_CAP * KT_THREADS];
+  const long long total = (long long)R * Smax;
+  const long long flat0 = (long long)blockIdx.x * KT_THREADS;
+  const long long mine = flat0 + threadIdx.x;
+  bool valid = false;
+  if (mine < total) {
+    const int r = (int)(mine / Smax), s = (int)(mine - (long long)r * Smax);
+    valid = s < n_slots[r];
+    if (!valid)
+      for (int k = 0; k < K; ++k) pidx[mine * K + k] = -1;
+  }
+  const int item = kt_compact(valid, threadIdx.x);
+  if (__all_sync(SPF_FULL, item < 0)) return;
+  const long long w = flat0 + (item < 0 ? 0 : item);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (item >= 0) { qx = sample_loc[3 * w]; qy = sample_loc[3 * w + 1]; qz = sample_loc[3 * w + 2]; }
+  unsigned long long key[KT_KR];
+  knn_thread(g, item >= 0, qx, qy, qz, r2, s_list + threadIdx.x, key);
+  if (item >= 0) {
+#pragma unroll
+    for (int k = 0; k < KT_KR; ++k)
+      if (k < K) pidx[w * K + k] = key[k] == KEY_NONE ? -1 : (int)(unsigned)(key[k] & 0xffffffffull);
+    if (key[0] != KEY_NONE) atomicAdd(&ray_nvalid[(int)(w / Smax)], 1);
+  }
+}
+
+__global__ void __launch_bounds__(KT_THREADS) k_knn_points_t(GridDev g, const float* __restrict__ q, long long Q, int K, float r2,
+                                                             int* __restrict__ pidx) {
+  __shared__ unsigned long long s_list[KT_CAP * KT_THREADS];
+  const long long flat0 = (long long)blockIdx.x * KT_THREADS;
+  const long long mine = flat0 + threadIdx.x;
+  bool valid = false;
+  if (mine < Q) {
+    int cx, cy, cz;
+    const int v = voxel_of(g, q[3 * mine], q[3 * mine + 1], q[3 * mine + 2], cx, cy, cz);
+    valid = v >= 0 && g.hit[v];
+    if (!valid)
+      for (int k = 0; k < K; ++k) pidx[mine * K + k] = -1;
+  }
+  const int item = kt_compact(valid, threadIdx.x);
+  if (__all_sync(SPF_FULL, item < 0)) return;
+  const long long w = flat0 + (item < 0 ? 0 : item);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (item >= 0) { qx = q[3 * w]; qy = q[3 * w + 1]; qz = q[3 * w + 2]; }
+  unsigned long long key[KT_KR];
+  knn_thread(g, item >= 0, qx, qy, qz, r2, s_list + threadIdx.x, key);
+  if (item >= 0) {
+#pragma unroll
+    for (int k = 0; k < KT_KR; ++k)
+      if (k < K) pidx[w * K + k] = key[k] == KEY_NONE ? -1 : (int)(unsigned)(key[k] & 0xffffffffull);
+  }
+}
+
+// 0 = automatic, 1 = always the warp-per-query kernels, 2 = the thread-per-query kernels wherever they apply (K <= 8,
+// radius > 0).  Automatic = thread-per-query for RAY SLOTS (consecutive slots of a ray walk the same cell columns, so a
+// warp's candidate loads share L1 lines: k_knn_slots 0.274 -> 0.205 ms on the 4096-ray DTU-shaped step) and
+// warp-per-query for POINT queries (coarse samples 0.06 apart or unordered points: 32 lanes in 32 different cells make
+// every candidate load 32 L1 wavefronts, 0.147 -> 0.268 ms) and for clouds with very dense voxels (spf_grid.dense_cloud:
+// garden-shaped 1 M points, ~1300 candidates per query, 0.77 -> 1.20 ms with a thread per query).  Full-image eval render,
+// DTU-shaped: k_knn_slots 13.1 -> 6.9 ms per image.
+static int g_knn_algo = 0;
+extern "C" int spf_knn_set_algo(int32_t algo) {
+  if (algo < 0 || algo > 2) return SPF_ERR_INVALID;
+  g_knn_algo = algo;
+  return SPF_OK;
+}
+static inline bool knn_use_thread_kernels(const spf_grid* g, int K, float radius2, bool ray_slots) {
+  if (K > KT_KR || !(radius2 > 0.0f) || g_knn_algo == 1) return false;
+  return g_knn_algo == 2 || (ray_slots && !g->dense_cloud);
+}
+
+// ------------------------------------------------------------------------------------------------
 // mask + slots, one warp per ray (knnquery.cu:171-221, knnquery.py:208-231)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_mask_slots(GridDev g, const float* __restrict__ raypos, int R, int D, int Smax,
@@ -376,6 +563,13 @@ extern "C" int spf_knn_slots(const spf_grid* g, const float* sample_loc, const i
   if (R <= 0) return SPF_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   SPF_CUDA(cudaMemsetAsync(ray_nvalid, 0, sizeof(int) * (size_t)R, st), "knn_slots memset");
+  if (knn_use_thread_kernels(g, K, radius2, true)) {
+    const long long total = (long long)R * Smax;
+    k_knn_slots_t<<<(unsigned)((total + KT_THREADS - 1) / KT_THREADS), KT_THREADS, 0, st>>>(
+        to_dev_query(g, radius2), sample_loc, n_slots, R, Smax, K, radius2, pidx, ray_nvalid);
+    SPF_CHECK_LAUNCH("k_knn_slots_t");
+    return SPF_OK;
+  }
   const int wpb = 8;
   long long warps = (long long)R * Smax;
   k_knn_slots<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(to_dev_query(g, radius2), sample_loc, n_slots, R, Smax, K,
@@ -389,6 +583,12 @@ extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int3
   if (K < 1 || K > 20) return SPF_ERR_INVALID;
   if (Q <= 0) return SPF_OK;
   if (!g || !q || !pidx) return SPF_ERR_INVALID;
+  if (knn_use_thread_kernels(g, K, radius2, false)) {
+    k_knn_points_t<<<(unsigned)((Q + KT_THREADS - 1) / KT_THREADS), KT_THREADS, 0, (cudaStream_t)stream_>>>(
+        to_dev_query(g, radius2), q, Q, K, radius2, pidx);
+    SPF_CHECK_LAUNCH("k_knn_points_t");
+    return SPF_OK;
+  }
   const int wpb = 8;
   // enough warps to fill the machine several times over (148 SMs x 64 resident warps), at most 32 points per warp
   int ppw = 32;

@@ -99,6 +99,8 @@ class VoxelGrid(torch.nn.Module):
         call("spf_grid_build", C.byref(g), ptr(points), ptr(self._cell_start), ptr(self._sorted), ptr(self._hit),
              ptr(self._stats_dev), ptr(ws), ws.numel(), stream())
         self._grid, self._key, self._stats, self._search_radius = g, key, None, None
+        # kernel-family hint for the ray-slot kNN (spf_grid.dense_cloud): one more small D2H per point-set build
+        g.dense_cloud = int(self.stats()["max_points_per_voxel"] > 256)
         self.grid_dim = tuple(dim)
         self.d_coord_shift = self.ranges[:3]
 

@@ -132,6 +132,52 @@ def test_full_size_properties():
     assert st["points_in_grid"] == 1_000_000
 
 
+@pytest.mark.parametrize("scene,n_points", [("dtu", 100_000), ("garden", 1_000_000)])
+def test_thread_per_query_kernels_equal_warp_per_query_kernels(scene, n_points):
+    """spf_knn_set_algo: the thread-per-query kernels (K <= 8, the hot path) and the warp-per-query kernels select the
+    same K smallest (d2, id) -- identical index lists in identical order -- for ray slots (ragged slot counts, rays that
+    miss) and for point queries (masked-out points, empty neighbourhoods), at BASELINE configs[1] / configs[2] size."""
+    from spurfies_b200 import _lib
+    sc = scenes.dtu_like(n_points) if scene == "dtu" else scenes.garden_like(n_points)
+    vg = make_grid(sc["pts"], sc["ranges"])
+    g = torch.Generator().manual_seed(11)
+    P = sc["pts"]
+    near = (P[torch.randint(0, n_points, (200_000,), generator=g)] + 0.02 * torch.randn(200_000, 3, generator=g))
+    far = (torch.rand(60_000, 3, generator=g) * 2 - 1) * float(sc["ranges"][3])
+    q = torch.cat([near, far])[torch.randperm(260_000, generator=g)].cuda().contiguous()
+    # rays: 2048 x 98 samples marching through the object (consecutive samples close together, like the sampler's)
+    o = (torch.rand(2048, 1, 3, generator=g) * 2 - 1) * 0.9 * float(sc["ranges"][3])
+    d = torch.nn.functional.normalize(torch.randn(2048, 1, 3, generator=g), dim=-1)
+    t = torch.sort(torch.rand(2048, 98, 1, generator=g) * 1.2 - 0.6, dim=1).values
+    rays = (o + d * t).cuda().contiguous()
+    out, ms = {}, {}
+    try:
+        for algo in (1, 2):
+            _lib.call("spf_knn_set_algo", algo)
+            for k in (8, 3):
+                res = []
+                for rep in range(2):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e2 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    a = vg.query_points(q, k, 2.0)
+                    e2.record()
+                    b = vg.query_dense(rays, k, 2.0, 80)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    res = (a, b[0], b[3])
+                    ms[(algo, k)] = (round(e0.elapsed_time(e2), 3), round(e2.elapsed_time(e1), 3))
+                out[(algo, k)] = res
+    finally:
+        _lib.call("spf_knn_set_algo", 0)
+    print(f"{scene}: ms (points, slots) per kernel family (1 = warp per query, 2 = thread per query):", {f"algo{a}_k{k}": v for (a, k), v in ms.items()})
+    for k in (8, 3):
+        for x, y in zip(out[(2, k)], out[(1, k)]):
+            assert torch.equal(x, y)
+    assert int((out[(2, 8)][0] >= 0).sum()) > 500_000 and int((out[(2, 8)][0][:, 0] < 0).sum()) > 10_000
+    assert int((out[(2, 8)][1] >= 0).sum()) > 100_000
+
+
 def test_search_grid_equals_reference_voxel_scan():
     """The radius-sized search grid is an access-path optimisation only: identical indices (same order) as scanning the
     27 reference voxels, for ray queries and point queries; and it switches itself off when radius > voxel edge."""
