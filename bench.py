@@ -167,7 +167,7 @@ def run_ours(args):
     # weak scaling: every rank runs the full per-GPU batch; strong scaling: the batch is sharded over the ranks
     rays_gpu = wl["rays"] if wl["scaling"] == "weak" else wl["rays"] // world
     sc, model = build_scene(device, precision=args.precision, scene=wl["scene"], n_points=wl["n_points"])
-    step = TrainStep(model, world_size=world, grad_compress=args.grad_compress)
+    step = TrainStep(model, world_size=world, grad_compress=args.grad_compress, dp_overlap=args.dp_overlap)
     nb = 8
     hb = host_batches(nb, rank, n_rays=rays_gpu, cam_radius=sc["cam_radius"])
     db = [to_device(h, device) for h in hb]
@@ -309,7 +309,8 @@ def run_ours(args):
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"] % (wl["n_points"], wl["rays"]),
                    "rays_per_gpu": rays_gpu, "k": 8, "max_shading_pts": 80, "parallelism": "ray-sharded dp%d" % world,
-                   "cuda_graph": graphed, "cuda_graph_note": step.graph_error, "grad_exchange": args.grad_compress or "fp32",
+                   "cuda_graph": graphed, "cuda_graph_note": step.graph_error, "grad_exchange": (args.grad_compress or "fp32") + (" (colour-latent part overlapped with the backward)" if step._early_n else "")
+                   + (" -- DIAGNOSTIC RUN WITHOUT THE GRADIENT EXCHANGE: NOT A VALID RESULT" if step._diag_skip_reduce else ""),
                    "l2": "distinct ray batch each step; per-step working set (saved activations, > 1 GB) >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last,
@@ -767,6 +768,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-reference-gpu", dest="reference_gpu", action="store_false",
                     help="skip timing the reference's GPU path (its compiled kernels + restated torch graph) on this GPU")
+    ap.add_argument("--dp-overlap", action="store_true",
+                    help="N > 1: reduce the colour latents' gradient inside the backward (opt-in, see TrainStep)")
     ap.add_argument("--grad-compress", default=None, choices=["bf16"],
                     help="experimental, N > 1: all-reduce the latent-table gradients as bf16 (default: exact fp32 exchange)")
     ap.add_argument("--workload", default="train", choices=["train", "garden", "eval", "mesh"],

@@ -10,11 +10,13 @@ so it runs after the all-reduce; every rank then takes the identical Adam step.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist
 
+from . import fields
 from .dist import FlatGradReducer
 from .model import PointVolSDF, VolSDFLoss
 from .optim import FusedAdam, cosine_lr
@@ -74,9 +76,16 @@ def _record_tree(v, stream) -> None:
 
 class TrainStep:
     def __init__(self, model: PointVolSDF, lr: float = 5.0e-4, grad_clip: float = 1.0, loss: Optional[VolSDFLoss] = None,
-                 world_size: int = 1, lr_schedule: bool = True, grad_compress: Optional[str] = None):
+                 world_size: int = 1, lr_schedule: bool = True, grad_compress: Optional[str] = None, dp_overlap: bool = False):
         """grad_compress="bf16" (opt-in, bf16 precision mode only): the latent tables' gradients -- 96 % of the exchanged
-        bytes -- are all-reduced as bf16 (FlatGradReducer.bf16_prefix); default None = exact fp32 exchange."""
+        bytes -- are all-reduced as bf16 (FlatGradReducer.bf16_prefix); default None = exact fp32 exchange.
+        dp_overlap (opt-in; world_size > 1, fp32 exchange): the colour latents' gradient (64 % of the exchanged bytes) is
+        all-reduced on NCCL's stream as soon as the colour field's backward is done, under the geometry backward and the
+        regulariser that follow; the rest is reduced after the backward.  Same sums, same step (tests/test_gpu_dist.py).
+        Off by default because it does not pay on NVSwitch: measured on 8 B200 (profiles/r03c_*): no exchange at all
+        4.12 ms/step, one all-reduce after the backward 4.30 ms (40 MB through NVLS at NCCL's own 411 GB/s model = 0.12 ms
+        + latency), early reduction started before the weight-gradient kernel 4.57 ms (NCCL's copy kernels next to a kernel
+        that runs at 90 % of the HBM peak), started after it: no difference beyond run-to-run noise at 2 GPUs."""
         self.model = model
         self.loss = loss or VolSDFLoss()
         for prm in list(model.F_geometry.parameters()) + list(model.T.parameters()):
@@ -94,14 +103,36 @@ class TrainStep:
             assert all(a is b for a, b in zip(lat, self.params)), "the latent tables must be the first parameters"
             n_half = sum((p.numel() + 3) // 4 * 4 for p in lat)
         self._reducer = FlatGradReducer(self.params, world_size, align=4, bf16_prefix=n_half)
+        self._early_n, self._early_work = 0, None
+        if world_size > 1 and dp_overlap and grad_compress is None and self.params[0] is model.neural_feats_color:
+            self._early_n = self._reducer.offsets[1] if len(self.params) > 1 else self._reducer.numel
+        # diagnosis only (bench.py marks the line): leave the gradient exchange out to time the step without it
+        self._diag_skip_reduce = world_size > 1 and os.environ.get("SPF_DP_DIAG_SKIP_REDUCE") == "1"
         # every p.data / p.grad becomes a view of a flat buffer; the gradient buffer is the one NCCL reduces
         self.opt = FusedAdam(self.params, lr=lr, max_norm=grad_clip if grad_clip else 0.0, grad_flat=self._reducer.flat())
         self._graph = None
         self._static = None
         self.graph_error = None
 
+    def _early_reduce(self):
+        """Fired by fields.ColorField.backward: the first `_early_n` elements of the flat gradient (the colour latents)
+        are final.  Asynchronous all-reduce: NCCL's stream waits for the kernels enqueued so far, this stream goes on."""
+        if self._early_work is not None:
+            raise RuntimeError("the colour field ran two backwards in one step: its gradient was already being reduced")
+        self._early_work = dist.all_reduce(self._reducer.flat()[:self._early_n], op=dist.ReduceOp.SUM,
+                                           group=self._reducer.group, async_op=True)
+
     def _allreduce_grads(self):
-        self._reducer.reduce(average=False)   # 1/world is folded into the optimiser's clip coefficient
+        if self._diag_skip_reduce:
+            return
+        if self._early_work is None:
+            self._reducer.reduce(average=False)   # 1/world is folded into the optimiser's clip coefficient
+            return
+        flat = self._reducer.flat()
+        if self._early_n < flat.numel():
+            dist.all_reduce(flat[self._early_n:], op=dist.ReduceOp.SUM, group=self._reducer.group)
+        self._early_work.wait()   # this stream waits for the early part (no host synchronisation)
+        self._early_work = None
 
     def _tick_lr(self):
         """scheduler.step() (train.py:363): host-side closed form, one 4-byte H2D copy; outside the captured graph."""
@@ -232,7 +263,13 @@ class TrainStep:
             p._spf_direct_grad = True
         # every p.grad is a view of the flat buffer: autograd accumulates into it in place.  It is all-zero here: the
         # optimiser kernel clears it in the same pass that consumes it (zero_grad, train.py:355).
-        losses["loss"].backward()
+        hook = self._early_n > 0 and not self._diag_skip_reduce and self._reducer.attached()
+        if hook:
+            fields.GRAD_READY_HOOKS["color_latent"] = self._early_reduce
+        try:
+            losses["loss"].backward()
+        finally:
+            fields.GRAD_READY_HOOKS["color_latent"] = None
         self._allreduce_grads()           # N > 1: one NCCL all-reduce (sum) of the flat buffer, no packing
         # clip_grad_norm_(1.0) (train.py:360-361), the NaN / Inf guard (train.py:548-564: a non-finite global norm skips
         # the whole update, exactly like the reference's dropped gradients), Adam and zero_grad: two kernels, no host sync.

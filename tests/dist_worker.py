@@ -35,13 +35,13 @@ def main():
     gt, rng = scenes.synthetic_gt(R, 3), scenes.rng_inputs(R, 3)
     ld = scenes.local_data(0, sc["cam_radius"], feat_res=(128, 96))
 
-    def make(w):
+    def make(w, **kw):
         torch.manual_seed(0)
         m = PointVolSDF(default_conf(), "24", "dtu", neural_points=sc["pts"], neural_colors=sc["colors"], precision=precision)
         with torch.no_grad():
             m.neural_feats_geometry.mul_(8.0)
             m.neural_feats_color[:, 3:].mul_(500.0)
-        return TrainStep(m, world_size=w, lr_schedule=False)
+        return TrainStep(m, world_size=w, lr_schedule=False, **kw)
 
     cu = lambda d: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}
 
@@ -89,6 +89,18 @@ def main():
     lo_chk, hi_chk = chk.clone(), chk.clone()
     dist.all_reduce(lo_chk, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi_chk, op=dist.ReduceOp.MAX)
+    # the whole step through TrainStep.__call__: early all-reduce of the colour-latent gradient inside the backward
+    # (dp_overlap, opt-in) against the single all-reduce after it, eagerly and as a replayed CUDA graph
+    variants = {}
+    for name, kw, graph in (("overlap", {"dp_overlap": True}, False), ("serial", {"dp_overlap": False}, False),
+                            ("overlap_graph", {"dp_overlap": True}, True)):
+        st = make(world, **kw)
+        assert (st._early_n > 0) == kw["dp_overlap"]
+        if graph:
+            captured = st.capture(*inputs(lo, hi))
+            assert captured, st.graph_error
+        st(*inputs(lo, hi))
+        variants[name] = (st.opt.flat_p - p0).clone()
     torch.cuda.synchronize()
     if rank == 0:
         gmax = float(g_big.abs().max())
@@ -99,6 +111,9 @@ def main():
             "adam_delta_absmax": float(d_big.abs().max()),
             "adam_delta_mean_abs_diff": float((d_dp - d_big).abs().mean()), "adam_delta_max_abs_diff": float((d_dp - d_big).abs().max()),
             "adam_delta_mean_abs": float(d_big.abs().mean()),
+            "overlap_vs_serial_mean_abs_diff": float((variants["overlap"] - variants["serial"]).abs().mean()),
+            "graph_vs_eager_mean_abs_diff": float((variants["overlap_graph"] - variants["overlap"]).abs().mean()),
+            "overlap_vs_manual_mean_abs_diff": float((variants["overlap"] - d_dp).abs().mean()),
             "ranks_identical": bool(torch.equal(lo_chk, hi_chk))}))
         sys.stdout.flush()
     dist.barrier()

@@ -9,6 +9,9 @@ for s in $STEPS; do
   case $s in
     test) timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -q -rA > $O/${T}_dist_pytest.log 2>&1; grep -E "passed|failed|skipped|sharded vs" $O/${T}_dist_pytest.log | cut -c1-1500 ;;
     bench) timeout 600 $RUN --steps 20 --warmup 3 > $O/${T}_bench_n$N.log 2> $O/${T}_bench_n$N.err; python tools/show_bench.py $O/${T}_bench_n$N.log ;;
+    overlap) timeout 600 $RUN --steps 20 --warmup 3 --dp-overlap > $O/${T}_overlap_n$N.log 2> $O/${T}_overlap_n$N.err; python tools/show_bench.py $O/${T}_overlap_n$N.log ;;
+    noexch) SPF_DP_DIAG_SKIP_REDUCE=1 timeout 600 $RUN --steps 20 --warmup 3 > $O/${T}_noexch_n$N.log 2> $O/${T}_noexch_n$N.err; python tools/show_bench.py $O/${T}_noexch_n$N.log ;;
+    nvls) NCCL_ALGO=NVLS NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,TUNING timeout 600 $RUN --steps 20 --warmup 3 > $O/${T}_nvls_n$N.log 2> $O/${T}_nvls_n$N.err; python tools/show_bench.py $O/${T}_nvls_n$N.log; grep -i "nvls\|algo" $O/${T}_nvls_n$N.log $O/${T}_nvls_n$N.err | head -8 | cut -c1-200 ;;
     bench16) timeout 600 $RUN --steps 20 --warmup 3 --grad-compress bf16 > $O/${T}_bench16_n$N.log 2> $O/${T}_bench16_n$N.err; python tools/show_bench.py $O/${T}_bench16_n$N.log ;;
     garden) timeout 900 $RUN --workload garden --steps 10 --warmup 3 > $O/${T}_garden_n$N.log 2> $O/${T}_garden_n$N.err; python tools/show_bench.py $O/${T}_garden_n$N.log ;;
     garden16) timeout 900 $RUN --workload garden --steps 10 --warmup 3 --grad-compress bf16 > $O/${T}_garden16_n$N.log 2> $O/${T}_garden16_n$N.err; python tools/show_bench.py $O/${T}_garden16_n$N.log ;;
