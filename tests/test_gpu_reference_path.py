@@ -49,8 +49,11 @@ def test_reference_graph_runs_unchanged_on_the_product_voxelgrid():
     errs.update({"loss." + k: abs(float(l_p[k]) - float(l_r[k])) / max(1.0, abs(float(l_r[k]))) for k in l_r})
     errs["grads"] = max(rel_err(a, b) for a, b in zip(g_p, g_r) if float(b.abs().max()) > 0)
     print("reference graph on product VoxelGrid vs on reference kernels:", {k: f"{v:.1e}" for k, v in errs.items()})
-    # identical inputs to an identical torch graph: only cuBLAS / atomics run-to-run noise remains
-    assert max(errs.values()) < 1e-4, errs
+    # identical inputs to an identical torch graph: only cuBLAS / atomics run-to-run noise remains.  The gradients are
+    # max-norm errors of scatter-added sums whose order changes from run to run (torch index_add atomics; the reference
+    # kernels emit each neighbour list in a nondeterministic order): observed 4e-5 ... 1.4e-4 over repeated runs
+    grads = errs.pop("grads")
+    assert max(errs.values()) < 1e-4 and grads < 5e-4, (errs, grads)
 
 
 def test_reference_gpu_path_matches_the_product_kernels():

@@ -33,9 +33,9 @@ def run(backward):
         d = torch.ones_like(hbar)
         if os.environ.get("SPF_TL_COMPACT", "1") == "1":   # the training path: gradient arrives as compact bf16 tiles
             from spurfies_b200.fields import Arena
-            dc = Arena.get("tl.d_hbc", (slots.rows_alloc(1), 256), torch.bfloat16, d.device)
+            dc = Arena.get("tl.d_hbc", (slots.rows_alloc(1), 256), torch.float16, d.device)
             dc.fill_(1.0)
-            slots.d_hb_compact = (dc, d.data_ptr())
+            slots.d_hb_compact = (dc, d.data_ptr(), fields.grad_scale(d, target=1.0))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         hbar.backward(d)
