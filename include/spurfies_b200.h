@@ -91,6 +91,12 @@ int spf_knn_set_algo(int32_t algo);
 /* a2+a3 fused for point queries (D = 1, Smax = 1: sdf_importance / get_sdf_eval / pseudo_sdf / tv_regul). */
 int spf_knn_points(const spf_grid* g, const float* q /*[Q,3]*/, int64_t Q, int32_t K, float radius2,
                    int32_t* pidx /*[Q,K]*/, void* stream);
+/* The same under a device-side predicate: when `skip` is non-NULL and *skip != 0 at launch time, no point is searched
+ * and every row of pidx is -1 (so the compaction that follows yields an empty list and the field kernels do nothing).
+ * The eval sampler (ray_sampler.py:466-468 loops `while not_converge.sum() > 0`) uses it to make the iterations after
+ * convergence free without reading the convergence flag back to the host. */
+int spf_knn_points_pred(const spf_grid* g, const float* q, int64_t Q, int32_t K, float radius2, int32_t* pidx,
+                        const int32_t* skip /*[1] device, may be NULL*/, void* stream);
 /* mask only (knnquery.cu:171-196) */
 int spf_mask_points(const spf_grid* g, const float* q, int64_t Q, int32_t* mask, void* stream);
 

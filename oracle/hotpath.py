@@ -248,11 +248,17 @@ def error_bound(beta, sdf, dists, d_star):
 
 
 def sample_z(p: Params, grid: OracleGrid, ray_dirs, cam_loc, cfg: SamplerCfg, training: bool, fast: int = -1,
-             rng: Optional[Dict[str, torch.Tensor]] = None, sdf_fn=None, trace: Optional[dict] = None):
+             rng: Optional[Dict[str, torch.Tensor]] = None, sdf_fn=None, trace: Optional[dict] = None,
+             force_iters: Optional[int] = None):
     """ErrorBoundSampler_pn.get_z_vals (ray_sampler.py:377-574) + UniformSampler (:34-59).
 
     rng (training): {"t_rand":[R,N_eval], "u":[R,N_samples], "sampling_idx":[N_extra] long}.
     Returns z_vals [R, N_samples + N_extra + 2].
+
+    force_iters (tests only): the outer loop is batch-global -- it runs while ANY ray of the batch is unconverged
+    (ray_sampler.py:466-468) and every iteration resamples every ray -- so a SUBSET of a batch reproduces the batch's
+    samples only if it runs the batch's number of iterations.  force_iters = that number replaces the subset's own
+    `not_converge` decision; everything else is unchanged.
     """
     R = ray_dirs.shape[0]
     max_total_iters = fast if fast >= 0 else cfg.max_total_iters
@@ -313,7 +319,7 @@ def sample_z(p: Params, grid: OracleGrid, ray_dirs, cam_loc, cfg: SamplerCfg, tr
         transmittance = torch.exp(-torch.cumsum(shifted, dim=-1))
         weights = alpha * transmittance
         total_iters += 1
-        not_converge = bool(beta.max() > beta0)
+        not_converge = bool(beta.max() > beta0) if force_iters is None else total_iters < force_iters
         more = not_converge and total_iters < max_total_iters
         if trace is not None:
             trace.setdefault("iters", []).append(dict(z=z_vals.clone(), sdf=d.clone(), d_star=d_star.clone(),

@@ -409,14 +409,15 @@ __global__ void __launch_bounds__(KT_THREADS) k_knn_slots_t(GridDev g, const flo
 }
 
 __global__ void __launch_bounds__(KT_THREADS) k_knn_points_t(GridDev g, const float* __restrict__ q, long long Q, int K, float r2,
-                                                             int* __restrict__ pidx) {
+                                                             int* __restrict__ pidx, const int* __restrict__ skip) {
   __shared__ unsigned long long s_list[KT_CAP * KT_THREADS];
   const long long flat0 = (long long)blockIdx.x * KT_THREADS;
   const long long mine = flat0 + threadIdx.x;
+  const bool skipped = skip && *skip;
   bool valid = false;
   if (mine < Q) {
     int cx, cy, cz;
-    const int v = voxel_of(g, q[3 * mine], q[3 * mine + 1], q[3 * mine + 2], cx, cy, cz);
+    const int v = skipped ? -1 : voxel_of(g, q[3 * mine], q[3 * mine + 1], q[3 * mine + 2], cx, cy, cz);
     valid = v >= 0 && g.hit[v];
     if (!valid)
       for (int k = 0; k < K; ++k) pidx[mine * K + k] = -1;
@@ -511,14 +512,17 @@ __global__ void k_knn_slots(GridDev g, const float* __restrict__ sample_loc, con
 // point queries: mask + kNN fused, each warp owns `ppw` consecutive points (ppw = 32 for huge, mostly masked-out
 // batches such as SDF grids; smaller when there are too few points to fill the machine with 32 per warp)
 __global__ void k_knn_points(GridDev g, const float* __restrict__ q, long long Q, int K, float r2,
-                             int* __restrict__ pidx, int ppw) {
+                             int* __restrict__ pidx, int ppw, const int* __restrict__ skip) {
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   long long i = w * ppw + lane;
   if (w * ppw >= Q) return;
+  const bool skipped = skip && *skip;   // device-side predicate (spf_knn_points_pred): every point is "outside"
   bool h = false;
   float x = 0, y = 0, z = 0;
-  if (lane < ppw && i < Q) {
+  if (lane < ppw && i < Q && skipped) {
+    for (int k = 0; k < K; ++k) pidx[i * K + k] = -1;
+  } else if (lane < ppw && i < Q) {
     x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2];
     int cx, cy, cz;
     int v = voxel_of(g, x, y, z, cx, cy, cz);
@@ -578,14 +582,14 @@ extern "C" int spf_knn_slots(const spf_grid* g, const float* sample_loc, const i
   return SPF_OK;
 }
 
-extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int32_t K, float radius2, int32_t* pidx,
-                              void* stream_) {
+extern "C" int spf_knn_points_pred(const spf_grid* g, const float* q, int64_t Q, int32_t K, float radius2, int32_t* pidx,
+                                   const int32_t* skip, void* stream_) {
   if (K < 1 || K > 20) return SPF_ERR_INVALID;
   if (Q <= 0) return SPF_OK;
   if (!g || !q || !pidx) return SPF_ERR_INVALID;
   if (knn_use_thread_kernels(g, K, radius2, false)) {
     k_knn_points_t<<<(unsigned)((Q + KT_THREADS - 1) / KT_THREADS), KT_THREADS, 0, (cudaStream_t)stream_>>>(
-        to_dev_query(g, radius2), q, Q, K, radius2, pidx);
+        to_dev_query(g, radius2), q, Q, K, radius2, pidx, skip);
     SPF_CHECK_LAUNCH("k_knn_points_t");
     return SPF_OK;
   }
@@ -596,9 +600,14 @@ extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int3
   while (ppw > 1 && (Q + ppw - 1) / ppw < want_warps) ppw >>= 1;
   long long warps = (Q + ppw - 1) / ppw;
   k_knn_points<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream_>>>(to_dev_query(g, radius2), q, Q, K,
-                                                                                            radius2, pidx, ppw);
+                                                                                            radius2, pidx, ppw, skip);
   SPF_CHECK_LAUNCH("k_knn_points");
   return SPF_OK;
+}
+
+extern "C" int spf_knn_points(const spf_grid* g, const float* q, int64_t Q, int32_t K, float radius2, int32_t* pidx,
+                              void* stream_) {
+  return spf_knn_points_pred(g, q, Q, K, radius2, pidx, nullptr, stream_);
 }
 
 extern "C" int spf_mask_points(const spf_grid* g, const float* q, int64_t Q, int32_t* mask, void* stream_) {

@@ -171,14 +171,19 @@ class VoxelGrid(torch.nn.Module):
              ptr(nvalid), stream())
         return pidx, loc, slot_sample, nvalid
 
-    def query_points(self, q: torch.Tensor, k: int, radius_limit_scale: float) -> torch.Tensor:
-        """Point queries (D = 1, Smax = 1 semantics): q [Q,3] -> pidx i32 [Q,k] (-1 rows where masked out / empty)."""
+    def query_points(self, q: torch.Tensor, k: int, radius_limit_scale: float, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Point queries (D = 1, Smax = 1 semantics): q [Q,3] -> pidx i32 [Q,k] (-1 rows where masked out / empty).
+        ``skip`` (int32 [1] on the device, optional): when non-zero at launch time nothing is searched and every row is
+        -1 (spf_knn_points_pred)."""
         assert k <= 20, "k cannot be greater than 20"
         if q.dtype != torch.float32:
             raise _lib.SpfError("q must be float32")
         Q = q.shape[0]
         pidx = torch.empty(Q, k, dtype=torch.int32, device=q.device)
-        call("spf_knn_points", C.byref(self.handle), ptr(q), Q, k, self.radius2(radius_limit_scale), ptr(pidx), stream())
+        if skip is not None:
+            assert skip.dtype == torch.int32 and skip.is_cuda and skip.numel() == 1
+        call("spf_knn_points_pred", C.byref(self.handle), ptr(q), Q, k, self.radius2(radius_limit_scale), ptr(pidx),
+             ptr(skip), stream())
         return pidx
 
     def mask_points(self, q: torch.Tensor) -> torch.Tensor:

@@ -139,6 +139,10 @@ class ErrorBoundSampler_pn:
         # iteration (`beta.max() > beta0`, :468); here every launch of the multi-iteration (eval) schedule is predicated
         # on this state instead (spf_sampler_iter_pred), so a full-image render has no host round trip.
         state = torch.zeros(2, dtype=torch.int32, device=dev)
+        # how many iterations of Algorithm 1 this batch used (device tensor, no sync; tests read it): the loop is
+        # batch-global (ray_sampler.py:466-468), so a ray's samples depend on it
+        iters_used = torch.ones(1, dtype=torch.int32, device=dev)
+        self.last_iters_used = iters_used
         n_extra = self.N_samples_extra
         cols = self.N_samples + 2 + n_extra
         total_iters = 0
@@ -168,7 +172,11 @@ class ErrorBoundSampler_pn:
 
         while total_iters < max_total_iters:
             with torch.no_grad():
-                s_new = model.sdf_importance(new_pts.view(-1, 3)).view(R, -1)
+                # once every ray of the batch has converged (state[1], set on the device) the remaining iterations of
+                # the predicated schedule read nothing of this: skip the search and the MLP on the device as well
+                done = state[1:2] if (total_iters >= 1 and hasattr(model, "_point_slots")) else None
+                s_new = (model.sdf_importance(new_pts.view(-1, 3), skip=done) if done is not None
+                         else model.sdf_importance(new_pts.view(-1, 3))).view(R, -1)
             if sdf is None:
                 sdf = s_new
             else:  # merge by the sort permutation (ray_sampler.py:405-415, 533)
@@ -197,6 +205,7 @@ class ErrorBoundSampler_pn:
                  float(self.far), None, 0, ptr(o), ptr(ray_dirs), ptr(probe_z), ptr(probe_p), ptr(state), 1, stream())
             final_draw(M, 2)                                                  # runs only if this iteration converged
             state[1:2].bitwise_or_((state[0:1] == 0).to(torch.int32))         # converged now or earlier
+            iters_used.add_((state[1:2] == 0).to(torch.int32))                # another iteration's result will be used
             beta_io, new_z, new_pts = beta_probe, probe_z, probe_p
         if z_out is not None:
             self.last_points = p_out
@@ -304,16 +313,18 @@ class PointVolSDF(nn.Module):
     def _pack(self) -> GeoPack:
         return self._geo_pack.get(self.F_geometry, self.T)
 
-    def _point_slots(self, x: torch.Tensor, tag: str = "points") -> SlotSet:
-        pidx = self._grid().query_points(x.contiguous().float(), self.conf.k, self.conf.r)
+    def _point_slots(self, x: torch.Tensor, tag: str = "points", skip: Optional[torch.Tensor] = None) -> SlotSet:
+        pidx = self._grid().query_points(x.contiguous().float(), self.conf.k, self.conf.r, skip=skip)
         return SlotSet(pidx, tag, self._owner)
 
     # ------------------------------------------------------------------ point SDF queries
-    def sdf_importance(self, inputs: torch.Tensor) -> torch.Tensor:
-        """pointneus_disent.py:348-421: SDF at points [N,3] -> [N], 1000 where no neighbour."""
+    def sdf_importance(self, inputs: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pointneus_disent.py:348-421: SDF at points [N,3] -> [N], 1000 where no neighbour.  ``skip`` (device int32
+        [1], optional): non-zero at launch time = the caller will not read the result (VoxelGrid.query_points): every
+        value is the 1000 filler and neither the search nor the MLP runs."""
         set_precision(self.precision)
         x = inputs.detach().contiguous().float()
-        slots = self._point_slots(x)
+        slots = self._point_slots(x, skip=skip)
         sdf, _, _ = geo_sdf_raw(self._pack(), slots, x, self.neural_pts, self.neural_feats_geometry.detach(),
                                 self.conf.rbf, False, False)
         return sdf
