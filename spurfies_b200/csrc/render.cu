@@ -440,11 +440,17 @@ __global__ void k_sampler_iter(const float* __restrict__ z, const float* __restr
   float e0 = error_bound_warp(sz, sd, sds, se_s, sf_s, M, beta0, lane);
   if (e0 <= eps) beta = beta0;
   float bmin = beta0, bmax = beta;
-  for (int j = 0; j < beta_iters; ++j) {
-    float mid = (bmin + bmax) / 2.0f;
-    float e = error_bound_warp(sz, sd, sds, se_s, sf_s, M, mid, lane);
-    if (e <= eps) bmax = mid;
-    else if (e > eps) bmin = mid;
+  // A ray that meets the bound at beta0 (every ray that misses the cloud, and every converged ray of a later iteration)
+  // starts the bisection on the empty interval [beta0, beta0]: each of its steps re-evaluates the bound at mid = beta0,
+  // finds e0 again and leaves bmax = beta0.  Skipping them is bit-identical and saves 10 of the ray's 11 evaluations
+  // (e0 is warp-uniform: a warp owns the ray).
+  if (!(e0 <= eps)) {
+    for (int j = 0; j < beta_iters; ++j) {
+      float mid = (bmin + bmax) / 2.0f;
+      float e = error_bound_warp(sz, sd, sds, se_s, sf_s, M, mid, lane);
+      if (e <= eps) bmax = mid;
+      else if (e > eps) bmin = mid;
+    }
   }
   beta = bmax;
   if (lane == 0) {
