@@ -85,8 +85,8 @@ int spf_mask_slots(const spf_grid* g, const float* raypos /*[R,D,3]*/, int32_t R
 int spf_knn_slots(const spf_grid* g, const float* sample_loc, const int32_t* n_slots, int32_t R, int32_t Smax,
                   int32_t K, float radius2, int32_t* pidx /*[R,Smax,K]*/, int32_t* ray_nvalid /*[R]*/, void* stream);
 /* Kernel choice for a3 (same results either way, tests compare them): 0 = automatic -- one THREAD per query for ray
- * slots when K <= 8 and radius2 > 0 (the hot path), one warp per query otherwise; 1 = always one warp per query;
- * 2 = one thread per query wherever K <= 8 and radius2 > 0 (point queries too). */
+ * slots and for point batches of >= 4 M points when K <= 8, radius2 > 0 and the cloud is not dense_cloud, one warp per
+ * query otherwise; 1 = always one warp per query; 2 = one thread per query wherever K <= 8 and radius2 > 0. */
 int spf_knn_set_algo(int32_t algo);
 /* a2+a3 fused for point queries (D = 1, Smax = 1: sdf_importance / get_sdf_eval / pseudo_sdf / tv_regul). */
 int spf_knn_points(const spf_grid* g, const float* q /*[Q,3]*/, int64_t Q, int32_t K, float radius2,

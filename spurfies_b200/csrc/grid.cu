@@ -408,50 +408,86 @@ __global__ void __launch_bounds__(KT_THREADS) k_knn_slots_t(GridDev g, const flo
   }
 }
 
+// Point queries are sparse (coarse ray samples: a quarter inside the dilated occupancy; SDF grids: a few per cent), so a
+// block compacts KT_PITEMS x 128 consecutive points and works through the survivors in dense rounds of 128 -- with one
+// point per thread most blocks kept a single half-empty warp alive and the SM ran 9 warps (0.27 ms for the step's coarse
+// pass against 0.15 ms of the warp-per-query kernel).
+#define KT_PITEMS 8
 __global__ void __launch_bounds__(KT_THREADS) k_knn_points_t(GridDev g, const float* __restrict__ q, long long Q, int K, float r2,
                                                              int* __restrict__ pidx, const int* __restrict__ skip) {
   __shared__ unsigned long long s_list[KT_CAP * KT_THREADS];
-  const long long flat0 = (long long)blockIdx.x * KT_THREADS;
-  const long long mine = flat0 + threadIdx.x;
+  __shared__ int s_item[KT_PITEMS * KT_THREADS];
+  __shared__ int s_wsum[KT_PITEMS * (KT_THREADS / 32)];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long flat0 = (long long)blockIdx.x * (KT_PITEMS * KT_THREADS);
   const bool skipped = skip && *skip;
-  bool valid = false;
-  if (mine < Q) {
-    int cx, cy, cz;
-    const int v = skipped ? -1 : voxel_of(g, q[3 * mine], q[3 * mine + 1], q[3 * mine + 2], cx, cy, cz);
-    valid = v >= 0 && g.hit[v];
-    if (!valid)
-      for (int k = 0; k < K; ++k) pidx[mine * K + k] = -1;
-  }
-  const int item = kt_compact(valid, threadIdx.x);
-  if (__all_sync(SPF_FULL, item < 0)) return;
-  const long long w = flat0 + (item < 0 ? 0 : item);
-  float qx = 0.f, qy = 0.f, qz = 0.f;
-  if (item >= 0) { qx = q[3 * w]; qy = q[3 * w + 1]; qz = q[3 * w + 2]; }
-  unsigned long long key[KT_KR];
-  knn_thread(g, item >= 0, qx, qy, qz, r2, s_list + threadIdx.x, key);
-  if (item >= 0) {
+  // validity of this thread's KT_PITEMS points (point it * 128 + tid of the block), -1 rows for the others
+  unsigned vbits = 0, ball[KT_PITEMS];
 #pragma unroll
-    for (int k = 0; k < KT_KR; ++k)
-      if (k < K) pidx[w * K + k] = key[k] == KEY_NONE ? -1 : (int)(unsigned)(key[k] & 0xffffffffull);
+  for (int it = 0; it < KT_PITEMS; ++it) {
+    const long long mine = flat0 + it * KT_THREADS + tid;
+    bool valid = false;
+    if (mine < Q) {
+      int cx, cy, cz;
+      const int v = skipped ? -1 : voxel_of(g, q[3 * mine], q[3 * mine + 1], q[3 * mine + 2], cx, cy, cz);
+      valid = v >= 0 && g.hit[v];
+      if (!valid)
+        for (int k = 0; k < K; ++k) pidx[mine * K + k] = -1;
+    }
+    ball[it] = __ballot_sync(SPF_FULL, valid);
+    vbits |= (unsigned)valid << it;
+    if (lane == 0) s_wsum[it * (KT_THREADS / 32) + wid] = __popc(ball[it]);
+  }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int it = 0; it < KT_PITEMS; ++it) {
+    int off = total;
+#pragma unroll
+    for (int w = 0; w < KT_THREADS / 32; ++w) {
+      const int c = s_wsum[it * (KT_THREADS / 32) + w];
+      if (w < wid) off += c;
+      total += c;
+    }
+    if ((vbits >> it) & 1) s_item[off + __popc(ball[it] & ((1u << lane) - 1))] = it * KT_THREADS + tid;
+  }
+  __syncthreads();
+  for (int base = 0; base < total; base += KT_THREADS) {
+    if (base + (wid << 5) >= total) break;              // warp-uniform: this warp has no work in this round or later
+    const int item = base + tid < total ? s_item[base + tid] : -1;
+    const long long w = flat0 + (item < 0 ? 0 : item);
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (item >= 0) { qx = q[3 * w]; qy = q[3 * w + 1]; qz = q[3 * w + 2]; }
+    unsigned long long key[KT_KR];
+    knn_thread(g, item >= 0, qx, qy, qz, r2, s_list + tid, key);
+    if (item >= 0) {
+#pragma unroll
+      for (int k = 0; k < KT_KR; ++k)
+        if (k < K) pidx[w * K + k] = key[k] == KEY_NONE ? -1 : (int)(unsigned)(key[k] & 0xffffffffull);
+    }
   }
 }
 
 // 0 = automatic, 1 = always the warp-per-query kernels, 2 = the thread-per-query kernels wherever they apply (K <= 8,
 // radius > 0).  Automatic = thread-per-query for RAY SLOTS (consecutive slots of a ray walk the same cell columns, so a
-// warp's candidate loads share L1 lines: k_knn_slots 0.274 -> 0.205 ms on the 4096-ray DTU-shaped step) and
-// warp-per-query for POINT queries (coarse samples 0.06 apart or unordered points: 32 lanes in 32 different cells make
-// every candidate load 32 L1 wavefronts, 0.147 -> 0.268 ms) and for clouds with very dense voxels (spf_grid.dense_cloud:
-// garden-shaped 1 M points, ~1300 candidates per query, 0.77 -> 1.20 ms with a thread per query).  Full-image eval render,
-// DTU-shaped: k_knn_slots 13.1 -> 6.9 ms per image.
+// warp's candidate loads share L1 lines: k_knn_slots 0.274 -> 0.205 ms on the 4096-ray DTU-shaped step, 13.1 -> 6.9 ms
+// per full eval image) and for very large POINT batches (SDF grids); warp-per-query for the other point queries and for
+// clouds with very dense voxels (spf_grid.dense_cloud: garden-shaped 1 M points, ~1300 candidates per query, 32 lanes in
+// 32 different cells make every candidate load 32 L1 wavefronts: 0.77 -> 1.20 ms with a thread per query).
 static int g_knn_algo = 0;
 extern "C" int spf_knn_set_algo(int32_t algo) {
   if (algo < 0 || algo > 2) return SPF_ERR_INVALID;
   g_knn_algo = algo;
   return SPF_OK;
 }
-static inline bool knn_use_thread_kernels(const spf_grid* g, int K, float radius2, bool ray_slots) {
+static inline bool knn_use_thread_kernels(const spf_grid* g, int K, float radius2, bool ray_slots, long long Q = 0) {
   if (K > KT_KR || !(radius2 > 0.0f) || g_knn_algo == 1) return false;
-  return g_knn_algo == 2 || (ray_slots && !g->dense_cloud);
+  if (g_knn_algo == 2) return true;
+  if (g->dense_cloud) return false;
+  // point queries: only the very large batches (SDF grids for marching cubes: 16 M consecutive grid points per chunk,
+  // 512^3 volume 35.0 -> 14.6 ms); the step's coarse pass (0.5 M points, 0.15 ms) has too few valid points to fill the
+  // machine with one thread per query, and a 2 M-point eval chunk is a draw
+  return ray_slots || Q >= (1ll << 22);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,8 +623,9 @@ extern "C" int spf_knn_points_pred(const spf_grid* g, const float* q, int64_t Q,
   if (K < 1 || K > 20) return SPF_ERR_INVALID;
   if (Q <= 0) return SPF_OK;
   if (!g || !q || !pidx) return SPF_ERR_INVALID;
-  if (knn_use_thread_kernels(g, K, radius2, false)) {
-    k_knn_points_t<<<(unsigned)((Q + KT_THREADS - 1) / KT_THREADS), KT_THREADS, 0, (cudaStream_t)stream_>>>(
+  if (knn_use_thread_kernels(g, K, radius2, false, Q)) {
+    const long long per_block = (long long)KT_PITEMS * KT_THREADS;
+    k_knn_points_t<<<(unsigned)((Q + per_block - 1) / per_block), KT_THREADS, 0, (cudaStream_t)stream_>>>(
         to_dev_query(g, radius2), q, Q, K, radius2, pidx, skip);
     SPF_CHECK_LAUNCH("k_knn_points_t");
     return SPF_OK;
