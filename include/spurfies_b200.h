@@ -280,6 +280,10 @@ int spf_grad_sumsq(const float* grad, int64_t n, float grad_scale, float* norm_s
 int spf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* norm_sq,
                   float* state /*[2]*/, float grad_scale, float max_norm, double beta1, double beta2, float eps,
                   int32_t zero_grad, float* info, void* stream);
+/* [S, 1/S] with S = 2^floor(log2(target / max|x|)) (clamped to 2^+-100): the per-step power-of-two scale of the
+ * tensor-core mode's fp16 gradient chain, computed on the device in one launch.  scratch: 2 words, zero before the first
+ * call, left zero by every call.  (No reference counterpart: the reference trains in fp32.) */
+int spf_grad_scale(const float* x, int64_t n, float target, float* out /*[2]*/, uint32_t* scratch /*[2]*/, void* stream);
 
 /* ---- f2: SDF-grid query feeding marching cubes (spurfies/utils/plots.py:188-287, 302-333; get_sdf_eval,
  * pointneus_disent.py:249-298) ------------------------------------------------------------------------------------- */

@@ -100,6 +100,7 @@ _SIGS = {
     "spf_knn_points": [_P, _P, _L, _I, _F, _P, _P],
     "spf_knn_points_pred": [_P, _P, _L, _I, _F, _P, _P, _P],
     "spf_knn_set_algo": [_I],
+    "spf_grad_scale": [_P, _L, _F, _P, _P, _P],
     "spf_mask_points": [_P, _P, _L, _P, _P],
     "spf_compact_valid": [_P, _L, _I, _P, _P, _P, _Z, _P],
     "spf_ray_prep": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],

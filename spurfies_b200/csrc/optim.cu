@@ -152,3 +152,52 @@ extern "C" int spf_adam_step(float* param, float* grad, float* exp_avg, float* e
   SPF_CHECK_LAUNCH("k_adam_tick");
   return SPF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// [S, 1 / S] of the tensor-core mode's scaled-fp16 gradient chain (fields.py::grad_scale): S = 2^floor(log2(target /
+// max|x|)), clamped to 2^+-100.  One launch instead of the ten elementwise / reduction launches of the torch expression
+// (abs, amax, clamp, reciprocal-multiply, log2, floor, clamp, neg, exp2 x2, stack).  |x| as raw bits orders like an
+// unsigned integer (NaN above everything, so a NaN gradient gives S = NaN as the torch expression does); the last block
+// to finish finalises and leaves the two scratch words zero for the next call.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grad_scale(const float* __restrict__ x, long long n, float target,
+                                                    float* __restrict__ out, unsigned* __restrict__ scratch) {
+  unsigned m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(SPF_FULL, m, o));
+  __shared__ unsigned s_m[8];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = max(m, s_m[w]);
+    atomicMax(scratch, m);
+    __threadfence();
+    if (atomicAdd(scratch + 1, 1u) == gridDim.x - 1) {   // last block
+      __threadfence();
+      const float raw = __uint_as_float(atomicExch(scratch, 0u));
+      const float amax = fmaxf(raw, 1.0e-30f);   // (fmaxf drops a NaN: tested on `raw`)
+      scratch[1] = 0u;
+      float S, invS;
+      if (raw != raw) {
+        S = invS = raw;
+      } else {
+        const float e = fminf(fmaxf(floorf(log2f(target / amax)), -100.0f), 100.0f);
+        S = exp2f(e);
+        invS = exp2f(-e);
+      }
+      out[0] = S;
+      out[1] = invS;
+    }
+  }
+}
+
+extern "C" int spf_grad_scale(const float* x, int64_t n, float target, float* out, uint32_t* scratch, void* stream_) {
+  if (!x || !out || !scratch || n <= 0 || !(target > 0.0f)) return SPF_ERR_INVALID;
+  const long long want = (n + 256 * 8 - 1) / (256 * 8);
+  const int nb = (int)(want < 296 ? (want < 1 ? 1 : want) : 296);
+  k_grad_scale<<<nb, 256, 0, (cudaStream_t)stream_>>>(x, (long long)n, target, out, scratch);
+  SPF_CHECK_LAUNCH("k_grad_scale");
+  return SPF_OK;
+}

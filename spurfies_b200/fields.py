@@ -77,7 +77,7 @@ class SlotSet:
         self.n = self.pidx.shape[0]
         dev = pidx.device
         self.list = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
-        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.count = torch.empty(1, dtype=torch.int32, device=dev)   # always written by spf_compact_valid
         ws = Arena.get("compact_ws", (_lib.lib.spf_compact_workspace_bytes(self.n),), torch.uint8, dev)
         call("spf_compact_valid", ptr(self.pidx), self.n, self.K, ptr(self.list), ptr(self.count), ptr(ws), ws.numel(),
              stream())
@@ -278,13 +278,26 @@ class _ZeroPool:
         return out
 
 
+_GS_SCRATCH = {}
+
+
 def grad_scale(upstream: torch.Tensor, target: float = 16.0) -> torch.Tensor:
     """Device tensor [S, 1/S] for the tensor-core mode's fp16 gradient chain: S = the power of two that brings the largest
     upstream gradient entry just below `target` (2^12 of fp16 headroom above for growth through the layers, 2^28 of range
-    below), computed on the device (no host sync, CUDA-graph capturable).  Powers of two make scaling / unscaling exact."""
-    amax = upstream.detach().abs().amax().to(torch.float32).clamp(min=1.0e-30)
-    e = torch.floor(torch.log2(target / amax)).clamp(-100.0, 100.0)
-    return torch.stack([torch.exp2(e), torch.exp2(-e)]).contiguous()
+    below), computed on the device by one launch (spf_grad_scale: no host sync, CUDA-graph capturable).  Powers of two
+    make scaling / unscaling exact."""
+    x = upstream.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    dev = x.device
+    scratch = _GS_SCRATCH.get(dev)
+    if scratch is None:
+        scratch = _GS_SCRATCH[dev] = torch.zeros(2, dtype=torch.int32, device=dev)   # kept zero by the kernel
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    if x.numel() == 0:
+        return out.fill_(1.0)
+    call("spf_grad_scale", ptr(x), x.numel(), float(target), ptr(out), ptr(scratch), stream())
+    return out
 
 
 def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None, gscale=None):
@@ -641,7 +654,7 @@ class TVRegul(torch.autograd.Function):
         (value and gradient), so that the average over the ranks is the full regulariser."""
         N, K = self_pidx.shape
         dev = feat_g.device
-        value = torch.zeros(1, dtype=torch.float32, device=dev)
+        value = torch.empty(1, dtype=torch.float32, device=dev)    # cleared inside spf_tv_fwd_bwd_range
         grad = torch.zeros_like(feat_g, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         call("spf_tv_fwd_bwd_range", ptr(pts), ptr(feat_g.detach().contiguous()), ptr(self_pidx), N, K, int(first),
              int(N if count is None else count), ptr(value), ptr(grad), float(scale), stream())

@@ -64,6 +64,18 @@ def default_conf(near: float = 0.5, **over) -> _Conf:
     return c
 
 
+_ZERO = {}
+
+
+def _zero_scalar(dev) -> torch.Tensor:
+    """A persistent read-only 0-d zero on `dev` (loss terms that are switched off): no fill launch per step."""
+    dev = torch.device(dev)
+    z = _ZERO.get(dev)
+    if z is None:
+        z = _ZERO[dev] = torch.zeros((), device=dev)
+    return z
+
+
 class LaplaceDensity(nn.Module):
     """alpha * Laplace(0, beta).cdf(-sdf)  (density.py:16-30).  The module form is API plumbing; on the hot path the
     density is evaluated inside the compositing / sampler kernels."""
@@ -429,7 +441,7 @@ class PointVolSDF(nn.Module):
         ray_mask = nvalid > 0
         # feature-consistency loss at the first back-facing zero crossing (pointneus_disent.py:727-763, DTU 3-view only)
         local_data = input.get("local_data", None)
-        local_loss = torch.zeros((), device=dev)
+        local_loss = _zero_scalar(dev)
         world, group = self._dp
         dp = world > 1 and self.training
         counts = {}
@@ -447,7 +459,7 @@ class PointVolSDF(nn.Module):
             if dp:
                 counts["pseudo"] = aux["pseudo_count"]
         else:
-            pseudo = torch.zeros((), device=dev)
+            pseudo = _zero_scalar(dev)
         eik_scale = None
         if dp:
             # global-count normalisation of the count-normalised means (one 12-byte all-reduce, no host sync)
@@ -467,7 +479,7 @@ class PointVolSDF(nn.Module):
             "xyz": x_new,
             "local_loss": local_loss,
             "pseudo_pts_loss": pseudo,
-            "tv_loss": self.tv_loss() if aux_losses else torch.zeros((), device=dev),
+            "tv_loss": self.tv_loss() if aux_losses else _zero_scalar(dev),
         }
         if self.white_bkgd:  # pointneus_disent.py:856-861 (computed but never written back there either)
             pass
@@ -540,7 +552,7 @@ class VolSDFLoss(nn.Module):
         mask_gt = ground_truth["mask"].to(dev).float()
         mask2 = mask_gt.squeeze()
         mask2 = mask2.reshape(mask2.shape[0], -1).contiguous()          # loss.py:83: mask.squeeze()[:, 0]
-        zero = torch.zeros((), device=dev)
+        zero = _zero_scalar(dev)
         tv = model_outputs.get("tv_loss") if self.tv_weight > 0 else None
         pseudo = model_outputs.get("pseudo_pts_loss") if self.pseudo_weight > 0 else None
         local = model_outputs.get("local_loss")

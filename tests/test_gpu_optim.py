@@ -295,3 +295,22 @@ def test_arena_reuse_before_backward_is_an_error():
     lb.backward()
     inter = m1.F_color[0].weight.grad
     assert float((inter - solo).abs().max()) <= 1e-4 * float(solo.abs().max())
+
+
+@pytest.mark.parametrize("n,scale", [(1, 3.0e-7), (1000, 1.0), (983_040, 2.5e-4), (5_000_000, 7.0e3)])
+def test_grad_scale_kernel_matches_torch_expression(n, scale):
+    """spf_grad_scale == the torch expression it replaces (S = 2^floor(log2(target / max|x|)), [S, 1/S]); NaN in, NaN out;
+    repeated calls (the scratch words are left zero)."""
+    from spurfies_b200.fields import grad_scale
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, generator=g) * scale).cuda()
+    for target in (16.0, 1.0):
+        amax = x.abs().amax().clamp(min=1.0e-30)
+        e = torch.floor(torch.log2(target / amax)).clamp(-100.0, 100.0)
+        want = torch.stack([torch.exp2(e), torch.exp2(-e)])
+        for _ in range(2):
+            got = grad_scale(x, target)
+            assert torch.equal(got, want), (got, want)
+    x[n // 2] = float("nan")
+    assert bool(torch.isnan(grad_scale(x)).all())
+    assert torch.equal(grad_scale(torch.zeros(8, device="cuda")), torch.tensor([2.0 ** 100, 2.0 ** -100], device="cuda"))
