@@ -52,7 +52,8 @@ def measured_traffic(kernel_regex):
     d = json.load(open(p))
     for name, v in d.get("kernels", {}).items():
         if re.search(kernel_regex, name):
-            return v.get("dram_bytes"), "profiles/%s (%s)" % (d.get("file", "ncu_traffic.json"), name)
+            return v.get("dram_bytes"), "profiles/ncu_traffic.json (%s of the ncu --set full capture %s, table in profiles/%s)" % (
+                name, d.get("file", "?"), d.get("file", "?").replace("_top.ncu-rep", "_ncu_full.md"))
     return None, None
 
 # kernels launched per C-ABI call (for gpu_launches)
@@ -633,27 +634,32 @@ def run_inference(args):
             inp = inputs[i % 3]
             if from_host:
                 inp = dict(inp, uv=uv_host.to(device, non_blocking=True))
-            out, (lo, hi) = E.render_image(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world)
+            if world > 1:   # two-row blocks dealt round-robin: contiguous slices leave the background ranks idle
+                out, _ = E.render_image_interleaved(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world,
+                                                    block=1024)
+            else:
+                out, (lo, hi) = E.render_image(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world)
             return out
 
         units, unit, metric = total, "rays/s", "eval rays/s (full-image render, inference)"
         desc = ("BASELINE configs[3]: full-image %dx%d eval render (%d rays, eval sampler schedule <= 5 iterations, %d-ray "
-                "chunks), DTU-shaped %d neural points, pixels sharded over the GPUs" % (W, H, total, args.eval_chunk, N_POINTS))
+                "chunks), DTU-shaped %d neural points, two-row pixel blocks dealt round-robin over the GPUs" % (W, H, total, args.eval_chunk, N_POINTS))
         d2h = lambda out: sum(out[k].numel() * 4 for k in ("rgb_values", "depth_values", "normal_map"))
     else:
         res = args.mesh_res
         grid = mesh.get_grid_uniform(res, (-1.0, 1.0))
         total = res ** 3
-        lo, hi = shard_range(total, rank, world)
-        vol = torch.empty(hi - lo, dtype=torch.float32, device=device)
+        cyc = (1 << 18) if world > 1 else None      # block-cyclic shares (one 512-point z column x 512): balanced ranks
+        n_local = mesh.cyclic_local_count(total, rank, world, cyc) if cyc else shard_range(total, rank, world)[1] - shard_range(total, rank, world)[0]
+        vol = torch.empty(n_local, dtype=torch.float32, device=device)
 
         def one(i, from_host=False):
-            mesh.sdf_volume(model, grid["xyz"], chunk=args.mesh_chunk, rank=rank, world=world, out=vol)
+            mesh.sdf_volume(model, grid["xyz"], chunk=args.mesh_chunk, rank=rank, world=world, out=vol, cyclic_block=cyc)
             return {"volume": vol}
 
         units, unit, metric = total, "grid points/s", "SDF grid points/s (marching-cubes query)"
         desc = ("BASELINE configs[4]: %d^3 SDF grid query (get_sdf_eval: kNN + prior MLP) over [-1,1]^3, DTU-shaped %d neural "
-                "points, grid slabs sharded over the GPUs, %d-point chunks" % (res, N_POINTS, args.mesh_chunk))
+                "points, block-cyclic shares of the grid over the GPUs, %d-point chunks" % (res, N_POINTS, args.mesh_chunk))
         d2h = lambda out: out["volume"].numel() * 4
 
     def barrier():
@@ -731,6 +737,8 @@ def run_inference(args):
         other = {}
 
         def add(name, nbytes, note):
+            if name not in kms and name + "_pred" in kms:   # the predicated entry point of the same kernel
+                name = name + "_pred"
             if name in kms and kms[name] > 0:
                 g = nbytes / (kms[name] * 1e-3) / 1e9
                 other[name] = {"achieved": g, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": g / pk["hbm_gbs"],

@@ -85,7 +85,7 @@ int spf_mask_slots(const spf_grid* g, const float* raypos /*[R,D,3]*/, int32_t R
 int spf_knn_slots(const spf_grid* g, const float* sample_loc, const int32_t* n_slots, int32_t R, int32_t Smax,
                   int32_t K, float radius2, int32_t* pidx /*[R,Smax,K]*/, int32_t* ray_nvalid /*[R]*/, void* stream);
 /* Kernel choice for a3 (same results either way, tests compare them): 0 = automatic -- one THREAD per query for ray
- * slots and for point batches of >= 4 M points when K <= 8, radius2 > 0 and the cloud is not dense_cloud, one warp per
+ * slots and for point batches of >= 1 M points when K <= 8, radius2 > 0 and the cloud is not dense_cloud, one warp per
  * query otherwise; 1 = always one warp per query; 2 = one thread per query wherever K <= 8 and radius2 > 0. */
 int spf_knn_set_algo(int32_t algo);
 /* a2+a3 fused for point queries (D = 1, Smax = 1: sdf_importance / get_sdf_eval / pseudo_sdf / tv_regul). */
@@ -295,6 +295,14 @@ int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, co
                          int32_t nz, int64_t lo, int64_t count, float fill, float* vol /*[count]*/,
                          int32_t* idx_out /*[cap]*/, float* pts_out /*[cap,3]*/, int32_t* counter /*[1]*/, int32_t cap,
                          void* stream);
+/* The same over a BLOCK-CYCLIC share of the grid (multi-GPU: contiguous slabs give the ranks whose slab crosses the object
+ * all the work): the grid's linear index space is cut into blocks of `block` points, block b belongs to rank b % world, and
+ * a rank numbers its own points consecutively (local index j -> global index ((j / block) * world + rank) * block +
+ * j % block).  lo / count / vol / idx_out are in LOCAL indices.  world = 1 is spf_grid_points_mask. */
+int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx, int32_t ny,
+                                int32_t nz, int64_t lo, int64_t count, int64_t block, int32_t world, int32_t rank, float fill,
+                                float* vol /*[count]*/, int32_t* idx_out /*[cap]*/, float* pts_out /*[cap,3]*/,
+                                int32_t* counter /*[1]*/, int32_t cap, void* stream);
 /* out[idx[i]] = vals[i] */
 int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream);
 

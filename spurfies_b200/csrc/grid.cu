@@ -484,10 +484,10 @@ static inline bool knn_use_thread_kernels(const spf_grid* g, int K, float radius
   if (K > KT_KR || !(radius2 > 0.0f) || g_knn_algo == 1) return false;
   if (g_knn_algo == 2) return true;
   if (g->dense_cloud) return false;
-  // point queries: only the very large batches (SDF grids for marching cubes: 16 M consecutive grid points per chunk,
-  // 512^3 volume 35.0 -> 14.6 ms); the step's coarse pass (0.5 M points, 0.15 ms) has too few valid points to fill the
-  // machine with one thread per query, and a 2 M-point eval chunk is a draw
-  return ray_slots || Q >= (1ll << 22);
+  // point queries: only the large batches (SDF grids for marching cubes: the ~2 M in-occupancy points of a 16 M-point
+  // chunk, consecutive along z: 512^3 volume 35.0 -> 14.6 ms); the step's coarse pass (0.5 M points, 0.15 ms) has too
+  // few valid points to fill the machine with one thread per query, and a 2 M-point eval chunk is a draw
+  return ray_slots || Q >= (1ll << 20);
 }
 
 // ------------------------------------------------------------------------------------------------

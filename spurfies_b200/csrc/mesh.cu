@@ -12,6 +12,7 @@
 //   linear index = (iy * nx + ix) * nz + iz,  point = (x[ix], y[iy], z[iz])
 __global__ void k_grid_points_mask(GridDev g, const float* __restrict__ xs, const float* __restrict__ ys,
                                    const float* __restrict__ zs, int nx, int ny, int nz, long long lo, long long count,
+                                   long long cyc_block, int cyc_world, int cyc_rank,
                                    float fill, float* __restrict__ vol, int* __restrict__ idx_out,
                                    float* __restrict__ pts_out, int* __restrict__ counter, int cap) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -19,7 +20,10 @@ __global__ void k_grid_points_mask(GridDev g, const float* __restrict__ xs, cons
   bool h = false;
   float x = 0.f, y = 0.f, z = 0.f;
   if (t < count) {
-    const long long i = lo + t;
+    // block-cyclic distribution over ranks (cyc_world == 1: identity): local index j = lo + t lives in this rank's
+    // (j / block)-th block, which is global block (j / block) * world + rank
+    const long long j = lo + t;
+    const long long i = cyc_world == 1 ? j : ((j / cyc_block) * cyc_world + cyc_rank) * cyc_block + (j % cyc_block);
     const int iz = (int)(i % nz);
     const long long r = i / nz;
     const int ix = (int)(r % nx), iy = (int)(r / nx);
@@ -48,19 +52,33 @@ __global__ void k_scatter_f32(const int* __restrict__ idx, const float* __restri
   if (i < n) out[idx[i]] = vals[i];
 }
 
-extern "C" int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx,
-                                    int32_t ny, int32_t nz, int64_t lo, int64_t count, float fill, float* vol,
-                                    int32_t* idx_out, float* pts_out, int32_t* counter, int32_t cap, void* stream_) {
+extern "C" int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx,
+                                           int32_t ny, int32_t nz, int64_t lo, int64_t count, int64_t block, int32_t world,
+                                           int32_t rank, float fill, float* vol, int32_t* idx_out, float* pts_out,
+                                           int32_t* counter, int32_t cap, void* stream_) {
   if (!g || !xs || !ys || !zs || !vol || !idx_out || !pts_out || !counter) return SPF_ERR_INVALID;
-  if (nx <= 0 || ny <= 0 || nz <= 0 || lo < 0 || count < 0 || lo + count > (int64_t)nx * ny * nz) return SPF_ERR_INVALID;
+  if (nx <= 0 || ny <= 0 || nz <= 0 || lo < 0 || count < 0 || block < 1 || world < 1 || rank < 0 || rank >= world)
+    return SPF_ERR_INVALID;
   if (count > 0x7fffffffLL) return SPF_ERR_UNSUPPORTED;   // chunk-local indices are int32
+  if (count > 0) {   // the last local index must map inside the grid
+    const int64_t j = lo + count - 1;
+    const int64_t i = world == 1 ? j : ((j / block) * world + rank) * block + (j % block);
+    if (i >= (int64_t)nx * ny * nz) return SPF_ERR_INVALID;
+  }
   cudaStream_t st = (cudaStream_t)stream_;
   SPF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st), "grid_points_mask memset");
   if (count == 0) return SPF_OK;
-  k_grid_points_mask<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(to_dev(g), xs, ys, zs, nx, ny, nz, lo, count, fill, vol,
-                                                                     idx_out, pts_out, counter, cap);
+  k_grid_points_mask<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(to_dev(g), xs, ys, zs, nx, ny, nz, lo, count, block, world,
+                                                                     rank, fill, vol, idx_out, pts_out, counter, cap);
   SPF_CHECK_LAUNCH("k_grid_points_mask");
   return SPF_OK;
+}
+
+extern "C" int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx,
+                                    int32_t ny, int32_t nz, int64_t lo, int64_t count, float fill, float* vol,
+                                    int32_t* idx_out, float* pts_out, int32_t* counter, int32_t cap, void* stream_) {
+  return spf_grid_points_mask_cyclic(g, xs, ys, zs, nx, ny, nz, lo, count, 1, 1, 0, fill, vol, idx_out, pts_out, counter, cap,
+                                     stream_);
 }
 
 extern "C" int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream_) {

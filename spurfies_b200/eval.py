@@ -67,3 +67,34 @@ def render_image(model, model_input: Dict, total_pixels: int, n_pixels: int = 16
         return merge_output(res, hi - lo, 1), (lo, hi)
     finally:
         model.train(was_training)
+
+
+def interleaved_pixels(total_pixels: int, rank: int, world: int, block: int = 1024) -> torch.Tensor:
+    """Pixel indices of `rank` when the image is dealt out in blocks of `block` consecutive pixels, round-robin over the
+    ranks (block b goes to rank b % world).  Contiguous slices (``render_image``) give the ranks whose rows cross the
+    object several times the work of the ranks that see background only -- 8 GPUs, DTU-shaped scene: 39.5 ms per image
+    against 222 ms / 8 = 27.8 ms of perfectly divided work; dealing out two-row blocks evens that out."""
+    if world < 1 or not (0 <= rank < world) or block < 1:
+        raise ValueError(f"bad rank/world/block {rank}/{world}/{block}")
+    idx = torch.arange(total_pixels, dtype=torch.long)
+    return idx[(idx // block) % world == rank]
+
+
+@torch.no_grad()
+def render_image_interleaved(model, model_input: Dict, total_pixels: int, n_pixels: int = 16384, rank: int = 0, world: int = 1,
+                             block: int = 1024, fast: int = -1, keys=RENDER_KEYS) -> Tuple[Dict, torch.Tensor]:
+    """Eval-mode render of this rank's interleaved pixel set (``interleaved_pixels``), in chunks of `n_pixels`.  Returns
+    (outputs over the set, the pixel indices they belong to); ``out[k]`` of all ranks scattered to ``idx`` is the image.
+    No collective.  (The eval sampler's iteration count is a property of the chunk, ray_sampler.py:466-468, so -- as
+    with any other choice of ``split_n_pixels`` in the reference -- a pixel can receive a slightly different sample set
+    than in a render with other chunks.)"""
+    idx = interleaved_pixels(total_pixels, rank, world, block)
+    sub = dict(model_input)
+    dev = model_input["uv"].device
+    sel = idx.to(dev)
+    sub["uv"] = model_input["uv"][:, sel]
+    for key in ("object_mask", "rgb"):
+        if key in sub:
+            sub[key] = model_input[key][:, sel]
+    out, _ = render_image(model, sub, int(idx.numel()), n_pixels=n_pixels, fast=fast, keys=keys)
+    return out, idx

@@ -55,18 +55,43 @@ def grid_points(xyz: Sequence[np.ndarray]) -> torch.Tensor:
     return torch.tensor(np.vstack([xx.ravel(), yy.ravel(), zz.ravel()]).T, dtype=torch.float)
 
 
+def cyclic_local_count(G: int, rank: int, world: int, block: int) -> int:
+    """Number of grid points of `rank` under the block-cyclic distribution (block b of `block` points -> rank b % world)."""
+    nb = (G + block - 1) // block
+    mine = (nb - rank + world - 1) // world if rank < nb else 0
+    n = mine * block
+    if mine > 0 and (nb - 1) % world == rank:      # the (possibly partial) last block is ours
+        n -= nb * block - G
+    return n
+
+
+def cyclic_global_index(local: torch.Tensor, rank: int, world: int, block: int) -> torch.Tensor:
+    """Global grid index of a rank's local indices (spf_grid_points_mask_cyclic)."""
+    local = local.to(torch.int64)
+    return ((local // block) * world + rank) * block + local % block
+
+
 @torch.no_grad()
 def sdf_volume(model, xyz: Sequence[np.ndarray], chunk: int = 1 << 24, rank: int = 0, world: int = 1,
-               out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Tuple[int, int]]:
+               out: Optional[torch.Tensor] = None, cyclic_block: Optional[int] = None) -> Tuple[torch.Tensor, Tuple[int, int]]:
     """SDF of ``model.get_sdf_eval`` at the grid points of axes ``xyz`` in the reference's order (index =
     (iy * nx + ix) * nz + iz).  Returns (flat fp32 device tensor over this rank's contiguous index range, (lo, hi)).
-    Reshape the full volume as ``[ny, nx, nz]`` (plots.py:259-261 then transposes it to [nx, ny, nz])."""
+    Reshape the full volume as ``[ny, nx, nz]`` (plots.py:259-261 then transposes it to [nx, ny, nz]).
+
+    ``cyclic_block`` (multi-GPU): instead of a contiguous slab the rank owns every world-th block of that many grid points
+    (``cyclic_global_index`` maps its consecutive local indices to grid indices) -- a contiguous slab that crosses the
+    object costs several times one that does not; the returned range is then (0, number of local points)."""
     set_precision(model.precision)
     dev = model.neural_pts.device
     ax = [torch.as_tensor(np.asarray(a, dtype=np.float64)).to(torch.float32).to(dev).contiguous() for a in xyz]
     nx, ny, nz = (int(a.numel()) for a in ax)
     G = nx * ny * nz
-    lo, hi = shard_range(G, rank, world)
+    if cyclic_block is None or world == 1:
+        lo, hi = shard_range(G, rank, world)
+        cyc = (1, 1, 0)
+    else:
+        lo, hi = 0, cyclic_local_count(G, rank, world, int(cyclic_block))
+        cyc = (int(cyclic_block), int(world), int(rank))
     if out is None:
         out = torch.empty(hi - lo, dtype=torch.float32, device=dev)
     assert out.numel() == hi - lo and out.is_cuda and out.dtype == torch.float32
@@ -80,8 +105,8 @@ def sdf_volume(model, xyz: Sequence[np.ndarray], chunk: int = 1 << 24, rank: int
     for c0 in range(lo, hi, chunk):
         n = min(chunk, hi - c0)
         vol = out[c0 - lo:c0 - lo + n]
-        call("spf_grid_points_mask", C.byref(grid.handle), ptr(ax[0]), ptr(ax[1]), ptr(ax[2]), nx, ny, nz, c0, n,
-             NO_NEIGHBOUR, ptr(vol), ptr(idx), ptr(pts), ptr(counter), chunk, stream())
+        call("spf_grid_points_mask_cyclic", C.byref(grid.handle), ptr(ax[0]), ptr(ax[1]), ptr(ax[2]), nx, ny, nz, c0, n,
+             cyc[0], cyc[1], cyc[2], NO_NEIGHBOUR, ptr(vol), ptr(idx), ptr(pts), ptr(counter), chunk, stream())
         m = int(counter.item())            # one 4-byte readback per chunk (the reference copies the whole chunk)
         if m == 0:
             continue

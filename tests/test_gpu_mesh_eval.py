@@ -98,3 +98,30 @@ def test_render_image_chunks_and_shards(setup):
                 chunks.append(model(s, aux_losses=False)["rgb_values"])
         assert torch.equal(part["rgb_values"], torch.cat(chunks))
     assert not model.training
+
+
+def test_block_cyclic_volume_and_interleaved_render_equal_the_whole(setup):
+    """Multi-GPU load balancing without a collective: the ranks' block-cyclic shares of the SDF grid scatter back to the
+    volume of one rank bit for bit, and the interleaved pixel sets render the pixels the model renders for them."""
+    from spurfies_b200 import eval as E
+    from spurfies_b200 import mesh, scenes
+    g, P, model = setup
+    grid = mesh.get_grid_uniform(22, (-0.8, 0.8))
+    whole, _ = mesh.sdf_volume(model, grid["xyz"], chunk=3000)
+    back = torch.full_like(whole, float("nan"))
+    for r in range(3):
+        part, (lo, hi) = mesh.sdf_volume(model, grid["xyz"], chunk=1000, rank=r, world=3, cyclic_block=128)
+        assert lo == 0 and hi == mesh.cyclic_local_count(22 ** 3, r, 3, 128) == part.numel()
+        back[mesh.cyclic_global_index(torch.arange(hi), r, 3, 128).cuda()] = part
+    assert torch.equal(back, whole)
+    cam = scenes.camera(1, 2.3)
+    uv = scenes.pixel_batch(96, seed=5)
+    inp = {"uv": uv.cuda(), "pose": cam["pose"].cuda(), "intrinsics": cam["intrinsics"].cuda(), "local_data": None}
+    covered = torch.zeros(96, dtype=torch.bool)
+    for r in range(2):
+        out, idx = E.render_image_interleaved(model, inp, 96, n_pixels=20, rank=r, world=2, block=8)
+        assert torch.equal(idx, E.interleaved_pixels(96, r, 2, 8)) and out["rgb_values"].shape == (idx.numel(), 3)
+        ref, _ = E.render_image(model, dict(inp, uv=uv[:, idx].cuda()), int(idx.numel()), n_pixels=20)
+        assert torch.equal(out["rgb_values"], ref["rgb_values"]) and torch.equal(out["weights"], ref["weights"])
+        covered[idx] = True
+    assert bool(covered.all())

@@ -84,3 +84,24 @@ def test_pack_jobs_struct_matches_the_header():
     assert C.sizeof(_lib.WgradJob) == 4 * C.sizeof(C.c_void_p) + 4 * 4          # lda, N, fmt, reserved
     assert _lib.PackJob.out.offset == 8 and _lib.PackJob.ld.offset == 16 and _lib.WgradJob.lda.offset == 32
     assert _lib.WgradJob.fmt.offset == 40
+
+
+def test_block_cyclic_shares_partition_the_index_space():
+    """mesh.cyclic_local_count / cyclic_global_index (spf_grid_points_mask_cyclic) and eval.interleaved_pixels: the ranks'
+    shares are disjoint, cover everything, and the local -> global map is the stated block-cyclic one."""
+    import torch
+    from spurfies_b200 import mesh
+    from spurfies_b200.eval import interleaved_pixels
+    for G, world, block in ((1000, 3, 64), (4096, 8, 512), (130, 4, 64), (5, 8, 2), (64, 1, 16)):
+        seen = []
+        for r in range(world):
+            n = mesh.cyclic_local_count(G, r, world, block)
+            gi = mesh.cyclic_global_index(torch.arange(n), r, world, block)
+            assert n == 0 or int(gi.max()) < G
+            assert bool(((gi // block) % world == r).all())
+            assert bool((gi[1:] > gi[:-1]).all())
+            seen.append(gi)
+            px = interleaved_pixels(G, r, world, block)
+            assert torch.equal(px, gi)
+        allv = torch.cat(seen).sort().values
+        assert torch.equal(allv, torch.arange(G))
