@@ -284,8 +284,8 @@ static inline GridDev to_dev_query(const spf_grid* g, float radius2) {
 // The result is the K smallest by (d2, id), as before: the selection is a total order, so it cannot depend on the scan
 // order -- bit-identical to knn_warp (tests/test_gpu_knn.py compares both with the oracle and with each other).
 // ------------------------------------------------------------------------------------------------
-#define KT_THREADS 128
-#define KT_CAP 24
+#define KT_THREADS 128   // measured on the 4096-ray step: 64-thread blocks 0.235 ms, 128: 0.209 ms; 2 / 4 slots per thread
+#define KT_CAP 24        // (256 / 512 slots per block, dense rounds as in k_knn_points_t): 0.232 / 0.292 ms
 #define KT_UNROLL 4
 #define KT_KR 8
 
