@@ -170,6 +170,8 @@ def test_thread_per_query_kernels_equal_warp_per_query_kernels(scene, n_points):
                 out[(algo, k)] = res
     finally:
         _lib.call("spf_knn_set_algo", 0)
+    # the kernel-family hint of the automatic mode: set from the build statistics (very dense voxels -> warp per query)
+    assert vg.handle.dense_cloud == (1 if scene == "garden" else 0), vg.stats()
     print(f"{scene}: ms (points, slots) per kernel family (1 = warp per query, 2 = thread per query):", {f"algo{a}_k{k}": v for (a, k), v in ms.items()})
     for k in (8, 3):
         for x, y in zip(out[(2, k)], out[(1, k)]):
@@ -269,3 +271,24 @@ def test_against_unmodified_reference_extension():
     b = ref_pidx.sort(-1).values
     assert torch.equal(a, b), f"{int((a != b).any(-1).sum())} of {a.shape[0] * a.shape[1]} slots differ"
     assert int((b >= 0).sum()) > 10000
+
+
+def test_point_queries_under_a_device_side_predicate():
+    """spf_knn_points_pred (VoxelGrid.query_points(skip=)): flag 0 -> the plain query; flag != 0 at launch time -> nothing
+    is searched, every row is -1 (the eval sampler's iterations after convergence); both kernel families."""
+    from spurfies_b200 import _lib
+    sc = scenes.dtu_like(30000, seed=3)
+    vg = make_grid(sc["pts"], sc["ranges"])
+    q = (sc["pts"][:20000] + 0.01 * torch.randn(20000, 3, generator=torch.Generator().manual_seed(2))).cuda().contiguous()
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    try:
+        for algo in (1, 2):
+            _lib.call("spf_knn_set_algo", algo)
+            plain = vg.query_points(q, 8, 2.0)
+            assert int((plain >= 0).sum()) > 50000
+            flag.zero_()
+            assert torch.equal(vg.query_points(q, 8, 2.0, skip=flag), plain)
+            flag.fill_(1)
+            assert bool((vg.query_points(q, 8, 2.0, skip=flag) == -1).all())
+    finally:
+        _lib.call("spf_knn_set_algo", 0)
