@@ -300,8 +300,10 @@ int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, co
  * a rank numbers its own points consecutively (local index j -> global index ((j / block) * world + rank) * block +
  * j % block).  lo / count / vol / idx_out are in LOCAL indices.  world = 1 is spf_grid_points_mask. */
 int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx, int32_t ny,
-                                int32_t nz, int64_t lo, int64_t count, int64_t block, int32_t world, int32_t rank, float fill,
-                                float* vol /*[count]*/, int32_t* idx_out /*[cap]*/, float* pts_out /*[cap,3]*/,
+                                int32_t nz, int64_t lo, int64_t count, int64_t block, int32_t world, int32_t rank,
+                                const float* affine /*[12] device or NULL: point = M (x,y,z) + c, M row-major then c -- the
+                                PCA-aligned grid of get_surface_by_grid(higher_res=True), plots.py:240-246*/,
+                                float fill, float* vol /*[count]*/, int32_t* idx_out /*[cap]*/, float* pts_out /*[cap,3]*/,
                                 int32_t* counter /*[1]*/, int32_t cap, void* stream);
 /* out[idx[i]] = vals[i] */
 int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream);

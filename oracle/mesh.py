@@ -58,3 +58,29 @@ def surface_volume(p, grid, grid_params, resolution=100, splitn=100000):
     z = np.concatenate(z, axis=0).astype(np.float32)
     x, y, zz = g["xyz"]
     return z.reshape(y.shape[0], x.shape[0], zz.shape[0]).transpose([1, 0, 2]), g
+
+
+def aligned_surface_volume(p, grid, recon_pc, resolution=100, splitn=100000):
+    """plots.py:222-261 with higher_res=True, from the surface samples `recon_pc` of the low-resolution mesh on: PCA
+    alignment, aligned grid (materialised), rotation of the grid points back into the scene frame, SDF of every point ->
+    (volume [nx, ny, nz], grid dict, vecs, s_mean, rotated grid points)."""
+    recon_pc = recon_pc.float()
+    s_mean = recon_pc.mean(dim=0)
+    s_cov = recon_pc - s_mean
+    s_cov = torch.mm(s_cov.transpose(0, 1), s_cov)
+    vecs = torch.view_as_real(torch.linalg.eig(s_cov)[1].transpose(0, 1))[:, :, 0]
+    if torch.det(vecs) < 0:
+        vecs = torch.mm(torch.tensor([[1, 0, 0], [0, 0, 1], [0, 1, 0]]).float(), vecs)
+    helper = torch.bmm(vecs.unsqueeze(0).repeat(recon_pc.shape[0], 1, 1), (recon_pc - s_mean).unsqueeze(-1)).squeeze()
+    g = get_grid(helper, resolution, eps=0.01)
+    pts = []
+    for pnts in torch.split(g["grid_points"], splitn, dim=0):
+        pts.append(torch.bmm(vecs.unsqueeze(0).repeat(pnts.shape[0], 1, 1).transpose(1, 2), pnts.unsqueeze(-1)).squeeze() + s_mean)
+    pts = torch.cat(pts, dim=0)
+    z = []
+    with torch.no_grad():
+        for pnts in torch.split(pts, splitn, dim=0):
+            z.append(H.point_sdf(p, grid, pnts).numpy())
+    z = np.concatenate(z, axis=0).astype(np.float32)
+    x, y, zz = g["xyz"]
+    return z.reshape(y.shape[0], x.shape[0], zz.shape[0]).transpose([1, 0, 2]), g, vecs, s_mean, pts

@@ -128,7 +128,7 @@ _SIGS = {
     "spf_grad_sumsq": [_P, _L, _F, _P, _P, _Z, _P],
     "spf_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _D, _D, _F, _I, _P, _P],
     "spf_grid_points_mask": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _F, _P, _P, _P, _P, _I, _P],
-    "spf_grid_points_mask_cyclic": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _F, _P, _P, _P, _P, _I, _P],
+    "spf_grid_points_mask_cyclic": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _P, _F, _P, _P, _P, _P, _I, _P],
     "spf_scatter_f32": [_P, _P, _I, _P, _P],
     "spf_local_loss_fwd": [_P, _P, _P, _P, _I, _I, _P, _P, _L, _L, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P,
                            _P],

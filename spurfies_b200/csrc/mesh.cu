@@ -12,7 +12,7 @@
 //   linear index = (iy * nx + ix) * nz + iz,  point = (x[ix], y[iy], z[iz])
 __global__ void k_grid_points_mask(GridDev g, const float* __restrict__ xs, const float* __restrict__ ys,
                                    const float* __restrict__ zs, int nx, int ny, int nz, long long lo, long long count,
-                                   long long cyc_block, int cyc_world, int cyc_rank,
+                                   long long cyc_block, int cyc_world, int cyc_rank, const float* __restrict__ affine,
                                    float fill, float* __restrict__ vol, int* __restrict__ idx_out,
                                    float* __restrict__ pts_out, int* __restrict__ counter, int cap) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,6 +28,12 @@ __global__ void k_grid_points_mask(GridDev g, const float* __restrict__ xs, cons
     const long long r = i / nz;
     const int ix = (int)(r % nx), iy = (int)(r / nx);
     x = xs[ix]; y = ys[iy]; z = zs[iz];
+    if (affine) {   // PCA-aligned grid of the higher_res pass (plots.py:240-246): p = M (x, y, z) + c, M row-major
+      const float gx = x, gy = y, gz = z;
+      x = affine[0] * gx + affine[1] * gy + affine[2] * gz + affine[9];
+      y = affine[3] * gx + affine[4] * gy + affine[5] * gz + affine[10];
+      z = affine[6] * gx + affine[7] * gy + affine[8] * gz + affine[11];
+    }
     vol[t] = fill;
     int cx, cy, cz;
     const int v = voxel_of(g, x, y, z, cx, cy, cz);
@@ -54,8 +60,8 @@ __global__ void k_scatter_f32(const int* __restrict__ idx, const float* __restri
 
 extern "C" int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx,
                                            int32_t ny, int32_t nz, int64_t lo, int64_t count, int64_t block, int32_t world,
-                                           int32_t rank, float fill, float* vol, int32_t* idx_out, float* pts_out,
-                                           int32_t* counter, int32_t cap, void* stream_) {
+                                           int32_t rank, const float* affine, float fill, float* vol, int32_t* idx_out,
+                                           float* pts_out, int32_t* counter, int32_t cap, void* stream_) {
   if (!g || !xs || !ys || !zs || !vol || !idx_out || !pts_out || !counter) return SPF_ERR_INVALID;
   if (nx <= 0 || ny <= 0 || nz <= 0 || lo < 0 || count < 0 || block < 1 || world < 1 || rank < 0 || rank >= world)
     return SPF_ERR_INVALID;
@@ -69,7 +75,7 @@ extern "C" int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, c
   SPF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st), "grid_points_mask memset");
   if (count == 0) return SPF_OK;
   k_grid_points_mask<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(to_dev(g), xs, ys, zs, nx, ny, nz, lo, count, block, world,
-                                                                     rank, fill, vol, idx_out, pts_out, counter, cap);
+                                                                     rank, affine, fill, vol, idx_out, pts_out, counter, cap);
   SPF_CHECK_LAUNCH("k_grid_points_mask");
   return SPF_OK;
 }
@@ -77,8 +83,8 @@ extern "C" int spf_grid_points_mask_cyclic(const spf_grid* g, const float* xs, c
 extern "C" int spf_grid_points_mask(const spf_grid* g, const float* xs, const float* ys, const float* zs, int32_t nx,
                                     int32_t ny, int32_t nz, int64_t lo, int64_t count, float fill, float* vol,
                                     int32_t* idx_out, float* pts_out, int32_t* counter, int32_t cap, void* stream_) {
-  return spf_grid_points_mask_cyclic(g, xs, ys, zs, nx, ny, nz, lo, count, 1, 1, 0, fill, vol, idx_out, pts_out, counter, cap,
-                                     stream_);
+  return spf_grid_points_mask_cyclic(g, xs, ys, zs, nx, ny, nz, lo, count, 1, 1, 0, nullptr, fill, vol, idx_out, pts_out, counter,
+                                     cap, stream_);
 }
 
 extern "C" int spf_scatter_f32(const int32_t* idx, const float* vals, int32_t n, float* out, void* stream_) {

@@ -1,7 +1,8 @@
 """the mesh-extraction caller of the hot path -- SDF volume on a regular grid, kept on the device.
 
 Mirrors ``spurfies/utils/plots.py``: ``get_grid_uniform`` (:289-300), ``get_grid`` (:302-333) and the SDF-evaluation
-half of ``get_surface_by_grid`` (:188-287, ``higher_res=False``, the only mode ``eval_spurfies.py:151-176`` uses).
+half of ``get_surface_by_grid`` (:188-287; ``higher_res=False`` is the only mode ``eval_spurfies.py:151-176`` uses, the
+PCA-aligned second pass of ``higher_res=True`` takes the low-resolution mesh's surface samples from the caller).
 The reference materialises all grid points, evaluates ``model.get_sdf_eval`` (pointneus_disent.py:249-298) in chunks
 of 100 000 and copies every chunk to the host; here ``sdf_volume`` generates the points on the fly, skips everything
 outside the dilated occupancy of the neural points (those values are the constant 1000) and leaves the volume in HBM.
@@ -73,14 +74,18 @@ def cyclic_global_index(local: torch.Tensor, rank: int, world: int, block: int) 
 
 @torch.no_grad()
 def sdf_volume(model, xyz: Sequence[np.ndarray], chunk: int = 1 << 24, rank: int = 0, world: int = 1,
-               out: Optional[torch.Tensor] = None, cyclic_block: Optional[int] = None) -> Tuple[torch.Tensor, Tuple[int, int]]:
+               out: Optional[torch.Tensor] = None, cyclic_block: Optional[int] = None,
+               affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, Tuple[int, int]]:
     """SDF of ``model.get_sdf_eval`` at the grid points of axes ``xyz`` in the reference's order (index =
     (iy * nx + ix) * nz + iz).  Returns (flat fp32 device tensor over this rank's contiguous index range, (lo, hi)).
     Reshape the full volume as ``[ny, nx, nz]`` (plots.py:259-261 then transposes it to [nx, ny, nz]).
 
     ``cyclic_block`` (multi-GPU): instead of a contiguous slab the rank owns every world-th block of that many grid points
     (``cyclic_global_index`` maps its consecutive local indices to grid indices) -- a contiguous slab that crosses the
-    object costs several times one that does not; the returned range is then (0, number of local points)."""
+    object costs several times one that does not; the returned range is then (0, number of local points).
+
+    ``affine = (M [3,3], c [3])``: the query points are ``M @ (x, y, z) + c`` (the PCA-aligned grid of
+    ``get_surface_by_grid(higher_res=True)``, plots.py:240-246, generated on the fly like the axis-aligned one)."""
     set_precision(model.precision)
     dev = model.neural_pts.device
     ax = [torch.as_tensor(np.asarray(a, dtype=np.float64)).to(torch.float32).to(dev).contiguous() for a in xyz]
@@ -102,11 +107,14 @@ def sdf_volume(model, xyz: Sequence[np.ndarray], chunk: int = 1 << 24, rank: int
     pts = torch.empty(chunk, 3, dtype=torch.float32, device=dev)
     counter = torch.zeros(1, dtype=torch.int32, device=dev)
     r2 = grid.radius2(model.conf.r)
+    aff = None
+    if affine is not None:
+        aff = torch.cat([affine[0].reshape(9), affine[1].reshape(3)]).to(device=dev, dtype=torch.float32).contiguous()
     for c0 in range(lo, hi, chunk):
         n = min(chunk, hi - c0)
         vol = out[c0 - lo:c0 - lo + n]
         call("spf_grid_points_mask_cyclic", C.byref(grid.handle), ptr(ax[0]), ptr(ax[1]), ptr(ax[2]), nx, ny, nz, c0, n,
-             cyc[0], cyc[1], cyc[2], NO_NEIGHBOUR, ptr(vol), ptr(idx), ptr(pts), ptr(counter), chunk, stream())
+             cyc[0], cyc[1], cyc[2], ptr(aff), NO_NEIGHBOUR, ptr(vol), ptr(idx), ptr(pts), ptr(counter), chunk, stream())
         m = int(counter.item())            # one 4-byte readback per chunk (the reference copies the whole chunk)
         if m == 0:
             continue
@@ -120,18 +128,51 @@ def sdf_volume(model, xyz: Sequence[np.ndarray], chunk: int = 1 << 24, rank: int
     return out, (lo, hi)
 
 
+def pca_alignment(recon_pc: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """plots.py:222-231: principal axes `vecs` (rows) and mean of the point cloud sampled from the low-resolution mesh."""
+    s_mean = recon_pc.mean(dim=0)
+    d = recon_pc - s_mean
+    s_cov = torch.mm(d.transpose(0, 1), d)
+    # (3x3: decomposed on the host -- LAPACK's ordering / signs, not a device library's that may differ between versions)
+    vecs = torch.view_as_real(torch.linalg.eig(s_cov.cpu())[1].transpose(0, 1))[:, :, 0].to(recon_pc.device)
+    if torch.det(vecs) < 0:
+        vecs = torch.mm(torch.tensor([[1, 0, 0], [0, 0, 1], [0, 1, 0]], device=vecs.device, dtype=vecs.dtype), vecs)
+    return vecs, s_mean
+
+
 def get_surface_by_grid(grid_params, model, resolution: int = 100, level: float = 0.0, higher_res: bool = False,
-                        chunk: int = 1 << 24) -> Dict:
+                        chunk: int = 1 << 24, recon_pc: Optional[torch.Tensor] = None) -> Dict:
     """plots.py:188-287 up to the marching-cubes call: returns the device SDF volume in the layout the reference hands to
-    ``measure.marching_cubes`` ([nx, ny, nz]), the grid spacing and origin, and whether the level set crosses it."""
+    ``measure.marching_cubes`` ([nx, ny, nz]), the grid spacing and origin, and whether the level set crosses it.
+
+    ``higher_res=True`` (plots.py:196-246): the second, PCA-aligned pass.  Its first half -- marching cubes of a 100^3
+    volume (``get_surface_by_grid(..., resolution=100)`` gives that volume), largest component, 10 000 surface samples --
+    is skimage / trimesh work outside the path; hand its samples in as ``recon_pc`` [P,3].  This function then does the
+    alignment (``pca_alignment``), builds the aligned grid and queries the SDF at the ROTATED grid points
+    ``vecs^T p + mean`` (generated on the fly, ``sdf_volume(affine=)``); the result also carries ``vecs`` / ``mean`` and
+    the first grid point that plots.py:270-275 uses to map the vertices back."""
     if higher_res:
-        raise NotImplementedError("higher_res=True (PCA-aligned second pass) is not used by eval_spurfies.py")
-    gp = np.asarray(grid_params, dtype=np.float64) * np.array([[1.5], [1.0]])   # plots.py:189
-    grid = get_grid(None, resolution, input_min=gp[0], input_max=gp[1], eps=0.0)
-    x, y, z = grid["xyz"]
-    flat, _ = sdf_volume(model, grid["xyz"], chunk=chunk)
+        if recon_pc is None:
+            raise ValueError("higher_res=True needs recon_pc: the points sampled from the low-resolution mesh "
+                             "(plots.py:198-220; marching cubes and mesh sampling are outside this package)")
+        dev = model.neural_pts.device
+        vecs, s_mean = pca_alignment(recon_pc.to(dev).float())
+        helper = torch.mm(recon_pc.to(dev).float() - s_mean, vecs.transpose(0, 1))          # plots.py:231-232
+        grid = get_grid(helper.cpu(), resolution, eps=0.01)
+        x, y, z = grid["xyz"]
+        M = vecs.transpose(0, 1).contiguous()                                                 # plots.py:243-245
+        flat, _ = sdf_volume(model, grid["xyz"], chunk=chunk, affine=(M, s_mean))
+        first = torch.mv(M, torch.tensor([x[0], y[0], z[0]], dtype=torch.float32, device=dev)) + s_mean
+    else:
+        gp = np.asarray(grid_params, dtype=np.float64) * np.array([[1.5], [1.0]])   # plots.py:189
+        grid = get_grid(None, resolution, input_min=gp[0], input_max=gp[1], eps=0.0)
+        x, y, z = grid["xyz"]
+        flat, _ = sdf_volume(model, grid["xyz"], chunk=chunk)
     vol = flat.view(len(y), len(x), len(z)).permute(1, 0, 2)
     lo, hi = torch.aminmax(vol)
     spacing = float(x[2] - x[1])
-    return {"volume": vol, "spacing": (spacing, spacing, spacing), "origin": (float(x[0]), float(y[0]), float(z[0])),
-            "has_surface": not (float(lo) > level or float(hi) < level), "xyz": grid["xyz"]}
+    out = {"volume": vol, "spacing": (spacing, spacing, spacing), "origin": (float(x[0]), float(y[0]), float(z[0])),
+           "has_surface": not (float(lo) > level or float(hi) < level), "xyz": grid["xyz"]}
+    if higher_res:
+        out.update(vecs=vecs, mean=s_mean, first_grid_point=first)
+    return out

@@ -125,3 +125,32 @@ def test_block_cyclic_volume_and_interleaved_render_equal_the_whole(setup):
         assert torch.equal(out["rgb_values"], ref["rgb_values"]) and torch.equal(out["weights"], ref["weights"])
         covered[idx] = True
     assert bool(covered.all())
+
+
+def test_pca_aligned_second_pass_matches_reference_restatement(setup):
+    """get_surface_by_grid(higher_res=True, recon_pc=...) (plots.py:222-261): same principal axes and aligned grid as the
+    oracle restatement, and the SDF at the ROTATED grid points (generated on the fly by the kernel) equals the oracle's on
+    the materialised, rotated points -- except where a rotated point sits within fp32 rounding of an occupancy boundary."""
+    from spurfies_b200 import mesh
+    g, P, model = setup
+    gen = torch.Generator().manual_seed(4)
+    # stand-in for the 10 000 samples of the low-resolution mesh: points of the cloud with small noise, stretched so that
+    # the principal axes are well separated
+    pick = g["scene"]["pts"][torch.randperm(g["scene"]["pts"].shape[0], generator=gen)[:3000]]
+    recon = pick * torch.tensor([1.0, 0.8, 0.6]) + 0.002 * torch.randn(3000, 3, generator=gen)
+    want, og, vecs, s_mean, pts = OM.aligned_surface_volume(P, P.make_grid(), recon, resolution=24, splitn=7000)
+    got = mesh.get_surface_by_grid(None, model, resolution=24, higher_res=True, chunk=5000, recon_pc=recon.cuda())
+    assert float((got["vecs"].cpu() - vecs).abs().max()) < 1e-4 and float((got["mean"].cpu() - s_mean).abs().max()) < 1e-6
+    for a, b in zip(got["xyz"], og["xyz"]):
+        assert a.shape == b.shape and float(np.abs(a - b).max()) < 1e-5
+    assert float((got["first_grid_point"].cpu() - pts[0]).abs().max()) < 1e-5
+    vol = got["volume"].cpu().numpy()
+    assert vol.shape == want.shape
+    same_mask = (vol == 1000.0) == (want == 1000.0)
+    assert same_mask.mean() > 0.999, same_mask.mean()
+    hit = (want != 1000.0) & (vol != 1000.0)
+    assert hit.sum() > 100
+    # the grid points differ by fp32 rounding of the rotation (<= 1e-6), the SDF by its gradient times that
+    assert rel_err(torch.from_numpy(vol[hit]), torch.from_numpy(want[hit])) < 1e-3
+    with pytest.raises(ValueError):
+        mesh.get_surface_by_grid(GRID_PARAMS, model, resolution=8, higher_res=True)
