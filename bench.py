@@ -44,16 +44,16 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel come from the ncu --set full capture of
 # THIS command, summarised by tools/summarise_ncu_full.py into profiles/ncu_traffic.json ({"file": ..., "kernels":
 # {name: {"dram_bytes": ...}}}); absent file -> traffic is null (never a constant in this source).
-def measured_traffic(kernel_regex):
+def measured_traffic(kernel_regex, workload="train"):
     import re
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json" if workload == "train" else "ncu_traffic_%s.json" % workload)
     if not os.path.exists(p):
         return None, None
     d = json.load(open(p))
     for name, v in d.get("kernels", {}).items():
         if re.search(kernel_regex, name):
-            return v.get("dram_bytes"), "profiles/ncu_traffic.json (%s of the ncu --set full capture %s, table in profiles/%s)" % (
-                name, d.get("file", "?"), d.get("file", "?").replace("_top.ncu-rep", "_ncu_full.md"))
+            return v.get("dram_bytes"), "profiles/%s (%s of the ncu --set full capture %s, table in profiles/%s)" % (
+                os.path.basename(p), name, d.get("file", "?"), d.get("file", "?").replace("_top.ncu-rep", "_ncu_full.md").replace(".ncu-rep", "_ncu_full.md"))
     return None, None
 
 # kernels launched per C-ABI call (for gpu_launches)
@@ -729,11 +729,13 @@ def run_inference(args):
             a = geo_flops / (kms[dom] * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": dom + " (all launches of one pass on rank 0: coarse / sampler / fine)",
                                 "achieved": a, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                "frac": a / pk["bf16_tflops_sustained"], "traffic": None, "ms_per_step": kms[dom],
+                                "frac": a / pk["bf16_tflops_sustained"],
+                                "traffic": measured_traffic(r"k_sdf_tc2", args.workload)[0],
+                                "traffic_source": measured_traffic(r"k_sdf_tc2", args.workload)[1], "ms_per_step": kms[dom],
                                 "pair_rows_per_step": pair_rows, "peak_source": pk["source"] + " bf16 sustained",
                                 "note": "EXECUTED FLOPs (411 648 per pair row forward, x2 with the d sdf / d input chain) over "
-                                        "every pair row of the pass / summed launch time; no ncu capture of this workload -> "
-                                        "traffic null"}
+                                        "every pair row of the pass / summed launch time; traffic = DRAM bytes of the "
+                                        "LONGEST k_sdf_tc2 launch of this workload's ncu capture (one launch, not the pass)"}
         other = {}
 
         def add(name, nbytes, note):
