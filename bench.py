@@ -725,13 +725,16 @@ def run_inference(args):
         kms = line["kernels_ms_per_step"]
         per_rank = 1.0 / world     # this rank's share of the units (every rank runs the same kernels on its slice)
         dom = "spf_sdf_fwd_tc" if args.precision == "bf16" else "spf_sdf_fwd_f32"
+        # the workload's longest geometry launch: the fine pass (with the Jacobian chain) of an eval chunk, the forward-only
+        # pass of a grid chunk
+        _rx = r"k_sdf_tc2<\(bool\)1>|k_sdf_tc2<true>|k_sdf_tc2<1>" if args.workload == "eval" else r"k_sdf_tc2<\(bool\)0>|k_sdf_tc2<false>|k_sdf_tc2<0>"
         if dom in kms and geo_flops > 0:
             a = geo_flops / (kms[dom] * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": dom + " (all launches of one pass on rank 0: coarse / sampler / fine)",
                                 "achieved": a, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": a / pk["bf16_tflops_sustained"],
-                                "traffic": measured_traffic(r"k_sdf_tc2", args.workload)[0],
-                                "traffic_source": measured_traffic(r"k_sdf_tc2", args.workload)[1], "ms_per_step": kms[dom],
+                                "traffic": measured_traffic(_rx, args.workload)[0],
+                                "traffic_source": measured_traffic(_rx, args.workload)[1], "ms_per_step": kms[dom],
                                 "pair_rows_per_step": pair_rows, "peak_source": pk["source"] + " bf16 sustained",
                                 "note": "EXECUTED FLOPs (411 648 per pair row forward, x2 with the d sdf / d input chain) over "
                                         "every pair row of the pass / summed launch time; traffic = DRAM bytes of the "
