@@ -630,15 +630,17 @@ def run_inference(args):
         inputs = [{"uv": uv_host.to(device), "pose": c["pose"].to(device), "intrinsics": c["intrinsics"].to(device),
                    "local_data": None} for c in cams]
 
-        def one(i, from_host=False):
+        def one(i, from_host=False, graph=None):
+            graph = args.cuda_graph if graph is None else graph
             inp = inputs[i % 3]
             if from_host:
                 inp = dict(inp, uv=uv_host.to(device, non_blocking=True))
             if world > 1:   # two-row blocks dealt round-robin: contiguous slices leave the background ranks idle
                 out, _ = E.render_image_interleaved(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world,
-                                                    block=1024)
+                                                    block=1024, graph=graph)
             else:
-                out, (lo, hi) = E.render_image(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world)
+                out, (lo, hi) = E.render_image(model, inp, total, n_pixels=args.eval_chunk, rank=rank, world=world,
+                                               graph=graph)
             return out
 
         units, unit, metric = total, "rays/s", "eval rays/s (full-image render, inference)"
@@ -653,7 +655,7 @@ def run_inference(args):
         n_local = mesh.cyclic_local_count(total, rank, world, cyc) if cyc else shard_range(total, rank, world)[1] - shard_range(total, rank, world)[0]
         vol = torch.empty(n_local, dtype=torch.float32, device=device)
 
-        def one(i, from_host=False):
+        def one(i, from_host=False, graph=None):
             mesh.sdf_volume(model, grid["xyz"], chunk=args.mesh_chunk, rank=rank, world=world, out=vol, cyclic_block=cyc)
             return {"volume": vol}
 
@@ -673,7 +675,6 @@ def run_inference(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    _lib.profile_reset(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -682,10 +683,16 @@ def run_inference(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # per-kernel times and the launch count: one eager pass with events around every C-ABI call (a graph replay cannot
+    # be instrumented; the timed passes above run without the instrumentation)
+    _lib.profile_reset(True)
+    for i in range(args.steps):
+        one(i, graph=False)
+    barrier()
     prof = _lib.profile_collect()
     _lib.profile_reset(False)
     with PairCounter() as pc:      # one untimed pass: pair rows / executed FLOPs of the geometry-field launches of a pass
-        one(0)
+        one(0, graph=False)
     torch.cuda.synchronize()
     pair_rows, geo_flops = pc.totals()
     # end to end: inputs from pinned host memory, the step's result copied back to pinned host memory
@@ -714,7 +721,10 @@ def run_inference(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": desc, "parallelism": "sharded dp%d, no collective" % world,
+                           "cuda_graph": bool(args.cuda_graph and args.workload == "eval"),
                            "l2": "working set per pass (kNN lists, activations) >> 126 MB L2"},
+                "kernel_timing": "CUDA events around each C-ABI call in a separate eager pass (the timed passes run "
+                                 "uninstrumented; eval chunks replay a CUDA graph unless --no-cuda-graph)",
                 "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit,
                         "h2d_bytes_per_step": int(uv_host.numel() * 4) if args.workload == "eval" else 0,
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_out.values())),
@@ -742,8 +752,9 @@ def run_inference(args):
         other = {}
 
         def add(name, nbytes, note):
-            if name not in kms and name + "_pred" in kms:   # the predicated entry point of the same kernel
-                name = name + "_pred"
+            for suffix in ("_pred", "_cyclic"):   # the predicated / block-cyclic entry point of the same kernel
+                if name not in kms and name + suffix in kms:
+                    name = name + suffix
             if name in kms and kms[name] > 0:
                 g = nbytes / (kms[name] * 1e-3) / 1e9
                 other[name] = {"achieved": g, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": g / pk["hbm_gbs"],

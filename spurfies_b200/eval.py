@@ -52,18 +52,70 @@ def merge_output(res: List[Dict], total_pixels: int, batch_size: int) -> Dict:
     return out
 
 
+class ChunkGraph:
+    """One full-size pixel chunk of the eval render as a CUDA graph: the eval forward has no host round trip (the
+    sampler's loop is predicated on the device), so its ~100 launches replay from one graph launch and the host cannot fall
+    behind the device between chunks.  Inputs are copied into static buffers before each replay; outputs are the graph's
+    static tensors (clone what must outlive the next replay)."""
+
+    def __init__(self, model, sample: Dict, fast: int, keys):
+        self.model, self.keys, self.fast = model, tuple(keys), fast
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in sample.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside the capture: lazy constants, arena buffers
+            model(self.static, fast=fast, aux_losses=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = model(self.static, fast=fast, aux_losses=False)
+            self.out = {k: out[k].detach() for k in self.keys}
+        torch.cuda.synchronize()
+
+    def __call__(self, chunk: Dict) -> Dict:
+        for k, v in chunk.items():
+            if torch.is_tensor(v):
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+def _chunk_graph(model, sample: Dict, fast: int, keys) -> Optional["ChunkGraph"]:
+    """Cached per (model, chunk size, schedule, point set); None if this forward cannot be captured (kept eager)."""
+    cache = model.__dict__.setdefault("_eval_graphs", {})
+    key = (int(sample["uv"].shape[1]), int(fast), tuple(keys), model.neural_pts.data_ptr(), model.neural_pts._version,
+           model.precision)
+    if key not in cache:
+        try:
+            cache[key] = ChunkGraph(model, sample, fast, keys)
+        except Exception as e:  # noqa: BLE001 -- report once, stay eager
+            import warnings
+            warnings.warn(f"spurfies_b200.eval: CUDA-graph capture of the eval chunk failed, rendering eagerly ({type(e).__name__}: {e})")
+            torch.cuda.synchronize()
+            cache[key] = None
+    return cache[key]
+
+
 @torch.no_grad()
 def render_image(model, model_input: Dict, total_pixels: int, n_pixels: int = 16384, rank: int = 0, world: int = 1,
-                 fast: int = -1, keys=RENDER_KEYS) -> Tuple[Dict, Tuple[int, int]]:
-    """Eval-mode render of this rank's pixel slice.  Returns (merged outputs over the slice, (lo, hi))."""
+                 fast: int = -1, keys=RENDER_KEYS, graph: bool = False) -> Tuple[Dict, Tuple[int, int]]:
+    """Eval-mode render of this rank's pixel slice.  Returns (merged outputs over the slice, (lo, hi)).
+    ``graph=True``: full-size chunks replay a captured CUDA graph (``ChunkGraph``; same kernels, same results); the
+    parameters must not change between renders that share a graph (it reads them in place, like the training graph)."""
     was_training = model.training
     model.eval()
     try:
         lo, hi = shard_range(total_pixels, rank, world)
         res = []
         for s in split_input(model_input, total_pixels, n_pixels, lo, hi):
-            out = model(s, fast=fast, aux_losses=False)
-            res.append({k: out[k].detach() for k in keys})
+            g = _chunk_graph(model, s, fast, keys) if (graph and s["uv"].shape[1] == n_pixels and s["uv"].is_cuda) else None
+            if g is not None:
+                out = g(s)
+                res.append({k: out[k].clone() for k in keys})
+            else:
+                out = model(s, fast=fast, aux_losses=False)
+                res.append({k: out[k].detach() for k in keys})
         return merge_output(res, hi - lo, 1), (lo, hi)
     finally:
         model.train(was_training)
@@ -82,7 +134,7 @@ def interleaved_pixels(total_pixels: int, rank: int, world: int, block: int = 10
 
 @torch.no_grad()
 def render_image_interleaved(model, model_input: Dict, total_pixels: int, n_pixels: int = 16384, rank: int = 0, world: int = 1,
-                             block: int = 1024, fast: int = -1, keys=RENDER_KEYS) -> Tuple[Dict, torch.Tensor]:
+                             block: int = 1024, fast: int = -1, keys=RENDER_KEYS, graph: bool = False) -> Tuple[Dict, torch.Tensor]:
     """Eval-mode render of this rank's interleaved pixel set (``interleaved_pixels``), in chunks of `n_pixels`.  Returns
     (outputs over the set, the pixel indices they belong to); ``out[k]`` of all ranks scattered to ``idx`` is the image.
     No collective.  (The eval sampler's iteration count is a property of the chunk, ray_sampler.py:466-468, so -- as
@@ -96,5 +148,5 @@ def render_image_interleaved(model, model_input: Dict, total_pixels: int, n_pixe
     for key in ("object_mask", "rgb"):
         if key in sub:
             sub[key] = model_input[key][:, sel]
-    out, _ = render_image(model, sub, int(idx.numel()), n_pixels=n_pixels, fast=fast, keys=keys)
+    out, _ = render_image(model, sub, int(idx.numel()), n_pixels=n_pixels, fast=fast, keys=keys, graph=graph)
     return out, idx

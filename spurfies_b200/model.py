@@ -169,7 +169,11 @@ class ErrorBoundSampler_pn:
                 u = (rng["u"] if rng is not None else torch.rand(R, self.N_samples)).to(dev, non_blocking=True).contiguous()
                 sidx = rng["sampling_idx"] if rng is not None else torch.randperm(M)[:n_extra]
             else:
-                sidx = torch.linspace(0, M - 1, n_extra).long()
+                # ray_sampler.py:552-553; cached on the device per M: no H2D copy per draw (CUDA-graph capturable)
+                key = ("sidx", M, n_extra)
+                if key not in cst:
+                    cst[key] = torch.linspace(0, M - 1, n_extra).long().to(dev, dtype=torch.int32).contiguous()
+                sidx = cst[key]
             sidx = sidx.to(dev, dtype=torch.int32).contiguous()
             if z_out is None:
                 z_out = torch.empty(R, cols, dtype=torch.float32, device=dev)
