@@ -84,8 +84,11 @@ class ChunkGraph:
 def _chunk_graph(model, sample: Dict, fast: int, keys) -> Optional["ChunkGraph"]:
     """Cached per (model, chunk size, schedule, point set); None if this forward cannot be captured (kept eager)."""
     cache = model.__dict__.setdefault("_eval_graphs", {})
+    # parameters are read in place by the captured kernels (the trainable ones are re-packed inside the graph); what the
+    # HOST caches by version -- the voxel grid of the point set, the packed frozen geometry MLP -- is part of the key
+    frozen = tuple((p.data_ptr(), p._version) for p in list(model.F_geometry.parameters()) + list(model.T.parameters()))
     key = (int(sample["uv"].shape[1]), int(fast), tuple(keys), model.neural_pts.data_ptr(), model.neural_pts._version,
-           model.precision)
+           model.precision, frozen)
     if key not in cache:
         try:
             cache[key] = ChunkGraph(model, sample, fast, keys)

@@ -285,7 +285,8 @@ def grad_scale(upstream: torch.Tensor, target: float = 16.0) -> torch.Tensor:
     """Device tensor [S, 1/S] for the tensor-core mode's fp16 gradient chain: S = the power of two that brings the largest
     upstream gradient entry just below `target` (2^12 of fp16 headroom above for growth through the layers, 2^28 of range
     below), computed on the device by one launch (spf_grad_scale: no host sync, CUDA-graph capturable).  Powers of two
-    make scaling / unscaling exact."""
+    make scaling / unscaling exact.  (The kernel's two scratch words are per device: calls must be stream-ordered with
+    respect to each other, as the step's two calls are.)"""
     x = upstream.detach()
     if x.dtype != torch.float32 or not x.is_contiguous():
         x = x.float().contiguous()
