@@ -90,6 +90,8 @@ def _chunk_graph(model, sample: Dict, fast: int, keys) -> Optional["ChunkGraph"]
     key = (int(sample["uv"].shape[1]), int(fast), tuple(keys), model.neural_pts.data_ptr(), model.neural_pts._version,
            model.precision, frozen)
     if key not in cache:
+        while len(cache) >= 4:            # a render needs two (full chunks + the ragged tail); bound what stays captured
+            cache.pop(next(iter(cache)))
         try:
             cache[key] = ChunkGraph(model, sample, fast, keys)
         except Exception as e:  # noqa: BLE001 -- report once, stay eager
@@ -104,7 +106,7 @@ def _chunk_graph(model, sample: Dict, fast: int, keys) -> Optional["ChunkGraph"]
 def render_image(model, model_input: Dict, total_pixels: int, n_pixels: int = 16384, rank: int = 0, world: int = 1,
                  fast: int = -1, keys=RENDER_KEYS, graph: bool = False) -> Tuple[Dict, Tuple[int, int]]:
     """Eval-mode render of this rank's pixel slice.  Returns (merged outputs over the slice, (lo, hi)).
-    ``graph=True``: full-size chunks replay a captured CUDA graph (``ChunkGraph``; same kernels, same results); the
+    ``graph=True``: chunks replay a captured CUDA graph per chunk size (``ChunkGraph``; same kernels, same results); the
     parameters must not change between renders that share a graph (it reads them in place, like the training graph)."""
     was_training = model.training
     model.eval()
@@ -112,7 +114,7 @@ def render_image(model, model_input: Dict, total_pixels: int, n_pixels: int = 16
         lo, hi = shard_range(total_pixels, rank, world)
         res = []
         for s in split_input(model_input, total_pixels, n_pixels, lo, hi):
-            g = _chunk_graph(model, s, fast, keys) if (graph and s["uv"].shape[1] == n_pixels and s["uv"].is_cuda) else None
+            g = _chunk_graph(model, s, fast, keys) if (graph and s["uv"].is_cuda) else None   # one graph per chunk size
             if g is not None:
                 out = g(s)
                 res.append({k: out[k].clone() for k in keys})
