@@ -632,6 +632,7 @@ extern "C" int spf_knn_points_pred(const spf_grid* g, const float* q, int64_t Q,
   }
   const int wpb = 8;
   // enough warps to fill the machine several times over (148 SMs x 64 resident warps), at most 32 points per warp
+  // (measured on the step's coarse pass, 0.5 M points: x2 -> 0.184 ms, x8 -> 0.150 ms, x32 / x128 -> 0.195 ms)
   int ppw = 32;
   const long long want_warps = (long long)spf_num_sms() * 64 * 8;
   while (ppw > 1 && (Q + ppw - 1) / ppw < want_warps) ppw >>= 1;
