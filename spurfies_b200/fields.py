@@ -323,6 +323,24 @@ def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None, gsca
     return out
 
 
+# Side stream for the colour field's weight-gradient launch (armed by train.TrainStep for the duration of one backward,
+# joined by it before the gradient exchange / optimiser).
+WGRAD_SIDE = {"armed": False, "stream": None, "pending": False}
+
+
+def wgrad_side_arm(on: bool) -> None:
+    if on and WGRAD_SIDE["stream"] is None:
+        WGRAD_SIDE["stream"] = torch.cuda.Stream()
+    WGRAD_SIDE["armed"] = bool(on)
+
+
+def wgrad_side_join() -> None:
+    """The current stream waits for the side-stream weight-gradient launch of this backward (no host sync)."""
+    if WGRAD_SIDE["pending"]:
+        torch.cuda.current_stream().wait_stream(WGRAD_SIDE["stream"])
+        WGRAD_SIDE["pending"] = False
+
+
 # callbacks fired inside the backward as soon as a parameter's gradient is final (set by train.TrainStep for the
 # duration of one backward; None = nobody listens)
 GRAD_READY_HOOKS = {"color_latent": None}
@@ -400,12 +418,29 @@ class ColorField(torch.autograd.Function):
                  ptr(d_hbar.contiguous()), ptr(h1), ptr(h2), ptr(m3), ptr(wn), ptr(dz1), ptr(dz2), ptr(dz3), ptr(gfeat),
                  stream())
         if tcm:  # hand-written split-K tcgen05 wgrad, row count read on the device
-            pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
             tw = ctx.direct_w   # W1's gradient needs its columns permuted back: through the pool; the rest may go direct
-            (dW3, db3), (dW2, db2), (dW1p, db1) = _wgrad_multi(
-                [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool,
-                targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])], gscale=gscale)
-            dW1 = torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1)
+
+            def wgrad():
+                pool = _ZeroPool(2 * 256 * 256 + 256 * 112 + 3 * 256, dev)
+                (dW3, db3), (dW2, db2), (dW1p, db1) = _wgrad_multi(
+                    [(dz3, h2, 256, 256, True), (dz2, h1, 256, 256, True), (dz1, in0, 128, 112, True)], slots, slots.K, pool,
+                    targets=[(tw[4], tw[5]), (tw[2], tw[3]), (None, tw[1])], gscale=gscale)
+                return torch.cat([dW1p[:, 64:103], dW1p[:, :64]], dim=1), db1, dW2, db2, dW3, db3
+
+            side = WGRAD_SIDE["stream"] if (WGRAD_SIDE["armed"] and all(t is not None for t in tw)) else None
+            if side is None:
+                dW1, db1, dW2, db2, dW3, db3 = wgrad()
+            else:
+                # every gradient of this launch lands in the trainer's flat buffer, so nothing downstream of this node
+                # reads it before the optimiser: run it on a side stream, under the geometry backward / regulariser /
+                # pseudo-point backward that follow on this one (small latency-bound kernels that fit next to the
+                # HBM-bound split-K kernel); train.TrainStep joins the stream before it touches the gradients
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    dW1, db1, dW2, db2, dW3, db3 = wgrad()
+                    tw[0].add_(dW1)
+                    dW1 = None
+                WGRAD_SIDE["pending"] = True
         else:    # exact mode: fp32 FFMA split-K kernel over the compact pair rows (device-side row count, no library GEMM)
             dW3, db3 = _wgrad_f32(dz3, h2, 256, slots, slots.K)
             dW2, db2 = _wgrad_f32(dz2, h1, 256, slots, slots.K)

@@ -103,6 +103,9 @@ class TrainStep:
             assert all(a is b for a, b in zip(lat, self.params)), "the latent tables must be the first parameters"
             n_half = sum((p.numel() + 3) // 4 * 4 for p in lat)
         self._reducer = FlatGradReducer(self.params, world_size, align=4, bf16_prefix=n_half)
+        # the colour field's split-K weight-gradient launch runs on a side stream under the rest of the backward
+        # (fields.WGRAD_SIDE); SPF_WGRAD_SIDE=0 keeps it in line
+        self.wgrad_side = os.environ.get("SPF_WGRAD_SIDE", "1") != "0"
         self._early_n, self._early_work = 0, None
         if world_size > 1 and dp_overlap and grad_compress is None and self.params[0] is model.neural_feats_color:
             self._early_n = self._reducer.offsets[1] if len(self.params) > 1 else self._reducer.numel
@@ -266,10 +269,14 @@ class TrainStep:
         hook = self._early_n > 0 and not self._diag_skip_reduce and self._reducer.attached()
         if hook:
             fields.GRAD_READY_HOOKS["color_latent"] = self._early_reduce
+        side = self.wgrad_side and self._reducer.attached() and self.model.precision == "bf16"
+        fields.wgrad_side_arm(side)
         try:
             losses["loss"].backward()
         finally:
             fields.GRAD_READY_HOOKS["color_latent"] = None
+            fields.wgrad_side_arm(False)
+        fields.wgrad_side_join()          # the colour field's weight gradients (side stream) are in the flat buffer
         self._allreduce_grads()           # N > 1: one NCCL all-reduce (sum) of the flat buffer, no packing
         # clip_grad_norm_(1.0) (train.py:360-361), the NaN / Inf guard (train.py:548-564: a non-finite global norm skips
         # the whole update, exactly like the reference's dropped gradients), Adam and zero_grad: two kernels, no host sync.
