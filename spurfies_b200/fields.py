@@ -325,7 +325,7 @@ def _wgrad_multi(jobs, slots, rows_per_unit, pool: _ZeroPool, targets=None, gsca
 
 # Side stream for the colour field's weight-gradient launch (armed by train.TrainStep for the duration of one backward,
 # joined by it before the gradient exchange / optimiser).
-WGRAD_SIDE = {"armed": False, "stream": None, "pending": False}
+WGRAD_SIDE = {"armed": False, "stream": None, "pending": False, "keep": []}
 
 
 def wgrad_side_arm(on: bool) -> None:
@@ -339,6 +339,8 @@ def wgrad_side_join() -> None:
     if WGRAD_SIDE["pending"]:
         torch.cuda.current_stream().wait_stream(WGRAD_SIDE["stream"])
         WGRAD_SIDE["pending"] = False
+    # only now may the caching allocator hand the launch's main-stream inputs to somebody else (see ColorField.backward)
+    WGRAD_SIDE["keep"].clear()
 
 
 # callbacks fired inside the backward as soon as a parameter's gradient is final (set by train.TrainStep for the
@@ -435,6 +437,10 @@ class ColorField(torch.autograd.Function):
                 # reads it before the optimiser: run it on a side stream, under the geometry backward / regulariser /
                 # pseudo-point backward that follow on this one (small latency-bound kernels that fit next to the
                 # HBM-bound split-K kernel); train.TrainStep joins the stream before it touches the gradients
+                # Its inputs were allocated on THIS stream: a block freed when this node returns (the [S, 1/S] pair, the
+                # slot set) could be re-issued to a later main-stream kernel while the side launch still reads it, so
+                # they stay referenced until the join.
+                WGRAD_SIDE["keep"].append((gscale, slots, dz1, dz2, dz3, h1, h2, in0))
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     dW1, db1, dW2, db2, dW3, db3 = wgrad()
