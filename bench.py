@@ -500,17 +500,21 @@ def knn_candidate_stats(model):
     return out
 
 
-def cpu_baseline(sample_rays=1024, repeats=3, threads=None, budget_s=None):
-    """The reference's CPU path (BASELINE configs[0]): the pure-torch oracle port with brute-force
-    cdist kNN on the DTU-shaped 100 k-point scene, 1024 rays x (64 + 34) samples, full fwd + bwd of the same loss --
-    INCLUDING the per-step tv_regul self-kNN over all N points that the reference recomputes every step
-    (utils.py:221-281) -- on all host threads.  Run UNSCALED: value = sample_rays / median step time; nothing is
-    extrapolated.  `budget_s` stops repeating once that much wall time has been spent (at least one timed step)."""
+def cpu_baseline(sample_rays=1024, repeats=3, threads=None, budget_s=None, also_brute=False):
+    """The reference's CPU path (BASELINE configs[0]): the oracle port on the DTU-shaped
+    100 k-point scene, 1024 rays x (64 + 34) samples, full fwd + bwd of the same loss -- INCLUDING the per-step tv_regul
+    self-kNN over all N points that the reference recomputes every step (utils.py:221-281) -- on all host threads.
+    The kNN is the C restatement of the reference's OWN algorithm (voxel-grid kernels, knnquery.cu:22-308; one thread, as
+    one CUDA thread per query there), which on a CPU is ~5x faster per step than the brute-force cdist+topk of the
+    reference's test oracle (test_queries.py:22-74) that BASELINE.md section 2 planned and earlier rounds timed: the
+    faster one is the baseline; `also_brute` times one brute-force step next to it.  Run UNSCALED: value = sample_rays /
+    median step time; nothing is extrapolated.  `budget_s` stops repeating once that much wall time has been spent (at
+    least one timed step)."""
     from oracle import hotpath as H
+    from oracle import knn as K
     from spurfies_b200 import scenes
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    H.KNN_BACKEND = "cdist"
     sc = scenes.dtu_like(N_POINTS, seed=24)
     P = H.init_params(sc["pts"], sc["colors"], seed=0)
     P.neural_feats_geometry *= 8.0
@@ -519,9 +523,22 @@ def cpu_baseline(sample_rays=1024, repeats=3, threads=None, budget_s=None):
         t.requires_grad_()
     grid = P.make_grid()
     cam = scenes.camera(0, sc["cam_radius"], RES)
+    knn_s = [0.0]
+    saved = {}
+    for name in ("query_dense", "query_dense_cdist", "mask"):   # the share of a step spent in the kNN
+        saved[name] = getattr(K.OracleGrid, name)
+
+        def timed(self, *a, _f=saved[name], **k):
+            t0 = time.perf_counter()
+            try:
+                return _f(self, *a, **k)
+            finally:
+                knn_s[0] += time.perf_counter() - t0
+        setattr(K.OracleGrid, name, timed)
 
     def full_step(n, seed, with_tv=True):
         uv, rng, gt = scenes.pixel_batch(n, seed, RES), scenes.rng_inputs(n, seed), scenes.synthetic_gt(n, seed)
+        knn_s[0] = 0.0
         t0 = time.perf_counter()
         out = H.render_forward(P, grid, uv, cam["pose"], cam["intrinsics"], H.SamplerCfg(), True, 1, rng, with_tv=with_tv)
         lo = H.volsdf_loss(out, gt["rgb"], gt["mask"][0, :, 0])
@@ -529,35 +546,52 @@ def cpu_baseline(sample_rays=1024, repeats=3, threads=None, budget_s=None):
         dt = time.perf_counter() - t0
         for t in P.trainable():
             t.grad = None
-        return dt
+        return dt, knn_s[0]
 
-    t_start = time.perf_counter()
-    full_step(16, 5, False)  # warm-up (thread pools, allocator); not timed
-    times = []
-    for r in range(max(1, repeats)):
-        times.append(full_step(sample_rays, 77 + r))
-        if budget_s is not None and time.perf_counter() - t_start > budget_s:
-            break
-    H.KNN_BACKEND = "grid"
-    t_step = statistics.median(times)
-    return {"value": sample_rays / t_step, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": "BASELINE configs[0], unscaled: pure-torch oracle port, brute-force cdist+topk kNN (test_queries.py:22-74), "
-                      "%d rays x 98 samples on %d neural points, fwd+bwd of the full loss incl. the per-step tv_regul self-kNN; "
-                      "median of %d timed steps (%s s) after one small warm-up step"
-                      % (sample_rays, N_POINTS, len(times), ", ".join("%.2f" % t for t in times)),
-            "seconds_per_step": t_step, "steps_timed": len(times), "rays_per_step": sample_rays}
+    try:
+        H.KNN_BACKEND = "grid"
+        t_start = time.perf_counter()
+        full_step(16, 5, False)  # warm-up (thread pools, allocator); not timed
+        times = []
+        for r in range(max(1, repeats)):
+            times.append(full_step(sample_rays, 77 + r))
+            if budget_s is not None and time.perf_counter() - t_start > budget_s:
+                break
+        brute = None
+        if also_brute:
+            H.KNN_BACKEND = "cdist"
+            bt, bk = full_step(sample_rays, 77)
+            brute = {"seconds_per_step": bt, "rays_per_s": sample_rays / bt, "knn_share": bk / bt, "steps_timed": 1,
+                     "what": "same step with the brute-force cdist+topk kNN of test_queries.py:22-74 (BASELINE.md section 2's "
+                             "plan; the baseline of the bench lines up to profiles/r04*)"}
+    finally:
+        H.KNN_BACKEND = "grid"
+        for name, f in saved.items():
+            setattr(K.OracleGrid, name, f)
+    t_step = statistics.median(t for t, _ in times)
+    cb = {"value": sample_rays / t_step, "unit": "rays/s", "cores": threads, "kind": "port",
+          "sample": "BASELINE configs[0], unscaled: oracle port (pure-torch graph on %d threads; kNN = C restatement of the "
+                    "reference's voxel-grid kernels, knnquery.cu:22-308, 1 thread), %d rays x 98 samples on %d neural points, "
+                    "fwd+bwd of the full loss incl. the per-step tv_regul self-kNN; median of %d timed steps (%s s) after one "
+                    "small warm-up step" % (threads, sample_rays, N_POINTS, len(times), ", ".join("%.2f" % t for t, _ in times)),
+          "seconds_per_step": t_step, "steps_timed": len(times), "rays_per_step": sample_rays, "knn": "grid",
+          "knn_share": statistics.median(k / t for t, k in times)}
+    if brute is not None:
+        cb["brute_force_knn"] = brute
+    return cb
 
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU path on the host cores.  The reference itself has no CPU implementation
      and its CUDA path is timed on the SAME GPU by the GPU arm (`reference_gpu` in our line): this arm is the
-    oracle PORT (`kind: "port"`), a stated baseline, not a like-for-like comparison."""
+    oracle PORT (`kind: "port"`, the faster of its two kNN back ends: see cpu_baseline), a stated baseline, not a
+    like-for-like comparison."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rays = args.cpu_rays
     t0 = time.perf_counter()
-    cb = cpu_baseline(sample_rays=rays, repeats=max(1, args.steps), budget_s=args.cpu_budget)
+    cb = cpu_baseline(sample_rays=rays, repeats=max(1, args.steps), budget_s=args.cpu_budget, also_brute=True)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "rays/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps_timed"], "steps_requested": args.steps,
             "warmup": 1, "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
