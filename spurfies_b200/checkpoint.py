@@ -60,17 +60,32 @@ def load_prior(model: torch.nn.Module, prior, freeze: bool = True) -> Dict[str, 
     return sd
 
 
+def reference_optimizer_layout(opt_sd: Dict) -> Dict:
+    """The reference builds its Adam with TWO parameter groups (train.py:168-189): an empty one (``sdf_feat``, lr 1e-2)
+    and the trainable tensors; ``torch.optim.Adam.load_state_dict`` insists on the same number and sizes of groups.  A
+    single-group state dict (``FusedAdam.state_dict()``) gets the empty group prepended; anything else is returned as is."""
+    groups = opt_sd["param_groups"]
+    if len(groups) != 1:
+        return opt_sd
+    empty = dict(groups[0])
+    empty["params"], empty["lr"] = [], 1e-2
+    return {"state": opt_sd["state"], "param_groups": [empty, groups[0]]}
+
+
 def save_checkpoints(checkpoints_path: str, epoch: int, model: torch.nn.Module, optimizer, iter_step: int,
-                     latest_only: bool = False) -> None:
+                     latest_only: bool = False, reference_layout: bool = True) -> None:
     """train.py:292-328: ``latest.pth`` always, ``<epoch>.pth`` unless ``latest_only``.  ``optimizer`` is anything with
-    a ``state_dict()`` (``FusedAdam``, or ``TrainStep.opt``)."""
+    a ``state_dict()`` (``FusedAdam``, or ``TrainStep.opt``); with ``reference_layout`` its file carries the reference's
+    two parameter groups, so the reference's own ``load_from_dir`` accepts it (``FusedAdam.load_state_dict`` reads either
+    layout)."""
     names = ["latest"] if latest_only else ["latest", str(epoch)]
     for sub in (MODEL_SUBDIR, OPTIM_SUBDIR):
         os.makedirs(os.path.join(checkpoints_path, sub), exist_ok=True)
     for n in names:
         torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "iter_step": int(iter_step)},
                    os.path.join(checkpoints_path, MODEL_SUBDIR, n + ".pth"))
-        torch.save({"epoch": epoch, "optimizer_state_dict": optimizer.state_dict()},
+        osd = optimizer.state_dict()
+        torch.save({"epoch": epoch, "optimizer_state_dict": reference_optimizer_layout(osd) if reference_layout else osd},
                    os.path.join(checkpoints_path, OPTIM_SUBDIR, n + ".pth"))
 
 

@@ -60,7 +60,7 @@ def test_checkpoint_directory_roundtrip(tmp_path):
     sum((p ** 2).sum() for p in a.parameters()).backward()
     opt.step()
     d = str(tmp_path / "checkpoints")
-    ck.save_checkpoints(d, 3, a, opt, iter_step=42)
+    ck.save_checkpoints(d, 3, a, opt, iter_step=42, reference_layout=False)
     assert sorted(os.listdir(os.path.join(d, ck.MODEL_SUBDIR))) == ["3.pth", "latest.pth"]
     assert sorted(os.listdir(os.path.join(d, ck.OPTIM_SUBDIR))) == ["3.pth", "latest.pth"]
     raw = torch.load(os.path.join(d, ck.MODEL_SUBDIR, "3.pth"), weights_only=False)
@@ -118,3 +118,33 @@ def test_local_prior_mapping_and_freeze(tmp_path):
     bad["model.field.local_sdf_field.0.weight"] = torch.zeros(256, 36)
     with pytest.raises(ValueError):
         ck.load_prior(_model(200), bad)
+
+
+def test_optimizer_file_loads_into_the_references_two_group_adam(tmp_path):
+    """train.py:168-189 builds Adam([{"params": [] (sdf_feat), "lr": 1e-2}, {"params": trainable, "lr": lr}]); torch
+    refuses a state dict with another group structure.  FusedAdam.state_dict() has ONE group: save_checkpoints writes
+    the reference's layout around it."""
+    m = _model(100)
+    ck.load_prior(m, _fake_prior())
+    params = [p for p in m.parameters() if p.requires_grad]
+    n = len(params)
+    g = torch.Generator().manual_seed(1)
+    fused_like = {"state": {i: {"step": torch.tensor(5.0), "exp_avg": torch.randn(p.shape, generator=g),
+                                "exp_avg_sq": torch.rand(p.shape, generator=g)} for i, p in enumerate(params)},
+                  "param_groups": [{"lr": 4e-4, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                                    "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                                    "fused": None, "params": list(range(n))}]}          # optim.py::FusedAdam.state_dict
+
+    class Opt:
+        def state_dict(self):
+            return fused_like
+    d = str(tmp_path / "checkpoints")
+    ck.save_checkpoints(d, 1, m, Opt(), iter_step=5, latest_only=True)
+    ref_opt = torch.optim.Adam([{"params": [], "lr": 1e-2}, {"params": params, "lr": 5e-4}])
+    with pytest.raises(ValueError):
+        ref_opt.load_state_dict(fused_like)
+    ref_opt.load_state_dict(torch.load(os.path.join(d, ck.OPTIM_SUBDIR, "latest.pth"), weights_only=False)["optimizer_state_dict"])
+    sd = ref_opt.state_dict()
+    assert [len(gr["params"]) for gr in sd["param_groups"]] == [0, n] and sd["param_groups"][1]["lr"] == 4e-4
+    assert all(torch.equal(sd["state"][i]["exp_avg"], fused_like["state"][i]["exp_avg"]) for i in range(n))
+    assert ck.reference_optimizer_layout(sd) is sd          # already two groups: untouched
