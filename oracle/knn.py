@@ -21,7 +21,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 import torch

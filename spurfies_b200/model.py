@@ -16,7 +16,6 @@ the oracle; the constructor takes the neural points as tensors (reading the .ply
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional
 
 import torch

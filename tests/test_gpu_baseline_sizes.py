@@ -17,7 +17,6 @@ import pytest
 import torch
 
 from oracle import hotpath as H
-from oracle import mesh as OM
 from tests.helpers import load_into_model, rel_err, trainable
 
 pytestmark = pytest.mark.gpu

@@ -89,3 +89,38 @@ def test_exact_ties_are_broken_by_point_id():
     assert g.query_dense(q, 3, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2]
     assert g.query_dense(q, 7, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2, 3, 4, 5, 6]
     assert g.query_dense(q, 8, 2.0, 1)["pidx"][0, 0].tolist() == [0, 1, 2, 3, 4, 5, 6, 7]
+
+
+def test_randomised_scenes_grid_equals_brute_force_and_slot_rule():
+    """Property check over clustered random clouds, ray bundles and (K, Smax, D): every slot is one of the first Smax
+    mask-hit samples of its ray, in order (knnquery.py:208-231); its neighbour list is the brute-force (d^2, id) top-K
+    of that sample; rays without a hit are all -1; points outside `ranges` never appear (knnquery.cu:49)."""
+    for seed, n, k, smax, d, rays in ((0, 3000, 8, 6, 24, 40), (1, 500, 1, 3, 16, 30), (2, 8000, 20, 24, 48, 25),
+                                      (3, 50, 3, 80, 12, 20), (4, 4000, 8, 1, 1, 200)):
+        gen = torch.Generator().manual_seed(seed)
+        centres = (torch.rand(6, 3, generator=gen) - 0.5) * 1.4
+        pts = centres[torch.randint(6, (n,), generator=gen)] + 0.06 * torch.randn(n, 3, generator=gen)
+        pts[: n // 50] = (torch.rand(n // 50, 3, generator=gen) - 0.5) * 3.0          # some points outside the ranges
+        ranges = (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
+        g = OracleGrid(pts[None], (0.025,) * 3, (3,) * 3, (3,) * 3, ranges)
+        o = (torch.rand(rays, 1, 3, generator=gen) - 0.5) * 2.4
+        tgt = centres[torch.randint(6, (rays,), generator=gen)][:, None] + 0.05 * torch.randn(rays, 1, 3, generator=gen)
+        t = torch.linspace(0.0, 1.6, d)[None, :, None]
+        raypos = (o + (tgt - o) * t).contiguous() if d > 1 else tgt.contiguous()
+        out = g.query_dense(raypos, k, 2.0, smax)
+        m = g.mask(raypos).bool()
+        inside = ((pts > -1.0) & (pts < 1.0)).all(-1)
+        for r in range(rays):
+            hits = torch.nonzero(m[r]).flatten()[:smax]
+            ss = out["slot_sample"][r]
+            assert torch.equal(ss[:len(hits)].long(), hits) and bool((ss[len(hits):] < 0).all()), (seed, r)
+            assert bool((out["pidx"][r, len(hits):] < 0).all())
+            if len(hits):
+                want = g.brute(raypos[r, hits], k, 2.0)
+                assert torch.equal(out["pidx"][r, :len(hits)], want), (seed, r)
+                assert torch.equal(out["sample_loc"][r, :len(hits)], raypos[r, hits])
+        used = out["pidx"][out["pidx"] >= 0].long()
+        assert bool(inside[used].all()), seed
+        assert torch.equal(out["ray_mask1"].bool(), m.any(-1))
+        assert torch.equal(out["ray_mask2"].bool(), (out["pidx"] >= 0).any(-1).any(-1))
+        assert int((out["pidx"] >= 0).sum()) > 0 or n < 100
