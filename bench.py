@@ -331,7 +331,7 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001 - a baseline that cannot run is reported, never fatal
             line["reference_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if args.cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=3, budget_s=40.0)
+        line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, repeats=3, budget_s=40.0, also_brute=True)
     print(json.dumps(line))
     shutdown()
 
