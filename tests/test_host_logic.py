@@ -105,3 +105,29 @@ def test_block_cyclic_shares_partition_the_index_space():
             assert torch.equal(px, gi)
         allv = torch.cat(seen).sort().values
         assert torch.equal(allv, torch.arange(G))
+
+
+def test_pack_sw128_is_the_documented_shared_memory_image():
+    """packing.py header: k-blocks of 64 columns; inside a k-block one 128-byte row per n; the eight 16-byte chunks of a
+    row XOR-swizzled by (n & 7).  Checked element by element against that formula (16-bit elements), for padded N and a
+    ragged K, fp16 and bf16."""
+    import numpy as np
+    from spurfies_b200.packing import image_bytes, pack_sw128
+    g = torch.Generator().manual_seed(0)
+    for N, K, n_pad, dt in ((24, 100, 32, torch.float16), (256, 256, None, torch.bfloat16), (3, 64, 8, torch.float16)):
+        W = torch.randn(N, K, generator=g)
+        img = pack_sw128(W, n_pad=n_pad, dtype=dt)
+        npad = n_pad or N
+        assert img.dtype == torch.uint8 and img.numel() == image_bytes(npad, K)
+        words = img.view(torch.int16).numpy()
+        ref = torch.zeros(npad, (K + 63) // 64 * 64)
+        ref[:N, :K] = W
+        ref16 = ref.to(dt).view(torch.int16).numpy()
+        n, k = np.meshgrid(np.arange(npad), np.arange(ref.shape[1]), indexing="ij")
+        kb, kk = k // 64, k % 64
+        chunk, within = kk // 8, kk % 8
+        byte = (kb * npad + n) * 128 + ((chunk ^ (n & 7)) * 16) + within * 2
+        assert np.array_equal(words[byte // 2], ref16)
+    # values beyond fp16 range saturate instead of becoming inf (an inf weight would poison every accumulator it meets)
+    big = pack_sw128(torch.tensor([[1.0e6, -1.0e6] + [0.0] * 6] * 8), dtype=torch.float16).view(torch.float16)
+    assert torch.isfinite(big).all() and float(big.abs().max()) == 65504.0
