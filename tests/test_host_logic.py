@@ -1,6 +1,7 @@
 """CPU: host-side logic around the kernels that needs no device (schedules, flat-buffer layout, mesh grids)."""
 import math
 
+import pytest
 import torch
 
 
@@ -131,3 +132,67 @@ def test_pack_sw128_is_the_documented_shared_memory_image():
     # values beyond fp16 range saturate instead of becoming inf (an inf weight would poison every accumulator it meets)
     big = pack_sw128(torch.tensor([[1.0e6, -1.0e6] + [0.0] * 6] * 8), dtype=torch.float16).view(torch.float16)
     assert torch.isfinite(big).all() and float(big.abs().max()) == 65504.0
+
+
+def _chunk_outputs(total, n_pixels, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    full = {"rgb_values": torch.randn(total, 3, generator=g), "depth_values": torch.randn(total, generator=g),
+            "xyz": torch.randn(total, 5, 3, generator=g), "local_loss": None}
+    res = [{k: (None if v is None else v[a:a + n_pixels]) for k, v in full.items()} for a in range(0, total, n_pixels)]
+    return full, res
+
+
+def test_split_input_and_merge_output_are_inverse():
+    """general.py:24-60 semantics: consecutive pixel chunks (ragged tail), per-pixel keys sliced, the rest shared; merged
+    outputs are the concatenation for 1-, 2- and 3-dimensional entries, None entries dropped, anything else refused."""
+    from spurfies_b200.eval import merge_output, split_input
+    total, n = 1000, 384
+    inp = {"uv": torch.arange(total * 2, dtype=torch.float32).reshape(1, total, 2), "pose": torch.eye(4)[None],
+           "intrinsics": torch.eye(4)[None], "rgb": torch.rand(1, total, 3), "object_mask": torch.ones(1, total, dtype=torch.bool)}
+    parts = split_input(inp, total, n)
+    assert [p["uv"].shape[1] for p in parts] == [384, 384, 232]
+    assert torch.equal(torch.cat([p["uv"] for p in parts], 1), inp["uv"])
+    assert torch.equal(torch.cat([p["rgb"] for p in parts], 1), inp["rgb"]) and all(p["pose"] is inp["pose"] for p in parts)
+    assert torch.equal(torch.cat([p["object_mask"] for p in parts], 1), inp["object_mask"])
+    sub = split_input(inp, total, n, lo=100, hi=600)                         # a rank's share of the pixels
+    assert torch.equal(torch.cat([p["uv"] for p in sub], 1), inp["uv"][:, 100:600])
+    full, res = _chunk_outputs(total, n)
+    out = merge_output(res, total, 1)
+    assert set(out) == {"rgb_values", "depth_values", "xyz"}
+    for k in out:
+        assert torch.equal(out[k], full[k]), k
+    with pytest.raises(NotImplementedError):
+        merge_output([{"bad": torch.zeros(2, 2, 2, 2)}], 2, 1)
+
+
+def test_merge_output_equals_the_reference_function_when_the_reference_is_present():
+    import importlib.util
+    import os
+    path = "/root/reference/spurfies/utils/general.py"
+    if not os.path.exists(path):
+        pytest.skip("authoring container only (/root/reference)")
+    from spurfies_b200.eval import merge_output
+    spec = importlib.util.spec_from_file_location("ref_general", path)
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    full, res = _chunk_outputs(777, 100, seed=1)
+    ours, ref = merge_output(res, 777, 1), G.merge_output(res, 777, 1)
+    assert set(ours) == set(ref) and all(torch.equal(ours[k], ref[k]) for k in ref)
+
+
+def test_graph_input_trees_refuse_a_changed_structure():
+    """train.py: a captured graph reads static input buffers; an entry that cannot be copied into them is an error."""
+    from spurfies_b200.train import _clone_tree, _copy_tree, _like_tree
+    src = {"uv": torch.rand(1, 8, 2), "local_data": {"feat": torch.rand(4, 3, 3), "size": 3.0}, "none": None}
+    st = _clone_tree(src)
+    assert st["uv"] is not src["uv"] and torch.equal(st["local_data"]["feat"], src["local_data"]["feat"]) and st["none"] is None
+    assert _like_tree(src)["local_data"]["feat"].shape == (4, 3, 3)
+    new = {"uv": torch.rand(1, 8, 2), "local_data": {"feat": torch.rand(4, 3, 3), "size": 3.0}, "none": None}
+    _copy_tree(st, new)
+    assert torch.equal(st["uv"], new["uv"]) and torch.equal(st["local_data"]["feat"], new["local_data"]["feat"])
+    with pytest.raises(ValueError, match="does not match"):
+        _copy_tree(st, {"uv": torch.rand(1, 9, 2)})
+    with pytest.raises(ValueError, match="was not a dict"):
+        _copy_tree({"uv": st["uv"], "local_data": None}, new)
+    with pytest.raises(ValueError, match="is None"):
+        _copy_tree(st, {"local_data": None})
