@@ -199,7 +199,21 @@ def profile_collect():
     return out
 
 
+# SPF_NVTX=1: an NVTX range per C-ABI call, named after the entry point (ncu --nvtx --nvtx-include "spf_sdf_fwd_tc/" ...)
+_NVTX = os.environ.get("SPF_NVTX") == "1"
+
+
 def call(name, *args):
+    if not _NVTX:
+        return _call(name, *args)
+    torch.cuda.nvtx.range_push(name)
+    try:
+        return _call(name, *args)
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
+def _call(name, *args):
     if _PROFILE["on"]:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
